@@ -1,0 +1,162 @@
+/* molar_b200.h — C ABI of libmolar_b200.so, the B200-native drop-in for MolAR's data-parallel
+ * hot path (distance search, Kabsch fit / RMSD, centre-of-mass / gyration reductions).
+ *
+ * The boundary follows the only native-plugin precedent in the reference, molar_gromacs
+ * (/root/reference/molar_gromacs/gromacs/wrapper.hpp:42-81): opaque handles, NULL / negative
+ * return + a thread-local last-error string, exceptions never cross the ABI, count-then-fill
+ * into caller-allocated arrays, plain pointers and sizes only.
+ *
+ * What each entry point replaces (paths relative to /root/reference/molar/src/):
+ *   mb_set_frame          State.coords : Vec<Pos> + State.pbox            state.rs:21-28
+ *   mb_set_masses         AtomStorage::masses()                           atom_storage.rs:272
+ *   mb_search_single      distance_search_single[_pbc]                    distance_search.rs:892-954
+ *   mb_search_double      distance_search_double[_pbc]                    distance_search.rs:659-754
+ *   mb_search_within      distance_search_within[_pbc]                    distance_search.rs:519-598
+ *   mb_center_of_mass     Measure::center_of_mass                         measure.rs:60-75
+ *   mb_gyration           Measure::gyration                               measure.rs:78-87,561-570
+ *   mb_rmsd               rmsd / rmsd_mw                                  measure.rs:485-504,538-558
+ *   mb_fit_transform      fit_transform / fit_transform_at_origin         measure.rs:507-535,613-643
+ *   mb_apply_transform    Modify::apply_transform                         modify.rs:32-36
+ *   mb_batch_*            the per-frame loop AnalysisTask::run drives     analysis_task.rs:113-280
+ *
+ * Data conventions (identical to the Rust side, so a binding passes its buffers as they are):
+ *   coordinates  Vec<Pos> = N x 3 f32, AoS, 12-byte stride                aliases.rs:23
+ *   box          nalgebra Matrix3<f32> storage = COLUMN-major 9 floats; columns are the box
+ *                vectors a,b,c (periodic_box.rs:9-13).  NULL = no box.
+ *   selections   sorted global atom indices as usize = uint64_t (providers.rs:45-48);
+ *                ids == NULL means the identity selection 0..n.
+ *   pbc_dims     PbcDims bit mask, bit d = dimension d periodic (periodic_box.rs:70-128);
+ *                0 selects the non-periodic variant of a search.
+ *
+ * Threading: a context is Send, not Sync (one context per calling thread, like TprHandle,
+ * io/tpr_handler.rs:18).  There is no global mutable state except the thread-local error.
+ * There is NO CPU fallback: without a CUDA device mb_open fails.
+ */
+#ifndef MOLAR_B200_H
+#define MOLAR_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct MbCtx MbCtx;
+
+/* return codes; they map onto MeasureError (measure.rs:732-762) */
+enum {
+    MB_OK = 0,
+    MB_ERR_ZERO_MASS = -1,  /* MeasureError::ZeroMass */
+    MB_ERR_SIZES = -2,      /* MeasureError::Sizes */
+    MB_ERR_SVD = -3,        /* MeasureError::Svd */
+    MB_ERR_NO_PBC = -4,     /* MeasureError::Pbc(PeriodicBoxError::NoPbc) */
+    MB_ERR_BOX = -5,        /* PeriodicBoxError::{ZeroLengthVector,InverseFailed} */
+    MB_ERR_ARG = -6,        /* bad argument / no frame / index out of range */
+    MB_ERR_CUDA = -7,       /* CUDA runtime error (message in mb_last_error) */
+    MB_ERR_STATE = -8       /* call sequence error (e.g. fill before search) */
+};
+
+/* Message of the last failed call on this thread; valid until the next call on this thread. */
+const char* mb_last_error(void);
+/* ABI version of this header */
+int mb_abi_version(void);
+
+/* ---- context ---------------------------------------------------------------------------- */
+MbCtx* mb_open(int device);            /* NULL on error */
+void   mb_close(MbCtx* ctx);
+/* cudaStream_t the context launches on (as void*), so a host can time it with its own events */
+void*  mb_stream(MbCtx* ctx);
+int    mb_synchronize(MbCtx* ctx);
+/* tuning knob: subdivision of the reference grid used for traversal (0 = automatic) */
+int    mb_set_option(MbCtx* ctx, const char* key, double value);
+
+/* ---- frame ------------------------------------------------------------------------------- */
+/* Copies the frame to the device (pinned staging + async H2D on the context stream). */
+int mb_set_frame(MbCtx* ctx, const float* xyz, size_t n_atoms, const float* box9_colmajor);
+/* Adopts a DEVICE pointer without copying (xyz_dev must stay valid until replaced). */
+int mb_set_frame_device(MbCtx* ctx, const float* xyz_dev, size_t n_atoms, const float* box9_colmajor);
+/* Copies the (possibly transformed) current frame back to the host. */
+int mb_get_frame(MbCtx* ctx, float* xyz_out, size_t n_atoms);
+/* Whole-system mass column. */
+int mb_set_masses(MbCtx* ctx, const float* masses, size_t n_atoms);
+/* A second coordinate set (e.g. the reference structure for rmsd / fit); same layout. */
+int mb_set_frame2(MbCtx* ctx, const float* xyz, size_t n_atoms);
+
+/* ---- distance search ----------------------------------------------------------------------
+ * Each call runs the search on the device and returns the number of results (>= 0) or a
+ * negative error code; results stay on the device until the next search on this context and
+ * are fetched with mb_fill_*.  Results are the reference's result SET: duplicates the reference
+ * would emit for degenerate grids are removed; `single` pairs are canonical (i < j); `double`
+ * pairs are (i from set 1, j from set 2); `within` ids are sorted and unique. */
+int64_t mb_search_single(MbCtx* ctx, float cutoff, const uint64_t* ids, size_t n, uint8_t pbc_dims);
+/* set 2 positions are taken from frame2 when use_frame2 != 0, else from the current frame */
+int64_t mb_search_double(MbCtx* ctx, float cutoff, const uint64_t* ids1, size_t n1,
+                         const uint64_t* ids2, size_t n2, int use_frame2, uint8_t pbc_dims);
+/* lower3/upper3: grid bounds of the non-periodic variant, as the caller of
+   distance_search_within passes them (selection/ast.rs:598-610); ignored when pbc_dims != 0;
+   NULL => bounds of set 1 padded by cutoff + EPSILON (what the `within` AST node does). */
+int64_t mb_search_within(MbCtx* ctx, float cutoff, const uint64_t* ids1, size_t n1,
+                         const uint64_t* ids2, size_t n2, int use_frame2, uint8_t pbc_dims,
+                         const float* lower3, const float* upper3);
+/* Count only (no pair list is materialised): the contact count of config 5. */
+int64_t mb_count_single(MbCtx* ctx, float cutoff, const uint64_t* ids, size_t n, uint8_t pbc_dims);
+/* ij: 2*P entries (usize pairs) ; dist: P entries or NULL */
+int mb_fill_pairs(MbCtx* ctx, uint64_t* ij, float* dist);
+int mb_fill_ids(MbCtx* ctx, uint64_t* ids);
+/* Device-side view of the last pair list: packed (uint32 i, uint32 j), P entries. */
+const void* mb_pairs_device(MbCtx* ctx, int64_t* n_pairs);
+/* Order-independent checksum of the last pair list computed on the device:
+   out[0] = sum over pairs of mix64(i<<32|j) (wrapping), out[1] = xor of the same. */
+int mb_pairs_checksum(MbCtx* ctx, uint64_t out2[2]);
+/* Reference grid dimensions used by the last search (Grid::dims). */
+int mb_last_grid_dims(MbCtx* ctx, uint64_t dims3[3]);
+
+/* ---- reductions / Kabsch (outputs f64 regardless of input width) ------------------------ */
+int mb_center_of_mass(MbCtx* ctx, const uint64_t* ids, size_t n, double out3[3]);
+int mb_gyration(MbCtx* ctx, const uint64_t* ids, size_t n, double* out);
+/* sel1 on the current frame, sel2 on frame2 (use_frame2 != 0) or on the current frame */
+int mb_rmsd(MbCtx* ctx, const uint64_t* ids1, size_t n1, const uint64_t* ids2, size_t n2,
+            int use_frame2, int mass_weighted, double* out);
+/* fits sel1 (current frame) ONTO sel2; R9 column-major, p' = R p + t */
+int mb_fit_transform(MbCtx* ctx, const uint64_t* ids1, size_t n1, const uint64_t* ids2, size_t n2,
+                     int use_frame2, int at_origin, double R9_colmajor[9], double t3[3]);
+/* in place on the current frame (device copy; fetch with mb_get_frame) */
+int mb_apply_transform(MbCtx* ctx, const uint64_t* ids, size_t n, const double R9_colmajor[9],
+                       const double t3[3]);
+
+/* ---- batched, device-resident trajectory (what the benchmark drives) -------------------- */
+/* Allocate n_frames x n_atoms x 3 f32 on the device and fill it with the synthetic generator
+   of SURVEY.md §8(d) (same bits as the oracle's orc_synth_frame): frame f of this context is
+   global frame first_frame + f. */
+int mb_batch_synth(MbCtx* ctx, uint64_t seed, uint64_t first_frame, size_t n_frames, size_t n_atoms,
+                   const float* box9_colmajor, int stray_permille);
+/* Upload host frames instead (n_frames x n_atoms x 3). */
+int mb_batch_upload(MbCtx* ctx, const float* xyz, size_t n_frames, size_t n_atoms,
+                    const float* box9_colmajor);
+int mb_batch_synth_masses(MbCtx* ctx, uint64_t seed, size_t n_atoms);
+/* Make batch frame f the current frame (no copy). */
+int mb_batch_select(MbCtx* ctx, size_t frame);
+/* Neighbour search on every frame [f0, f1): per-frame pair count and checksum written to
+   host arrays (may be NULL); pair lists stay on the device and are overwritten frame by frame.
+   mode 0 = enumerate pairs, 1 = count only. */
+int mb_batch_search(MbCtx* ctx, float cutoff, uint8_t pbc_dims, size_t f0, size_t f1, int mode,
+                    int64_t* counts, uint64_t* checksums2);
+/* Kabsch fit of every frame [f0,f1) onto frame `ref_frame`, superposition in place and
+   unweighted RMSD after the fit (config 4).  rmsd_out: f1-f0 doubles (host, may be NULL). */
+int mb_batch_fit(MbCtx* ctx, size_t ref_frame, size_t f0, size_t f1, int superpose, double* rmsd_out);
+/* Per-frame COM + gyration + contact count (config 5): out is (f1-f0) x 5 doubles
+   {com_x, com_y, com_z, rg, count}.  The same rows are left in device memory at
+   mb_batch_scalars_device() for an NCCL gather by the host. */
+int mb_batch_pipeline(MbCtx* ctx, float cutoff, uint8_t pbc_dims, size_t f0, size_t f1, double* out);
+const void* mb_batch_scalars_device(MbCtx* ctx, size_t* n_rows, size_t* row_doubles);
+/* number of kernels this context has launched since it was opened (for gpu_launches) */
+uint64_t mb_launch_count(MbCtx* ctx);
+/* Instrumentation.  With option "profile"=1 every pair-search kernel launch is bracketed by CUDA
+   events on the context stream; "search_kernel_ms" / "search_kernel_launches" return the totals
+   since the option was last set.  Other keys: "pair_capacity", "sm_count". */
+int mb_get_stat(MbCtx* ctx, const char* key, double* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MOLAR_B200_H */

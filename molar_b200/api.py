@@ -1,0 +1,346 @@
+"""Host-side mirror of the reference's Python interface for the hot path.
+
+Same names, argument meaning and error behaviour as pymolar
+(molar_python/src/lib.rs:137-376; Sel.com/gyration/apply_transform: molar_python/src/selection.rs:816-941):
+
+    pairs, dist = distance_search(cutoff, sel1, sel2=None, dims=None)
+    r = rmsd(sel1, sel2); rw = rmsd_mw(sel1, sel2)
+    tr = fit_transform(sel1, sel2); sel1.apply_transform(tr)
+    sel.com(); sel.gyration()
+
+A `System` owns one device context (one per calling thread: Send, not Sync) holding the frame,
+the mass column and the box; a `Sel` is a sorted array of global indices into it, exactly like
+MolAR's Sel (providers.rs:45-48).  Everything is computed by libmolar_b200.so on the GPU.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _capi
+from ._capi import MolarB200Error, check, f32p, f64p, u64p, i64p
+
+
+def _pbc_bits(dims):
+    if dims is None:
+        return 0
+    if isinstance(dims, (int, np.integer)):
+        return int(dims) & 7
+    return (1 if dims[0] else 0) | (2 if dims[1] else 0) | (4 if dims[2] else 0)
+
+
+class PeriodicBox:
+    """matrix: 3x3, COLUMNS are the box vectors a,b,c (periodic_box.rs:9-13)."""
+
+    def __init__(self, matrix):
+        self.matrix = np.asarray(matrix, dtype=np.float32).reshape(3, 3)
+
+    @property
+    def colmajor9(self):
+        return np.ascontiguousarray(self.matrix.T.reshape(9))
+
+    def get_matrix(self):
+        return self.matrix.copy()
+
+
+class IsometryTransform:
+    """p' = R p + t (nalgebra IsometryMatrix3, what fit_transform returns)."""
+
+    def __init__(self, R, t):
+        self.R = np.asarray(R, dtype=np.float64).reshape(3, 3)
+        self.t = np.asarray(t, dtype=np.float64).reshape(3)
+
+
+class System:
+    def __init__(self, coords, masses=None, box=None, device=0):
+        self._lib = _capi.load()
+        self._h = self._lib.mb_open(device)
+        if not self._h:
+            raise MolarB200Error(_capi.MB_ERR_CUDA, _capi.last_error())
+        self._n = 0
+        self.box = None
+        self.set_state(coords, box)
+        if masses is not None:
+            self.set_masses(masses)
+
+    # -- lifetime --
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.mb_close(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __len__(self):
+        return self._n
+
+    # -- state (System::set_state, selection/system.rs:230-236) --
+    def set_state(self, coords, box=None):
+        xyz = np.ascontiguousarray(coords, dtype=np.float32).reshape(-1, 3)
+        if box is not None and not isinstance(box, PeriodicBox):
+            box = PeriodicBox(box)
+        self.box = box
+        b9 = box.colmajor9.ctypes.data_as(f32p) if box is not None else None
+        check(self._lib.mb_set_frame(self._h, xyz.ctypes.data, xyz.shape[0], b9))
+        self._n = xyz.shape[0]
+
+    def set_masses(self, masses):
+        m = np.ascontiguousarray(masses, dtype=np.float32).reshape(-1)
+        if m.shape[0] != self._n:
+            raise ValueError(f"masses: {m.shape[0]} != {self._n} atoms")
+        check(self._lib.mb_set_masses(self._h, m.ctypes.data, m.shape[0]))
+
+    def set_option(self, key, value):
+        check(self._lib.mb_set_option(self._h, key.encode(), float(value)))
+
+    def coords(self):
+        out = np.empty((self._n, 3), np.float32)
+        check(self._lib.mb_get_frame(self._h, out.ctypes.data, self._n))
+        return out
+
+    # -- selections (System::__call__) --
+    def __call__(self, arg=None):
+        if arg is None:
+            return Sel(self, None, self._n)
+        if isinstance(arg, tuple) and len(arg) == 2:
+            idx = np.arange(arg[0], arg[1] + 1, dtype=np.uint64)  # inclusive range, like pymolar
+        else:
+            idx = np.unique(np.asarray(arg, dtype=np.uint64))  # Sel indices are a sorted set
+        if idx.size == 0:
+            raise ValueError("empty selection")
+        if int(idx[-1]) >= self._n:
+            raise IndexError(f"index {int(idx[-1])} out of range ({self._n} atoms)")
+        return Sel(self, idx, idx.size)
+
+    def launch_count(self):
+        return int(self._lib.mb_launch_count(self._h))
+
+
+class Sel:
+    def __init__(self, system, index, n):
+        self.sys = system
+        self.index = index  # None = all atoms
+        self._n = int(n)
+
+    def __len__(self):
+        return self._n
+
+    def _ids(self):
+        return (self.index.ctypes.data_as(u64p) if self.index is not None else None), self._n
+
+    def get_index(self):
+        return np.arange(self._n, dtype=np.uint64) if self.index is None else self.index.copy()
+
+    def com(self, dims=None):
+        if _pbc_bits(dims):
+            raise NotImplementedError("periodic centre of mass is outside the accelerated path")
+        out = np.zeros(3, np.float64)
+        p, n = self._ids()
+        check(self.sys._lib.mb_center_of_mass(self.sys._h, p, n, out.ctypes.data_as(f64p)))
+        return out
+
+    def gyration(self):
+        out = C.c_double(0.0)
+        p, n = self._ids()
+        check(self.sys._lib.mb_gyration(self.sys._h, p, n, C.byref(out)))
+        return out.value
+
+    def apply_transform(self, tr):
+        R9 = np.ascontiguousarray(tr.R.T.reshape(9), dtype=np.float64)
+        t3 = np.ascontiguousarray(tr.t, dtype=np.float64)
+        p, n = self._ids()
+        check(self.sys._lib.mb_apply_transform(self.sys._h, p, n, R9.ctypes.data_as(f64p), t3.ctypes.data_as(f64p)))
+
+
+def _same_or_frame2(sel1, sel2):
+    """sel2 may live in another System (the reference structure): stage its frame as frame2."""
+    if sel2.sys is sel1.sys:
+        return 0
+    xyz2 = sel2.sys.coords()
+    check(sel1.sys._lib.mb_set_frame2(sel1.sys._h, xyz2.ctypes.data, xyz2.shape[0]))
+    return 1
+
+
+def distance_search(cutoff, data1, data2=None, dims=None):
+    """pymolar.distance_search (molar_python/src/lib.rs:254-376): (pairs[N,2], distances[N]).
+
+    The pair SET equals the reference's; order is unspecified (the reference's order is rayon's).
+    Single-selection pairs are canonical i<j and de-duplicated."""
+    if isinstance(cutoff, str):
+        raise NotImplementedError("'vdw' cutoff is outside the accelerated path (SURVEY.md §8f)")
+    s = data1.sys
+    pbc = _pbc_bits(dims)
+    if pbc and s.box is None:
+        raise MolarB200Error(_capi.MB_ERR_NO_PBC, "pbc operation without periodic box")
+    p1, n1 = data1._ids()
+    if data2 is None:
+        cnt = check(s._lib.mb_search_single(s._h, cutoff, p1, n1, pbc))
+    else:
+        use2 = _same_or_frame2(data1, data2)
+        p2, n2 = data2._ids()
+        cnt = check(s._lib.mb_search_double(s._h, cutoff, p1, n1, p2, n2, use2, pbc))
+    pairs = np.empty((cnt, 2), np.uint64)
+    dist = np.empty(cnt, np.float32)
+    if cnt:
+        check(s._lib.mb_fill_pairs(s._h, pairs.ctypes.data, dist.ctypes.data))
+    return pairs, dist
+
+
+def within(cutoff, data1, data2, dims=None, lower=None, upper=None):
+    """distance_search_within[_pbc] (distance_search.rs:519-598) as the `within` AST node calls it
+    (selection/ast.rs:589-631): sorted unique ids of data1 atoms within cutoff of any data2 atom."""
+    s = data1.sys
+    pbc = _pbc_bits(dims)
+    use2 = _same_or_frame2(data1, data2)
+    p1, n1 = data1._ids()
+    p2, n2 = data2._ids()
+    lo = np.ascontiguousarray(lower, np.float32).ctypes.data_as(f32p) if lower is not None else None
+    up = np.ascontiguousarray(upper, np.float32).ctypes.data_as(f32p) if upper is not None else None
+    cnt = check(s._lib.mb_search_within(s._h, cutoff, p1, n1, p2, n2, use2, pbc, lo, up))
+    out = np.empty(cnt, np.uint64)
+    if cnt:
+        check(s._lib.mb_fill_ids(s._h, out.ctypes.data))
+    return out
+
+
+def rmsd(sel1, sel2):
+    """measure.rs:485-504; raises on size mismatch like MeasureError::Sizes."""
+    s = sel1.sys
+    use2 = _same_or_frame2(sel1, sel2)
+    p1, n1 = sel1._ids()
+    p2, n2 = sel2._ids()
+    out = C.c_double(0.0)
+    check(s._lib.mb_rmsd(s._h, p1, n1, p2, n2, use2, 0, C.byref(out)))
+    return out.value
+
+
+rmsd_py = rmsd
+
+
+def rmsd_mw(sel1, sel2):
+    s = sel1.sys
+    use2 = _same_or_frame2(sel1, sel2)
+    p1, n1 = sel1._ids()
+    p2, n2 = sel2._ids()
+    out = C.c_double(0.0)
+    check(s._lib.mb_rmsd(s._h, p1, n1, p2, n2, use2, 1, C.byref(out)))
+    return out.value
+
+
+def fit_transform(sel1, sel2, at_origin=False):
+    """Transform that best fits sel1 ONTO sel2 (measure.rs:507-535)."""
+    s = sel1.sys
+    use2 = _same_or_frame2(sel1, sel2)
+    p1, n1 = sel1._ids()
+    p2, n2 = sel2._ids()
+    R9 = np.zeros(9, np.float64)
+    t3 = np.zeros(3, np.float64)
+    check(s._lib.mb_fit_transform(s._h, p1, n1, p2, n2, use2, int(at_origin), R9.ctypes.data_as(f64p),
+                                  t3.ctypes.data_as(f64p)))
+    return IsometryTransform(R9.reshape(3, 3).T.copy(), t3)
+
+
+class Trajectory:
+    """Device-resident block of frames: the GPU analogue of the per-frame loop that
+    AnalysisTask::run drives (analysis_task.rs:113-280)."""
+
+    def __init__(self, device=0):
+        self._lib = _capi.load()
+        self._h = self._lib.mb_open(device)
+        if not self._h:
+            raise MolarB200Error(_capi.MB_ERR_CUDA, _capi.last_error())
+        self.n_frames = 0
+        self.n_atoms = 0
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.mb_close(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_option(self, key, value):
+        check(self._lib.mb_set_option(self._h, key.encode(), float(value)))
+
+    def synth(self, seed, first_frame, n_frames, n_atoms, box, stray_permille=0, mass_seed=None):
+        b = box if isinstance(box, PeriodicBox) else PeriodicBox(box)
+        check(self._lib.mb_batch_synth(self._h, seed, first_frame, n_frames, n_atoms,
+                                       b.colmajor9.ctypes.data_as(f32p), stray_permille))
+        if mass_seed is not None:
+            check(self._lib.mb_batch_synth_masses(self._h, mass_seed, n_atoms))
+        self.n_frames, self.n_atoms = n_frames, n_atoms
+
+    def upload(self, frames, box=None, masses=None):
+        x = np.ascontiguousarray(frames, dtype=np.float32)
+        nf, na = x.shape[0], x.shape[1]
+        b9 = None
+        if box is not None:
+            b = box if isinstance(box, PeriodicBox) else PeriodicBox(box)
+            b9 = b.colmajor9.ctypes.data_as(f32p)
+        check(self._lib.mb_batch_upload(self._h, x.ctypes.data, nf, na, b9))
+        if masses is not None:
+            m = np.ascontiguousarray(masses, dtype=np.float32)
+            check(self._lib.mb_set_masses(self._h, m.ctypes.data, m.shape[0]))
+        self.n_frames, self.n_atoms = nf, na
+
+    def frame(self, f):
+        check(self._lib.mb_batch_select(self._h, f))
+        out = np.empty((self.n_atoms, 3), np.float32)
+        check(self._lib.mb_get_frame(self._h, out.ctypes.data, self.n_atoms))
+        return out
+
+    def search(self, cutoff, dims=(True, True, True), f0=0, f1=None, count_only=False, checksums=False):
+        f1 = self.n_frames if f1 is None else f1
+        counts = np.zeros(f1 - f0, np.int64)
+        chk = np.zeros((f1 - f0, 2), np.uint64) if checksums else None
+        check(self._lib.mb_batch_search(self._h, cutoff, _pbc_bits(dims), f0, f1, 1 if count_only else 0,
+                                        counts.ctypes.data_as(i64p),
+                                        chk.ctypes.data_as(u64p) if checksums else None))
+        return (counts, chk) if checksums else counts
+
+    def last_pairs(self):
+        """Pair list of the last frame searched (host copy)."""
+        n = C.c_int64(0)
+        self._lib.mb_pairs_device(self._h, C.byref(n))
+        pairs = np.empty((n.value, 2), np.uint64)
+        if n.value:
+            check(self._lib.mb_fill_pairs(self._h, pairs.ctypes.data, None))
+        return pairs
+
+    def fit(self, ref_frame=0, f0=0, f1=None, superpose=True):
+        f1 = self.n_frames if f1 is None else f1
+        out = np.zeros(f1 - f0, np.float64)
+        check(self._lib.mb_batch_fit(self._h, ref_frame, f0, f1, int(superpose), out.ctypes.data_as(f64p)))
+        return out
+
+    def pipeline(self, cutoff, dims=(True, True, True), f0=0, f1=None):
+        f1 = self.n_frames if f1 is None else f1
+        out = np.zeros((f1 - f0, 5), np.float64)
+        check(self._lib.mb_batch_pipeline(self._h, cutoff, _pbc_bits(dims), f0, f1, out.ctypes.data_as(f64p)))
+        return out
+
+    def scalars_device(self):
+        rows, rd = C.c_size_t(0), C.c_size_t(0)
+        p = self._lib.mb_batch_scalars_device(self._h, C.byref(rows), C.byref(rd))
+        return p, rows.value, rd.value
+
+    def stream(self):
+        return self._lib.mb_stream(self._h)
+
+    def stat(self, key):
+        out = C.c_double(0.0)
+        check(self._lib.mb_get_stat(self._h, key.encode(), C.byref(out)))
+        return out.value
+
+    def synchronize(self):
+        check(self._lib.mb_synchronize(self._h))
+
+    def launch_count(self):
+        return int(self._lib.mb_launch_count(self._h))

@@ -1,0 +1,50 @@
+"""Build libmolar_b200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIBDIR = os.path.join(HERE, "lib")
+LIB = os.path.join(LIBDIR, "libmolar_b200.so")
+SOURCES = ["mb_api.cu", "mb_search.cu", "mb_measure.cu", "mb_batch.cu"]
+HEADERS = ["mb_common.cuh", "mb_reduce.cuh", os.path.join("..", "..", "include", "molar_b200.h")]
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-lineinfo", "-O3", "-std=c++17",
+    "-Xcompiler", "-fPIC,-ffp-contract=off,-fno-fast-math,-Wall",
+    "-Xptxas", "-v",
+    "--expt-relaxed-constexpr", "--extended-lambda",
+    "-shared",
+]
+
+
+def needs_build():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + [os.path.abspath(__file__)]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    if not force and not needs_build():
+        return LIB
+    os.makedirs(LIBDIR, exist_ok=True)
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    log = os.path.join(LIBDIR, "build.log")
+    with open(log, "w") as f:
+        f.write(" ".join(cmd) + "\n" + r.stdout)
+    if verbose or r.returncode != 0:
+        sys.stderr.write(r.stdout)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed (see %s)" % log)
+    return LIB
+
+
+if __name__ == "__main__":
+    build(force="--force" in sys.argv, verbose=True)
+    print(LIB)

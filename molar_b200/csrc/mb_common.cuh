@@ -1,0 +1,202 @@
+// mb_common.cuh — shared declarations of libmolar_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/molar_b200.h"
+
+namespace mb {
+
+// ---------------------------------------------------------------------------------------------
+// error plumbing: thread-local message, never throw across the ABI
+// (precedent: molar_gromacs/gromacs/wrapper.cpp:32,139-158)
+// ---------------------------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+int fail(int code, const char* fmt, ...);
+
+#define MB_CUDA(call)                                                                         \
+    do {                                                                                      \
+        cudaError_t _e = (call);                                                              \
+        if (_e != cudaSuccess)                                                                \
+            return ::mb::fail(MB_ERR_CUDA, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__, \
+                              cudaGetErrorString(_e));                                        \
+    } while (0)
+
+#define MB_TRY(expr)              \
+    do {                          \
+        int _rc = (expr);         \
+        if (_rc < 0) return _rc;  \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// PeriodicBox on the host, f32, in the reference's evaluation order
+// (molar/src/periodic_box.rs:25-66,156-176,369-375).  Row-major m[r][c]; columns = a,b,c.
+// ---------------------------------------------------------------------------------------------
+struct HostBox {
+    float m[3][3];
+    float inv[3][3];
+    int ncorr;
+    float corr[26][3];
+};
+// returns MB_OK or MB_ERR_BOX
+int host_box_from_colmajor(const float* m9, HostBox* out);
+void host_box_lab_extents(const HostBox& b, float out[3]);
+
+// Box as kernels see it (passed by value inside kernel parameter structs).
+struct DevBox {
+    float m[9];    // row-major
+    float inv[9];  // row-major
+    int ncorr;
+    float corr[26 * 3];
+};
+DevBox to_dev_box(const HostBox& b);
+
+// ---------------------------------------------------------------------------------------------
+// grow-only device buffer
+// ---------------------------------------------------------------------------------------------
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes);  // keeps contents only if no reallocation was needed
+    void release();
+    template <class T>
+    T* as() const { return static_cast<T*>(p); }
+};
+
+// ---------------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------------
+struct SearchResult {
+    int kind = 0;  // 0 none, 1 pairs (single), 2 pairs (double), 3 ids (within), 4 count only
+    int64_t count = 0;
+    bool has_dist = false;
+    uint64_t grid_dims[3] = {0, 0, 0};
+};
+
+struct Ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int sm_count = 148;
+    uint64_t launches = 0;
+
+    // current frame
+    const float* d_xyz = nullptr;  // points into xyz_own, the batch, or adopted memory
+    size_t n_atoms = 0;
+    DevBuf xyz_own;
+    bool has_box = false;
+    HostBox box;
+    // second coordinate set
+    DevBuf xyz2;
+    size_t n_atoms2 = 0;
+    // masses
+    DevBuf masses;
+    size_t n_masses = 0;
+
+    // selections uploaded for the current call
+    DevBuf ids1, ids2;
+    // pinned staging
+    void* h_pinned = nullptr;
+    size_t h_pinned_cap = 0;
+    int pinned_reserve(size_t bytes);
+
+    // search scratch
+    DevBuf tmp4a, tmp4b;    // binned atoms (float4: eff pos + id bits), unsorted
+    DevBuf cellid_a, cellid_b, rank_a;
+    DevBuf refcell_a, refcell_b;  // packed reference cell coords (u64) for the general kernel
+    DevBuf sorted4;         // atoms sorted by fine cell
+    DevBuf cell_count, cell_start, scan_tmp;
+    DevBuf pairs, dists, flags, out_ids;
+    DevBuf counters;        // small block of device counters / results
+    DevBuf reduce_tmp;      // per-block partials
+    SearchResult last;
+    size_t pair_cap = 0;
+
+    // options
+    int opt_subdiv = 0;       // 0 auto, else forced k for all dims
+    int opt_force_brute = 0;  // force the general all-pairs kernel
+    double opt_atoms_per_cell = 12.0;
+    int opt_with_dist = 1;
+    int opt_profile = 0;      // record CUDA events around every search-kernel launch
+    std::vector<cudaEvent_t> prof_events;  // begin/end pairs not yet harvested
+    double prof_search_ms = 0.0;
+    uint64_t prof_search_launches = 0;
+    int harvest_profile();
+
+    // batch (device-resident trajectory)
+    DevBuf batch;
+    size_t batch_frames = 0, batch_atoms = 0;
+    bool batch_has_box = false;
+    DevBuf batch_scalars;  // rows of doubles
+    size_t batch_rows = 0, batch_row_doubles = 0;
+    DevBuf batch_tmp, batch_ref;
+
+    // memoised search plan (owned by mb_search.cu)
+    void* plan_cache = nullptr;
+};
+
+// ---------------------------------------------------------------------------------------------
+// exact-arithmetic device helpers.  Every product and sum on a decision path must round on
+// its own (Rust does not contract to FMA): use the _rn intrinsics, which nvcc never fuses.
+// ---------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ float xmul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float xadd(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float xsub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float xdiv(float a, float b) { return __fdiv_rn(a, b); }
+
+// nalgebra gemv order: ((M_i0*v0) + M_i1*v1) + M_i2*v2   (periodic_box.rs:340-360)
+__device__ __forceinline__ void xmatvec(const float* __restrict__ M, float v0, float v1, float v2,
+                                        float& r0, float& r1, float& r2) {
+    r0 = xadd(xadd(xmul(M[0], v0), xmul(M[1], v1)), xmul(M[2], v2));
+    r1 = xadd(xadd(xmul(M[3], v0), xmul(M[4], v1)), xmul(M[5], v2));
+    r2 = xadd(xadd(xmul(M[6], v0), xmul(M[7], v1)), xmul(M[8], v2));
+}
+// Vector3::norm_squared: (x*x + y*y) + z*z
+__device__ __forceinline__ float xnorm2(float x, float y, float z) {
+    return xadd(xadd(xmul(x, x), xmul(y, y)), xmul(z, z));
+}
+// (pos2 - pos1).norm_squared()   (distance_search.rs:446,460,488,507)
+__device__ __forceinline__ float d2_direct(float ax, float ay, float az, float bx, float by, float bz) {
+    return xnorm2(xsub(bx, ax), xsub(by, ay), xsub(bz, az));
+}
+// PeriodicBox::distance_squared(p1,p2,dims)   (periodic_box.rs:286-318,379-381)
+__device__ __forceinline__ float d2_pbc(const DevBox& bx, float ax, float ay, float az, float bxx, float byy,
+                                        float bzz, unsigned w) {
+    float v0 = xsub(bxx, ax), v1 = xsub(byy, ay), v2 = xsub(bzz, az);
+    float f0, f1, f2;
+    xmatvec(bx.inv, v0, v1, v2, f0, f1, f2);
+    if (w & 1u) f0 = xsub(f0, roundf(f0));
+    if (w & 2u) f1 = xsub(f1, roundf(f1));
+    if (w & 4u) f2 = xsub(f2, roundf(f2));
+    float s0, s1, s2;
+    xmatvec(bx.m, f0, f1, f2, s0, s1, s2);
+    float best2 = xnorm2(s0, s1, s2);
+    if (bx.ncorr == 0 || w != 7u) return best2;
+    for (int c = 0; c < bx.ncorr; ++c) {
+        float n2 = xnorm2(xadd(s0, bx.corr[3 * c]), xadd(s1, bx.corr[3 * c + 1]), xadd(s2, bx.corr[3 * c + 2]));
+        if (n2 < best2) best2 = n2;
+    }
+    return best2;
+}
+#endif  // __CUDACC__
+
+// implemented in the respective translation units
+int search_single_impl(Ctx* c, float cutoff, const uint64_t* ids, size_t n, uint8_t pbc, int mode,
+                       int64_t* count_out);
+int batch_search_impl(Ctx* c, float cutoff, uint8_t pbc, size_t f0, size_t f1, int mode, int64_t* counts,
+                      uint64_t* checksums2);
+int enqueue_count_frame(Ctx* c, const float* xyz, size_t n, float cutoff, uint8_t pbc,
+                        unsigned long long* d_counter2);
+void free_plan_cache(Ctx* c);
+int batch_fit_impl(Ctx* c, size_t ref_frame, size_t f0, size_t f1, int superpose, double* rmsd_out);
+int enqueue_batch_moments(Ctx* c, size_t f0, size_t f1, double* d_rows8, double* partials, unsigned* tickets,
+                          int nb);
+}  // namespace mb
+
+struct MbCtx {
+    mb::Ctx c;
+};

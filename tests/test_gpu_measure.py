@@ -1,0 +1,163 @@
+"""GPU parity: reductions and Kabsch through the C ABI vs the f64 oracle.
+Tolerance from BASELINE.json north_star: 1e-6 relative to the reference f64 path."""
+import numpy as np
+import pytest
+from scipy.spatial.transform import Rotation
+
+from oracle import oracle_py as orc
+from tests.helpers import SEED, TRIC
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-6  # the stated tolerance; observed agreement is ~1e-12
+
+M = np.diag([6.0, 7.0, 8.0]).astype(np.float32)
+
+
+@pytest.fixture(scope="module")
+def mb():
+    import molar_b200
+    return molar_b200
+
+
+def _data(n, seed=0):
+    return orc.synth_frame(SEED + seed, 0, n, M), orc.synth_masses(SEED + seed, n)
+
+
+@pytest.mark.parametrize("n,ids", [(5000, None), (100003, None), (100000, "stride3"), (7, None), (1, None)])
+def test_com_gyration(mb, n, ids):
+    xyz, m = _data(n, 1)
+    sel_ids = np.arange(0, n, 3, dtype=np.uint64) if ids else None
+    s = mb.System(xyz, masses=m)
+    sel = s(sel_ids) if sel_ids is not None else s()
+    rc, com = orc.center_of_mass(xyz, m, sel_ids)
+    rc, rg = orc.gyration(xyz, m, sel_ids)
+    assert np.allclose(sel.com(), com, rtol=RTOL, atol=0)
+    assert abs(sel.gyration() - rg) <= RTOL * max(rg, 1e-30) + 1e-12
+    s.close()
+
+
+def test_com_far_from_origin_small_rg(mb):
+    xyz, m = _data(20000, 2)
+    xyz = (xyz * np.float32(0.01) + np.float32(500.0)).astype(np.float32)
+    s = mb.System(xyz, masses=m)
+    rc, rg = orc.gyration(xyz, m)
+    assert abs(s().gyration() - rg) / rg < RTOL
+    s.close()
+
+
+def test_zero_mass_and_sizes_errors(mb):
+    xyz, m = _data(100, 3)
+    s = mb.System(xyz, masses=np.zeros(100, np.float32))
+    with pytest.raises(mb.MolarB200Error) as e:
+        s().com()
+    assert e.value.code == -1  # ZeroMass (measure.rs:70-71)
+    with pytest.raises(mb.MolarB200Error) as e:
+        mb.rmsd(s([0, 1, 2]), s([3, 4]))
+    assert e.value.code == -2  # Sizes (measure.rs:494-496)
+    s.close()
+
+
+def test_rmsd_and_rmsd_mw(mb):
+    a, m = _data(50000, 4)
+    b = orc.synth_frame(999, 1, 50000, M)
+    s1 = mb.System(a, masses=m)
+    s2 = mb.System(b, masses=m)
+    rc, r = orc.rmsd(a, None, b, None)
+    rc, rw = orc.rmsd(a, None, b, None, masses1=m)
+    assert abs(mb.rmsd(s1(), s2()) - r) / r < RTOL
+    assert abs(mb.rmsd_mw(s1(), s2()) - rw) / rw < RTOL
+    ids1 = np.arange(0, 30000, 2, dtype=np.uint64)
+    ids2 = np.arange(10000, 25000, dtype=np.uint64)
+    rc, r = orc.rmsd(a, ids1, b, ids2)
+    assert abs(mb.rmsd(s1(ids1), s2(ids2)) - r) / r < RTOL
+    s1.close()
+    s2.close()
+
+
+@pytest.mark.parametrize("angle", [80.0, 179.0, 3.0])
+def test_fit_transform_apply_rmsd(mb, angle):
+    # the reference's eigen_test scenario (selection.rs:148-172): rotate by 80 deg, fit, rmsd ~ 0
+    xyz, m = _data(40000, 5)
+    rot = Rotation.from_euler("zyx", [angle, 20.0, -35.0], degrees=True).as_matrix()
+    moved = ((xyz.astype(np.float64) @ rot.T) + np.array([1.0, -2.0, 0.5])).astype(np.float32)
+    s1 = mb.System(moved, masses=m)
+    s2 = mb.System(xyz, masses=m)
+    tr = mb.fit_transform(s1(), s2())
+    rc, R, t = orc.fit_transform(moved, m, None, xyz, m, None)
+    assert np.allclose(tr.R, R, rtol=0, atol=RTOL) and np.allclose(tr.t, t, rtol=RTOL, atol=1e-6 * np.abs(t).max())
+    assert np.allclose(tr.R.T @ tr.R, np.eye(3), atol=1e-12) and abs(np.linalg.det(tr.R) - 1) < 1e-12
+    s1().apply_transform(tr)
+    fitted = s1.coords()
+    expect = orc.apply_transform_f64(moved, None, R, t)
+    assert np.allclose(fitted, expect, rtol=RTOL, atol=1e-6)
+    assert mb.rmsd(s1(), s2()) < 1e-5
+    s1.close()
+    s2.close()
+
+
+def test_fit_transform_subsets_separate_masses_and_origin(mb):
+    xyz, m = _data(30000, 6)
+    other = orc.synth_frame(4242, 3, 30000, M)
+    ids1 = np.arange(100, 20100, dtype=np.uint64)
+    ids2 = np.arange(5000, 25000, dtype=np.uint64)
+    s1 = mb.System(xyz, masses=m)
+    s2 = mb.System(other, masses=m)
+    for at_origin in (False, True):
+        tr = mb.fit_transform(s1(ids1), s2(ids2), at_origin=at_origin)
+        rc, R, t = orc.fit_transform(xyz, m, ids1, other, m, ids2, at_origin=at_origin)
+        assert rc == 0
+        assert np.allclose(tr.R, R, atol=1e-6) and np.allclose(tr.t, t, atol=1e-5)
+    s1.close()
+    s2.close()
+
+
+def test_fit_reflection(mb):
+    xyz, m = _data(5000, 7)
+    mir = xyz.copy()
+    mir[:, 0] *= -1
+    s1 = mb.System(mir, masses=m)
+    s2 = mb.System(xyz, masses=m)
+    tr = mb.fit_transform(s1(), s2())
+    rc, R, t = orc.fit_transform(mir, m, None, xyz, m, None)
+    assert abs(np.linalg.det(tr.R) - 1) < 1e-12 and np.allclose(tr.R, R, atol=1e-6)
+    s1.close()
+    s2.close()
+
+
+def test_batch_fit_config4_shape(mb):
+    """config 4 at reduced frame count: fit every frame onto frame 0, superpose, RMSD."""
+    n, nf = 500_000, 6
+    t = mb.Trajectory()
+    t.synth(SEED, 0, nf, n, TRIC, mass_seed=SEED)
+    m = orc.synth_masses(SEED, n)
+    ref = orc.synth_frame(SEED, 0, n, TRIC)
+    before = [t.frame(f) for f in range(nf)]
+    assert np.array_equal(before[0], ref)
+    r = t.fit(ref_frame=0, superpose=True)
+    for f in (0, 1, nf - 1):
+        rc, R, tt = orc.fit_transform(before[f], m, None, ref, m, None)
+        exp = orc.apply_transform_f64(before[f], None, R, tt)
+        exp_r = np.sqrt(((exp - ref) ** 2).sum(1).mean())
+        assert abs(r[f] - exp_r) <= RTOL * exp_r + 1e-9
+        assert np.allclose(t.frame(f), exp, rtol=RTOL, atol=2e-6)
+    assert r[0] < 1e-6
+    t.close()
+
+
+def test_batch_pipeline_config5_shape(mb):
+    n, nf = 200_000, 3
+    box = (TRIC * np.float32(0.6)).astype(np.float32)
+    t = mb.Trajectory()
+    t.synth(SEED, 5, nf, n, box, mass_seed=SEED)
+    rows = t.pipeline(1.2)
+    m = orc.synth_masses(SEED, n)
+    b = orc.Box(matrix=box)
+    for f in range(nf):
+        xyz = orc.synth_frame(SEED, 5 + f, n, box)
+        rc, com = orc.center_of_mass(xyz, m)
+        rc, rg = orc.gyration(xyz, m)
+        assert np.allclose(rows[f, :3], com, rtol=RTOL) and abs(rows[f, 3] - rg) / rg < RTOL
+        if f == 0:
+            ij, d, dims = orc.search_single(1.2, xyz, None, b, 7, 8)
+            assert int(rows[f, 4]) == len(orc.canonical_pairs(ij))
+    t.close()

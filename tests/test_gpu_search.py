@@ -1,0 +1,213 @@
+"""GPU parity: neighbour search through the C ABI vs the CPU oracle.  Bit-exact pair sets
+(sorted (min,max) sets) and bit-exact f32 distances."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle_py as orc
+from tests.helpers import SEED, TRIC, assert_same_pairs, gpu_canonical, oracle_single
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def mb():
+    import molar_b200
+    return molar_b200
+
+
+def run_single(mb, xyz, cutoff, box=None, dims=None, ids=None, **opts):
+    s = mb.System(xyz, box=box)
+    for k, v in opts.items():
+        s.set_option(k, v)
+    sel = s(ids) if ids is not None else s()
+    pairs, dist = mb.distance_search(cutoff, sel, dims=dims)
+    s.close()
+    return gpu_canonical(pairs, dist)
+
+
+ORTHO_SMALL = np.diag([4.0, 4.4, 5.1]).astype(np.float32)
+
+
+def test_single_pbc_small_general_kernel(mb):
+    xyz = orc.synth_frame(SEED, 0, 1200, ORTHO_SMALL)
+    op, od, dims = oracle_single(1.2, xyz, box=ORTHO_SMALL, pbc=7)
+    gp, gd = run_single(mb, xyz, 1.2, box=ORTHO_SMALL, dims=[True] * 3)
+    assert_same_pairs(gp, gd, op, od)
+
+
+@pytest.mark.parametrize("diag", [(2.0, 2.9, 1.3), (1.3, 5.0, 2.5), (3.7, 1.0, 6.0)])
+def test_single_pbc_degenerate_grid(mb, diag):
+    # dims of 1 and 2: the same cell pair is reached directly AND wrapped (SURVEY §7 hard part 3)
+    M = np.diag(diag).astype(np.float32)
+    xyz = orc.synth_frame(SEED + 1, 0, 700, M, stray_permille=30)
+    op, od, dims = oracle_single(1.2, xyz, box=M, pbc=7)
+    assert min(dims) <= 2
+    gp, gd = run_single(mb, xyz, 1.2, box=M, dims=[True] * 3)
+    assert gp.shape == op.shape and np.array_equal(gp, op)
+    # a degenerate pair can be reported with several distances by the reference; we keep the minimum
+    assert np.array_equal(gd, od)
+
+
+@pytest.mark.parametrize("subdiv", [0, 1, 2, 3])
+def test_single_pbc_cells_orthorhombic(mb, subdiv):
+    M = np.diag([6.0, 7.0, 8.0]).astype(np.float32)
+    xyz = orc.synth_frame(SEED + 2, 0, 30000, M, stray_permille=10)
+    op, od, dims = oracle_single(1.2, xyz, box=M, pbc=7)
+    assert list(dims) == [5, 5, 6]
+    gp, gd = run_single(mb, xyz, 1.2, box=M, dims=[True] * 3, subdiv=subdiv)
+    assert_same_pairs(gp, gd, op, od)
+
+
+@pytest.mark.parametrize("subdiv", [0, 1, 2])
+def test_single_pbc_cells_triclinic_config3_shape(mb, subdiv):
+    M = (TRIC * np.float32(0.3)).astype(np.float32)
+    xyz = orc.synth_frame(SEED + 3, 0, 27000, M, stray_permille=10)
+    op, od, dims = oracle_single(1.2, xyz, box=M, pbc=7)
+    gp, gd = run_single(mb, xyz, 1.2, box=M, dims=[True] * 3, subdiv=subdiv)
+    assert_same_pairs(gp, gd, op, od)
+
+
+def test_single_pbc_cells_triclinic_adversarial_positive_shear(mb):
+    # SURVEY §7 hard part 2: the reference grid misses pairs here; parity = bug-compatible
+    L = 6.0
+    M = np.array([[L, 0, L / 2], [0, L, L / 2], [0, 0, L / np.sqrt(2)]], np.float32)
+    xyz = orc.synth_frame(SEED + 4, 0, 22000, M, stray_permille=10)
+    op, od, dims = oracle_single(1.2, xyz, box=M, pbc=7)
+    gp, gd = run_single(mb, xyz, 1.2, box=M, dims=[True] * 3)
+    assert_same_pairs(gp, gd, op, od)
+    gp2, gd2 = run_single(mb, xyz, 1.2, box=M, dims=[True] * 3, force_brute=1)
+    assert_same_pairs(gp2, gd2, op, od)
+
+
+def test_single_pbc_reference_triclinic_fixture(mb, golden_dir):
+    # molar/tests/triclinic.pdb (CRYST1 93.753^3, 60/60/90), every 9th atom
+    z = np.load(os.path.join(golden_dir, "triclinic_sub.npz"))
+    a, b, c, al, be, ga = [float(v) for v in z["cryst1"]]
+    box = orc.Box(vectors_angles=(a, b, c, al, be, ga))
+    M = box.matrix
+    xyz = z["xyz"]
+    ij, d, dims = orc.search_single(1.0, xyz, None, box, 7, 4)
+    op, od = orc.canonical_pairs(ij, d)
+    gp, gd = run_single(mb, xyz, 1.0, box=M, dims=[True] * 3)
+    assert_same_pairs(gp, gd, op, od)
+
+
+@pytest.mark.parametrize("dims", [[True, True, False], [False, True, False], [True, False, True]])
+def test_single_partial_pbc(mb, dims):
+    M = np.diag([6.0, 7.0, 8.0]).astype(np.float32)
+    xyz = orc.synth_frame(SEED + 5, 0, 12000, M, stray_permille=40)
+    pbc = sum(1 << i for i in range(3) if dims[i])
+    op, od, gd_ = oracle_single(1.2, xyz, box=M, pbc=pbc)
+    gp, gd = run_single(mb, xyz, 1.2, box=M, dims=dims)
+    assert_same_pairs(gp, gd, op, od)
+
+
+def test_single_nonperiodic_config1_2lao(mb, golden_dir):
+    # BASELINE config 1: 2k-atom protein, distance_search within 1.0 nm + rmsd to self
+    xyz = np.load(os.path.join(golden_dir, "2lao.npz"))["xyz"]
+    op, od, dims = oracle_single(1.0, xyz)
+    gp, gd = run_single(mb, xyz, 1.0)
+    assert_same_pairs(gp, gd, op, od)
+    s = mb.System(xyz)
+    assert mb.rmsd(s(), s()) == 0.0
+    s.close()
+
+
+def test_single_nonperiodic_cells(mb):
+    M = np.diag([6.0, 7.0, 8.0]).astype(np.float32)
+    xyz = orc.synth_frame(SEED + 6, 0, 25000, M) - np.float32(2.5)  # negative coordinates too
+    op, od, dims = oracle_single(0.9, xyz)
+    gp, gd = run_single(mb, xyz, 0.9)
+    assert_same_pairs(gp, gd, op, od)
+
+
+def test_single_with_selection_ids(mb):
+    M = np.diag([6.0, 7.0, 8.0]).astype(np.float32)
+    xyz = orc.synth_frame(SEED + 7, 0, 30000, M)
+    ids = np.arange(0, 30000, 2, dtype=np.uint64)
+    op, od, dims = oracle_single(1.2, xyz, ids=ids, box=M, pbc=7)
+    gp, gd = run_single(mb, xyz, 1.2, box=M, dims=[True] * 3, ids=ids)
+    assert_same_pairs(gp, gd, op, od)
+    assert set(np.unique(gp).tolist()) <= set(ids.tolist())
+
+
+def test_double_search_vs_oracle(mb):
+    M = np.diag([5.0, 5.5, 6.0]).astype(np.float32)
+    xyz = orc.synth_frame(SEED + 8, 0, 6000, M, stray_permille=10)
+    ids1 = np.arange(0, 6000, 3, dtype=np.uint64)
+    ids2 = np.arange(1, 6000, 2, dtype=np.uint64)
+    box = orc.Box(matrix=M)
+    for pbc in (0, 7):
+        ij, d, dims = orc.search_double(1.0, xyz, ids1, xyz, ids2, box if pbc else None, pbc, 4)
+        op, od = orc.ordered_pairs(ij, d)
+        s = mb.System(xyz, box=M)
+        pairs, dist = mb.distance_search(1.0, s(ids1), s(ids2), dims=[bool(pbc)] * 3)
+        s.close()
+        gp, gd = orc.ordered_pairs(pairs, dist)
+        assert len(gp) == len(pairs)
+        assert_same_pairs(gp, gd, op, od)
+
+
+CASES = ["within_0.5_resid10", "within_0.3_resid20", "within_0.5_resid555", "within_0.5_pbc_resid555"]
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_within_reference_golden_vectors(mb, golden_dir, case):
+    """The reference's own golden answers (molar/tests/generated_vmd_tests.in:27,35;
+    generated_pteros_tests.in:21,27) reproduced by the CUDA path."""
+    from molar_b200.api import within
+    z = np.load(os.path.join(golden_dir, "albumin_within.npz"))
+    cutoff, pbc = z[case + "_params"]
+    M = z["box9"].reshape(3, 3).T
+    s = mb.System(z["xyz"], box=M)
+    inner = s(z[case + "_inner"].astype(np.uint64))
+    got = within(float(np.float32(cutoff)), s(), inner, dims=int(pbc))
+    s.close()
+    assert np.array_equal(got.astype(np.int64), z[case + "_answer"])
+
+
+def test_empty_and_error_paths(mb):
+    M = np.diag([6.0, 7.0, 8.0]).astype(np.float32)
+    xyz = orc.synth_frame(SEED, 0, 100, M)
+    s = mb.System(xyz)  # no box
+    with pytest.raises(mb.MolarB200Error) as e:
+        mb.distance_search(1.0, s(), dims=[True, True, True])
+    assert e.value.code == -4  # NoPbc
+    pairs, dist = mb.distance_search(1e-4, s())  # nothing within cutoff
+    assert pairs.shape == (0, 2) and dist.shape == (0,)
+    with pytest.raises(IndexError):
+        s([1000])
+    s.close()
+
+
+# ---- full-size configs (BASELINE.json configs[1], configs[2]) ---------------------------------
+
+def test_config2_100k_orthorhombic_exact(mb):
+    M = np.diag([10.0, 10.0, 10.0]).astype(np.float32)
+    xyz = orc.synth_frame(SEED, 0, 100000, M)
+    op, od, dims = oracle_single(1.2, xyz, box=M, pbc=7, nthreads=8)
+    assert list(dims) == [8, 8, 8]
+    gp, gd = run_single(mb, xyz, 1.2, box=M, dims=[True] * 3)
+    assert_same_pairs(gp, gd, op, od)
+
+
+def test_config3_1m_triclinic_properties(mb):
+    """1M atoms: too slow for the oracle inside the test budget, so size-independent properties:
+    count-only == enumerated count; the order-independent checksum and count do not depend on the
+    traversal subdivision (k=1 walks exactly the reference's own cell pairs); the device generator
+    produces the oracle's bits."""
+    n = 1_000_000
+    t = mb.Trajectory()
+    t.synth(SEED, 0, 2, n, TRIC)
+    assert np.array_equal(t.frame(1)[:5000], orc.synth_frame(SEED, 1, 5000, TRIC))
+    counts, chk = t.search(1.2, checksums=True)
+    counts_only = t.search(1.2, count_only=True)
+    assert np.array_equal(counts, counts_only)
+    expect = n * (n / abs(np.linalg.det(TRIC.astype(np.float64)))) * (4 / 3) * np.pi * 1.2 ** 3 / 2
+    assert np.all(np.abs(counts - expect) / expect < 0.01)
+    t.set_option("subdiv", 1)
+    counts1, chk1 = t.search(1.2, f0=0, f1=1, checksums=True)
+    assert counts1[0] == counts[0] and np.array_equal(chk1[0], chk[0])
+    t.close()
