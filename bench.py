@@ -1,0 +1,340 @@
+#!/usr/bin/env python3
+"""bench.py — frames/sec of the hot path on synthetic frames (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl ours|reference]
+
+One rank per GPU (torchrun for N>1), frames sharded across ranks (weak scaling: every rank owns
+`--frames` resident frames and one step = one pass of the hot path over all of them).  Prints ONE
+JSON line on rank 0.  torch is used for plumbing only (torch.distributed barrier / NCCL gather of
+the per-frame scalars, CUDA events on the library's own stream); every number is produced by
+libmolar_b200.so through its C ABI.
+
+Workloads (BASELINE.json configs):
+  search1m   configs[2]  1M-atom triclinic box, 1.2 nm neighbour-pair enumeration   (default, headline)
+  search100k configs[1]  100k-atom orthorhombic box, 1.2 nm
+  fit500k    configs[3]  500k-atom Kabsch fit + superposition + RMSD to frame 0
+  pipeline1m configs[4]  1M-atom COM + gyration + 1.2 nm contact count, NCCL scalar gather
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SEED = 20260
+TRIC = np.array([[21.5, -2.7, -2.7], [0.0, 21.5, -2.7], [0.0, 0.0, 21.5]], np.float32)
+ORTHO = np.diag([10.0, 10.0, 10.0]).astype(np.float32)
+CUTOFF = 1.2
+
+WORKLOADS = {
+    "search1m": dict(n_atoms=1_000_000, box=TRIC, frames=16, kind="search",
+                     desc="1M-atom triclinic box, 1.2 nm neighbour-pair enumeration (configs[2])"),
+    "search100k": dict(n_atoms=100_000, box=ORTHO, frames=128, kind="search",
+                       desc="100k-atom orthorhombic box, 1.2 nm neighbour search (configs[1])"),
+    "fit500k": dict(n_atoms=500_000, box=TRIC, frames=64, kind="fit",
+                    desc="500k-atom Kabsch fit + superposition + RMSD to frame 0 (configs[3])"),
+    "pipeline1m": dict(n_atoms=1_000_000, box=TRIC, frames=16, kind="pipeline",
+                       desc="1M-atom COM + gyration + 1.2 nm contact count (configs[4])"),
+}
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for k, nm in enumerate(names):
+                    if r[5 + k].lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm: the reference's CPU algorithm (C++ restatement, all host threads)
+# ---------------------------------------------------------------------------------------------
+def cpu_frames_per_sec(wl, n_frames, nthreads, first_frame=0, budget_s=60.0):
+    """Times the oracle (kind "port": MolAR itself is Rust and cannot be built here) on up to
+    n_frames frames, stopping early once budget_s of CPU work has been spent (bounded sample)."""
+    from oracle import oracle_py as orc
+    n, box = wl["n_atoms"], wl["box"]
+    b = orc.Box(matrix=box)
+    n_gen = min(n_frames, 4)
+    frames = [orc.synth_frame(SEED, first_frame + f, n, box) for f in range(n_gen)]
+    masses = orc.synth_masses(SEED, n)
+    ref = frames[0]
+    done = 0
+    t0 = time.perf_counter()
+    for it in range(n_frames):
+        xyz = frames[it % n_gen]
+        if done and time.perf_counter() - t0 > budget_s:
+            break
+        done += 1
+        if wl["kind"] == "search":
+            h = orc.lib().orc_search_single_pbc(CUTOFF, xyz.ctypes.data_as(orc._f32p), None, n, b.h, 7, nthreads)
+            orc.lib().orc_result_free(h)
+        elif wl["kind"] == "fit":
+            rc, R, t = orc.fit_transform(xyz, masses, None, ref, masses, None, prec="f32")
+            moved = orc.apply_transform_f32(xyz, None, R, t)
+            orc.rmsd(moved, None, ref, None, prec="f32")
+        else:
+            orc.center_of_mass(xyz, masses, prec="f32")
+            orc.gyration(xyz, masses, prec="f32")
+            h = orc.lib().orc_search_single_pbc(CUTOFF, xyz.ctypes.data_as(orc._f32p), None, n, b.h, 7, nthreads)
+            orc.lib().orc_result_free(h)
+    dt = time.perf_counter() - t0
+    return done / dt, dt, done
+
+
+def run_reference(args, wl):
+    rank, world, local = dist_env()
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    nthreads = cores if wl["kind"] != "fit" else 1  # measure.rs paths are serial in the reference
+    for _ in range(args.warmup if args.warmup < 2 else 1):
+        cpu_frames_per_sec(wl, 1, nthreads)
+    fps, dt, done = cpu_frames_per_sec(wl, max(1, args.steps), nthreads, first_frame=1, budget_s=90.0)
+    line = {
+        "impl": "reference", "metric": "frames/sec", "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * dt / done,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl["desc"], "n_atoms": wl["n_atoms"], "cutoff_nm": CUTOFF,
+                   "frames_per_step": 1, "note": "one step = one frame on the host cores"},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": nthreads, "kind": "port",
+                         "sample": f"{done} frames of the workload ({dt:.1f} s); C++ restatement of MolAR's "
+                                   f"CPU algorithm (MolAR is Rust; no cargo in this image)"},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------
+def run_ours(args, wl):
+    import torch
+    import torch.distributed as dist
+    import molar_b200 as mb
+
+    rank, world, local = dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; libmolar_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n, box, F, kind = wl["n_atoms"], wl["box"], args.frames or wl["frames"], wl["kind"]
+
+    traj = mb.Trajectory(device=local)
+    traj.synth(SEED, rank * F, F, n, box, mass_seed=SEED)  # rank r owns global frames [r*F, (r+1)*F)
+    traj.set_option("profile", 1)
+    ext = torch.cuda.ExternalStream(traj.stream(), device=local)
+
+    def step():
+        if kind == "search":
+            return traj.search(CUTOFF)
+        if kind == "fit":
+            return traj.fit(ref_frame=0, superpose=True)
+        return traj.pipeline(CUTOFF)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        res = step()
+    traj.set_option("profile", 1)  # reset the kernel-time accumulators
+    l0 = traj.launch_count()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(ext)
+    for _ in range(args.steps):
+        res = step()
+    # per-frame scalars -> every rank (NCCL over NVLink; the only collective on the path)
+    scal = torch.as_tensor(np.asarray(res, dtype=np.float64).reshape(F, -1), device=f"cuda:{local}")
+    if world > 1:
+        gathered = torch.empty((world * F, scal.shape[1]), dtype=torch.float64, device=f"cuda:{local}")
+        dist.all_gather_into_tensor(gathered, scal)
+    e1.record(ext)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=f"cuda:{local}", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    clk = clocks.stop() if rank == 0 else None
+    launches = traj.launch_count() - l0
+    k_ms = traj.stat("search_kernel_ms")
+    k_n = traj.stat("search_kernel_launches")
+    fps = world * F * args.steps / (ms / 1000.0)
+
+    # ---- end-to-end through the public per-call API with HOST buffers (pinned), rank-local -------
+    from oracle import oracle_py as orc  # only to synthesise host-side input frames
+    e2e_frames = min(F, 4)
+    host = [torch.from_numpy(orc.synth_frame(SEED, rank * F + f, n, box)).pin_memory() for f in range(e2e_frames)]
+    sysm = mb.System(host[0].numpy(), masses=orc.synth_masses(SEED, n), box=box)
+    refsys = mb.System(host[0].numpy(), masses=orc.synth_masses(SEED, n), box=box) if kind == "fit" else None
+
+    def e2e_once(x):
+        sysm.set_state(x.numpy(), box)  # H2D of the frame (12 B/atom) from pinned memory
+        if kind == "search":
+            lib, h = sysm._lib, sysm._h
+            return mb._capi.check(lib.mb_search_single(h, CUTOFF, None, n, 7))  # D2H: the pair count
+        if kind == "fit":
+            tr = mb.fit_transform(sysm(), refsys())
+            sysm().apply_transform(tr)
+            return mb.rmsd(sysm(), refsys())
+        c = sysm().com()
+        g = sysm().gyration()
+        lib, h = sysm._lib, sysm._h
+        return (c, g, mb._capi.check(lib.mb_count_single(h, CUTOFF, None, n, 7)))
+
+    sysm.set_option("with_dist", 0)
+    e2e_once(host[0])
+    barrier()
+    t0 = time.perf_counter()
+    reps = max(1, min(args.steps, 4))
+    for _ in range(reps):
+        for x in host:
+            e2e_once(x)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device=f"cuda:{local}", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_fps = world * reps * e2e_frames / e2e_s
+    d2h = {"search": 8, "fit": 8 + 96, "pipeline": 40}[kind]
+
+    if rank == 0:
+        peak, which = peaks()
+        if kind in ("search", "pipeline"):
+            pairs = float(np.mean(res)) if kind == "search" else float(np.mean(np.asarray(res)[:, 4]))
+            alg_bytes = 12.0 * n + (8.0 * pairs if kind == "search" else 4.0 * n)
+            kern = "search_cells_kernel"
+            k_avg_ms = k_ms / max(k_n, 1)
+        else:
+            pairs = 0.0
+            alg_bytes = 24.0 * n
+            kern = "fit_moments_kernel+superpose_rmsd_kernel (whole step)"
+            k_avg_ms = ms / (F * args.steps)
+        achieved = alg_bytes / (k_avg_ms * 1e-3) / 1e9 if k_avg_ms > 0 else 0.0
+        line = {
+            "metric": "frames/sec", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl["desc"], "n_atoms": n, "cutoff_nm": CUTOFF, "frames_per_step_per_gpu": F,
+                       "pairs_per_frame": pairs, "l2": f"inputs {F * n * 12 / 1e6:.0f} MB/GPU > 126 MB L2"
+                       if F * n * 12 > 126e6 else "pair output per frame exceeds L2; inputs re-streamed",
+                       "parallelism": f"frames sharded over {world} GPU(s)"},
+            "roofline": {"bound": "hbm", "kernel": kern, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": which,
+                         "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": k_avg_ms,
+                         "kernel_share_of_step": (k_ms / ms) if kind != "fit" else 1.0},
+            "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": 12 * n, "d2h_bytes_per_step": d2h,
+                    "note": "one step = one frame through the per-call C ABI from pinned host memory"},
+            "gpu_launches": int(launches),
+            "clocks": clk,
+        }
+        if not args.no_cpu and world == 1:
+            cores = os.cpu_count() or 1
+            nthreads = cores if kind != "fit" else 1
+            nfr = {"search": 2, "fit": 20, "pipeline": 2}[kind] if n >= 500_000 else 20
+            cfps, cdt, nfr = cpu_frames_per_sec(wl, nfr, nthreads, budget_s=25.0)
+            line["cpu_baseline"] = {"value": cfps, "unit": "frames/s", "cores": nthreads, "kind": "port",
+                                    "sample": f"{nfr} frames of the same workload ({cdt:.1f} s); C++ restatement "
+                                              f"of MolAR's CPU algorithm, not MolAR itself"}
+        print(json.dumps(line))
+    traj.close()
+    sysm.close()
+    if refsys:
+        refsys.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="search1m", choices=sorted(WORKLOADS))
+    ap.add_argument("--frames", type=int, default=0, help="resident frames per GPU (one step = one pass over them)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    import __graft_entry__
+    __graft_entry__.build()
+    if args.impl == "reference":
+        return run_reference(args, wl)
+    return run_ours(args, wl)
+
+
+if __name__ == "__main__":
+    sys.exit(main())
