@@ -120,6 +120,7 @@ struct Ctx {
     int opt_force_brute = 0;  // force the general all-pairs kernel
     double opt_atoms_per_cell = 12.0;
     int opt_with_dist = 1;
+    int opt_exact_pbc = 0;    // 1: wrapped cell pairs always use the exact PeriodicBox path (no filter)
     int opt_profile = 0;      // record CUDA events around every search-kernel launch
     std::vector<cudaEvent_t> prof_events;  // begin/end pairs not yet harvested
     double prof_search_ms = 0.0;

@@ -55,6 +55,8 @@ struct SearchParams {
     const unsigned* cell_start;
     GridSpec g;
     float rc2;
+    float rc2_lo, rc2_hi;  // band around cutoff^2 outside which the shifted-image filter is decisive
+    int fast_pbc;          // 1: wrapped cell pairs may use the filter (see plan_cells)
     int nrows;
     NbrRow rows[MAX_ROWS];
     uint2* pairs;
@@ -299,70 +301,192 @@ __device__ __forceinline__ void warp_flush(uint2* stage, float* stage_d, int& st
     stage_n = 0;
 }
 
+// ---- packed f32x2 helpers (sm_100: FADD2 / FMUL2 process two neighbour atoms per lane) ----------
+// sub.rn / mul.rn are IEEE per element, so each half rounds exactly like the scalar op.  The sums
+// of squares stay SCALAR __fadd_rn: ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 (even
+// with -fmad=false), which would break bit-exactness; it never contracts into a scalar FADD.
+__device__ __forceinline__ unsigned long long pk2(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void upk2(unsigned long long u, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(u));
+}
+__device__ __forceinline__ unsigned long long sub2(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+// squared distances of two neighbours (packed) to one home atom: (dx*dx + dy*dy) + dz*dz, unfused
+__device__ __forceinline__ void d2_pair(unsigned long long nx, unsigned long long ny, unsigned long long nz,
+                                        const float4& h, float& d0, float& d1) {
+    unsigned long long dx = sub2(nx, pk2(h.x, h.x)), dy = sub2(ny, pk2(h.y, h.y)), dz = sub2(nz, pk2(h.z, h.z));
+    unsigned long long xx = mul2(dx, dx), yy = mul2(dy, dy), zz = mul2(dz, dz);
+    float x0, x1, y0, y1, z0, z1;
+    upk2(xx, x0, x1);
+    upk2(yy, y0, y1);
+    upk2(zz, z0, z1);
+    d0 = xadd(xadd(x0, y0), z0);
+    d1 = xadd(xadd(x1, y1), z1);
+}
+
+// Emit the pairs of one neighbour atom per lane (bit j of `mask` = hit against home atom j).
+template <int MODE, bool PBCW>
+__device__ __forceinline__ void emit_hits(const SearchParams& P, const float4* __restrict__ home, unsigned mask,
+                                          const float4& nb, unsigned w, int off, uint2* stage, float* stage_d) {
+    const unsigned nid = __float_as_uint(nb.w);
+    while (mask) {
+        const int j = 31 - __clz(mask);
+        mask ^= 1u << j;
+        const float4 h = home[j];
+        const unsigned hid = __float_as_uint(h.w);
+        stage[off] = make_uint2(min(hid, nid), max(hid, nid));
+        if (MODE == 1) {
+            float d2 = PBCW ? d2_pbc(P.g.box, h.x, h.y, h.z, nb.x, nb.y, nb.z, w)
+                            : d2_direct(h.x, h.y, h.z, nb.x, nb.y, nb.z);
+            stage_d[off] = __fsqrt_rn(d2);
+        }
+        ++off;
+    }
+}
+
+// One contiguous run [s,e) of neighbour atoms against the home batch.  Each lane owns TWO neighbour
+// atoms (64 per warp step, two coalesced float4 streams); home atoms are broadcast from shared memory.
+// KIND: 0 direct difference, 1 direct + self filter (home cell against itself),
+//       2 wrapped cell pair, fast filter (shifted image + exact re-check in a band around cutoff^2),
+//       3 wrapped cell pair, exact PeriodicBox::distance_squared for every test.
 // MODE: 0 pairs, 1 pairs + distances, 2 count only
-template <int MODE, bool PBCW, bool SELF>
+template <int MODE, int KIND>
 __device__ __forceinline__ void process_run(const SearchParams& P, const float4* __restrict__ home, int nh,
-                                            int hb, unsigned s, unsigned e, unsigned w, uint2* stage,
-                                            float* stage_d, int& stage_n, unsigned long long& count,
-                                            unsigned lane) {
-    const int nh4 = (nh + 3) & ~3;
+                                            int hb, unsigned s, unsigned e, unsigned w, unsigned wsgn,
+                                            uint2* stage, float* stage_d, int& stage_n,
+                                            unsigned long long& count, unsigned lane) {
     const float rc2 = P.rc2;
-    for (unsigned base = s; base < e; base += 32) {
-        unsigned ni = base + lane;
-        float4 nb;
-        if (ni < e) nb = __ldg(&P.sorted[ni]);
-        else nb = make_float4(__int_as_float(0x7fc00000), 0.f, 0.f, 0.f);  // NaN: never within cutoff
-        unsigned mask = 0;
-        for (int j = 0; j < nh4; j += 4) {
+    const float qnan = __int_as_float(0x7fc00000);
+    float sx = 0.f, sy = 0.f, sz = 0.f;
+    if (KIND == 2) {
+        // lattice shift that maps the neighbour image the reference's rounding selects:
+        // neighbour cell above the home cell (wsgn bit set) => n_d = +1 => subtract column d
 #pragma unroll
-            for (int jj = 0; jj < 4; ++jj) {
-                float4 h = home[j + jj];
-                float d2 = PBCW ? d2_pbc(P.g.box, h.x, h.y, h.z, nb.x, nb.y, nb.z, w)
-                                : d2_direct(h.x, h.y, h.z, nb.x, nb.y, nb.z);
-                bool hit = d2 <= rc2;
-                if (SELF) hit = hit && (ni > (unsigned)(hb + j + jj));
-                mask |= (hit ? 1u : 0u) << (j + jj);
+        for (int d = 0; d < 3; ++d)
+            if ((w >> d) & 1u) {
+                float sg = ((wsgn >> d) & 1u) ? -1.0f : 1.0f;
+                sx += sg * P.g.box.m[d];
+                sy += sg * P.g.box.m[3 + d];
+                sz += sg * P.g.box.m[6 + d];
+            }
+    }
+    for (unsigned base = s; base < e; base += 64) {
+        const unsigned ni0 = base + lane, ni1 = base + 32 + lane;
+        float4 n0 = make_float4(qnan, 0.f, 0.f, 0.f), n1 = n0;  // NaN: never within cutoff
+        if (ni0 < e) n0 = __ldg(&P.sorted[ni0]);
+        if (ni1 < e) n1 = __ldg(&P.sorted[ni1]);
+        unsigned m0 = 0, m1 = 0;
+        if (KIND == 0 || KIND == 2) {
+            const unsigned long long nx = pk2(n0.x + sx, n1.x + sx), ny = pk2(n0.y + sy, n1.y + sy),
+                                     nz = pk2(n0.z + sz, n1.z + sz);
+            unsigned a0 = 0, a1 = 0;  // KIND 2: possible hits (superset), m0/m1 = certain hits
+#pragma unroll
+            for (int j0 = 0; j0 < 32; j0 += 4) {
+                if (j0 >= nh) break;
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    const int j = j0 + jj;
+                    const float4 h = home[j];
+                    float d0, d1;
+                    d2_pair(nx, ny, nz, h, d0, d1);
+                    if (KIND == 0) {
+                        if (d0 <= rc2) m0 |= 1u << j;
+                        if (d1 <= rc2) m1 |= 1u << j;
+                    } else {
+                        if (d0 <= P.rc2_lo) m0 |= 1u << j;
+                        if (d1 <= P.rc2_lo) m1 |= 1u << j;
+                        if (d0 <= P.rc2_hi) a0 |= 1u << j;
+                        if (d1 <= P.rc2_hi) a1 |= 1u << j;
+                    }
+                }
+            }
+            if (KIND == 2) {
+                a0 ^= m0;
+                a1 ^= m1;
+                if (__any_sync(0xffffffffu, (a0 | a1) != 0u)) {
+                    // within the rounding band of cutoff^2: decide with the reference's own arithmetic
+                    while (a0) {
+                        const int j = 31 - __clz(a0);
+                        a0 ^= 1u << j;
+                        const float4 h = home[j];
+                        if (d2_pbc(P.g.box, h.x, h.y, h.z, n0.x, n0.y, n0.z, w) <= rc2) m0 |= 1u << j;
+                    }
+                    while (a1) {
+                        const int j = 31 - __clz(a1);
+                        a1 ^= 1u << j;
+                        const float4 h = home[j];
+                        if (d2_pbc(P.g.box, h.x, h.y, h.z, n1.x, n1.y, n1.z, w) <= rc2) m1 |= 1u << j;
+                    }
+                }
+            }
+        } else {
+            const int nh4 = (nh + 3) & ~3;
+            for (int j = 0; j < nh4; ++j) {
+                const float4 h = home[j];
+                float d0, d1;
+                if (KIND == 3) {
+                    d0 = d2_pbc(P.g.box, h.x, h.y, h.z, n0.x, n0.y, n0.z, w);
+                    d1 = d2_pbc(P.g.box, h.x, h.y, h.z, n1.x, n1.y, n1.z, w);
+                } else {
+                    d0 = d2_direct(h.x, h.y, h.z, n0.x, n0.y, n0.z);
+                    d1 = d2_direct(h.x, h.y, h.z, n1.x, n1.y, n1.z);
+                }
+                bool h0 = d0 <= rc2, h1 = d1 <= rc2;
+                if (KIND == 1) {
+                    h0 = h0 && (ni0 > (unsigned)(hb + j));
+                    h1 = h1 && (ni1 > (unsigned)(hb + j));
+                }
+                m0 |= (h0 ? 1u : 0u) << j;
+                m1 |= (h1 ? 1u : 0u) << j;
             }
         }
+        const int c0 = __popc(m0), c1 = __popc(m1);
         if (MODE == 2) {
-            count += __popc(mask);
+            count += c0 + c1;
             continue;
         }
-        int cnt = __popc(mask);
-        int inc = cnt;
+        // one scan for both halves: low 16 bits = first atom, high 16 bits = second atom
+        int inc = c0 | (c1 << 16);
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             int t = __shfl_up_sync(0xffffffffu, inc, o);
             if (lane >= (unsigned)o) inc += t;
         }
-        int total = __shfl_sync(0xffffffffu, inc, 31);
-        if (total == 0) continue;
-        if (stage_n + total > STAGE_CAP) warp_flush<MODE == 1>(stage, stage_d, stage_n, P, lane);
-        int off = stage_n + inc - cnt;
-        unsigned nid = __float_as_uint(nb.w);
-        while (mask) {
-            int j = __ffs(mask) - 1;
-            mask &= mask - 1;
-            float4 h = home[j];
-            unsigned hid = __float_as_uint(h.w);
-            stage[off] = make_uint2(min(hid, nid), max(hid, nid));
-            if (MODE == 1) {
-                float d2 = PBCW ? d2_pbc(P.g.box, h.x, h.y, h.z, nb.x, nb.y, nb.z, w)
-                                : d2_direct(h.x, h.y, h.z, nb.x, nb.y, nb.z);
-                stage_d[off] = __fsqrt_rn(d2);
-            }
-            ++off;
+        const int tot = __shfl_sync(0xffffffffu, inc, 31);
+        const int t0 = tot & 0xffff, t1 = tot >> 16;
+        if (t0) {
+            if (stage_n + t0 > STAGE_CAP) warp_flush<MODE == 1>(stage, stage_d, stage_n, P, lane);
+            emit_hits<MODE, (KIND >= 2)>(P, home, m0, n0, w, stage_n + (inc & 0xffff) - c0, stage, stage_d);
+            stage_n += t0;
         }
-        stage_n += total;
+        if (t1) {
+            if (stage_n + t1 > STAGE_CAP) warp_flush<MODE == 1>(stage, stage_d, stage_n, P, lane);
+            emit_hits<MODE, (KIND >= 2)>(P, home, m1, n1, w, stage_n + (inc >> 16) - c1, stage, stage_d);
+            stage_n += t1;
+        }
     }
 }
 
 // Is reference cell `cn` MASK-adjacent to `ch` along one dim, and is that adjacency a wrapped one?
 // Valid when every periodic dim has >= 3 reference cells (the kernel's precondition), where each
 // unordered adjacent cell pair appears exactly once in search_plan with a unique wrapped flag.
-__device__ __forceinline__ bool ref_adjacent(int ch, int cn, int dim, bool periodic, unsigned& wbit) {
+__device__ __forceinline__ bool ref_adjacent(int ch, int cn, int dim, bool periodic, unsigned& wbit,
+                                             unsigned& sbit) {
     int diff = abs(cn - ch);
     wbit = 0;
+    sbit = cn > ch ? 1u : 0u;  // wrapped: is the neighbour cell the one at the high end?
     if (diff <= 1) return true;
     if (periodic && diff == dim - 1) {
         wbit = 1;
@@ -412,7 +536,7 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32) search_cells_kernel(const _
                                                : make_float4(__int_as_float(0x7fc00000), 0.f, 0.f, 0.f);
             __syncwarp();
             // self cell: pairs inside the home cell, each once (sorted index order)
-            process_run<MODE, false, true>(P, home, nh, (int)hb, hs, he, 0u, stage, stage_d, stage_n, count, lane);
+            process_run<MODE, 1>(P, home, nh, (int)hb, hs, he, 0u, 0u, stage, stage_d, stage_n, count, lane);
 
             for (int r = 0; r < P.nrows; ++r) {
                 const NbrRow row = P.rows[r];
@@ -423,9 +547,9 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32) search_cells_kernel(const _
                 const int rl_n = nz * fdy + ny, rl_h = fz * fdy + fy;
                 if (rl_n < rl_h) continue;
                 const bool same_row = rl_n == rl_h;
-                unsigned wy, wz;
-                if (!ref_adjacent(cy, ny / g.k[1], g.dims[1], pery, wy)) continue;
-                if (!ref_adjacent(cz, nz / g.k[2], g.dims[2], perz, wz)) continue;
+                unsigned wy, wz, sy, sz;
+                if (!ref_adjacent(cy, ny / g.k[1], g.dims[1], pery, wy, sy)) continue;
+                if (!ref_adjacent(cz, nz / g.k[2], g.dims[2], perz, wz, sz)) continue;
                 const unsigned row_base = (unsigned)rl_n * (unsigned)fdx;
                 // x range, possibly split by the periodic boundary into <= 2 raw segments
                 int xa = fx + row.dxlo, xb = fx + row.dxhi;
@@ -448,37 +572,36 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32) search_cells_kernel(const _
                     if (lo > hi) continue;
                     // walk the reference x-cells the segment covers; merge runs with equal flags
                     int run_lo = -1, run_hi = -1;
-                    unsigned run_w = 0;
+                    unsigned run_w = 0, run_s = 0;
+                    auto flush_run = [&]() {
+                        if (run_lo < 0) return;
+                        unsigned s = P.cell_start[row_base + run_lo], e = P.cell_start[row_base + run_hi + 1];
+                        if (s < e) {
+                            if (!run_w) process_run<MODE, 0>(P, home, nh, (int)hb, s, e, 0u, 0u, stage, stage_d, stage_n, count, lane);
+                            else if (P.fast_pbc) process_run<MODE, 2>(P, home, nh, (int)hb, s, e, run_w, run_s, stage, stage_d, stage_n, count, lane);
+                            else process_run<MODE, 3>(P, home, nh, (int)hb, s, e, run_w, run_s, stage, stage_d, stage_n, count, lane);
+                        }
+                        run_lo = -1;
+                    };
                     for (int cxn = lo / g.k[0]; cxn <= hi / g.k[0]; ++cxn) {
-                        unsigned wx;
-                        bool adj = ref_adjacent(cx, cxn, g.dims[0], perx, wx);
+                        unsigned wx, sx;
+                        bool adj = ref_adjacent(cx, cxn, g.dims[0], perx, wx, sx);
                         int a = max(lo, cxn * g.k[0]), b = min(hi, cxn * g.k[0] + g.k[0] - 1);
                         unsigned w = wx | (wy << 1) | (wz << 2);
-                        if (adj && run_lo >= 0 && w == run_w) {
+                        unsigned sg = sx | (sy << 1) | (sz << 2);
+                        if (adj && run_lo >= 0 && w == run_w && ((sg ^ run_s) & w) == 0) {
                             run_hi = b;
                             continue;
                         }
-                        if (run_lo >= 0) {
-                            unsigned s = P.cell_start[row_base + run_lo], e = P.cell_start[row_base + run_hi + 1];
-                            if (s < e) {
-                                if (run_w) process_run<MODE, true, false>(P, home, nh, (int)hb, s, e, run_w, stage, stage_d, stage_n, count, lane);
-                                else process_run<MODE, false, false>(P, home, nh, (int)hb, s, e, 0u, stage, stage_d, stage_n, count, lane);
-                            }
-                            run_lo = -1;
-                        }
+                        flush_run();
                         if (adj) {
                             run_lo = a;
                             run_hi = b;
                             run_w = w;
+                            run_s = sg;
                         }
                     }
-                    if (run_lo >= 0) {
-                        unsigned s = P.cell_start[row_base + run_lo], e = P.cell_start[row_base + run_hi + 1];
-                        if (s < e) {
-                            if (run_w) process_run<MODE, true, false>(P, home, nh, (int)hb, s, e, run_w, stage, stage_d, stage_n, count, lane);
-                            else process_run<MODE, false, false>(P, home, nh, (int)hb, s, e, 0u, stage, stage_d, stage_n, count, lane);
-                        }
-                    }
+                    flush_run();
                 }
             }
         }
@@ -795,6 +918,8 @@ static double min_cell_dist2(const double M[3][3], const int delta[3]) {
 struct Plan {
     GridSpec g;
     bool use_cells;
+    int fast_pbc;
+    float rc2_lo, rc2_hi;
     int nrows;
     NbrRow rows[MAX_ROWS];
     size_t ncells;
@@ -917,6 +1042,49 @@ static void plan_cells(const Ctx* c, Plan& pl, float cutoff, size_t n) {
         }
         pl.ncells = ncells;
         pl.use_cells = true;
+        // Shifted-image filter for wrapped cell pairs (process_run KIND 2).  Sound when
+        //  (a) every periodic dim has >= 4 reference cells, so the reference's round() of the
+        //      fractional difference of two atoms in wrapped-adjacent cells is always +-1, and
+        //  (b) every periodic dim's perpendicular box width exceeds 2.01*cutoff, so no OTHER image
+        //      (including the triclinic corrections, periodic_box.rs:299-317) can be within cutoff.
+        // Then d2 from the shifted difference and the reference's d2 approximate the same real
+        // number; |difference| <= eps (bound below), and only tests inside [rc2-eps, rc2+eps] are
+        // re-evaluated with the reference's exact arithmetic.
+        pl.fast_pbc = 0;
+        pl.rc2_lo = pl.rc2_hi = cutoff * cutoff;
+        if (g.periodic_variant && !c->opt_exact_pbc) {
+            bool ok2 = true;
+            double Mb[3][3], tb[3];
+            for (int r = 0; r < 3; ++r)
+                for (int col = 0; col < 3; ++col) Mb[r][col] = g.box.m[r * 3 + col];
+            thickness(Mb, tb);
+            double lsum = 0, kappa = 1.0;
+            for (int r = 0; r < 3; ++r) {
+                double rowsum = 0;
+                for (int col = 0; col < 3; ++col) {
+                    lsum += std::fabs((double)g.box.m[r * 3 + col]);
+                    double acc = 0;
+                    for (int q = 0; q < 3; ++q) acc += std::fabs((double)g.box.m[r * 3 + q]) * std::fabs((double)g.box.inv[q * 3 + col]);
+                    rowsum += acc;
+                }
+                kappa = std::max(kappa, rowsum);
+            }
+            for (int d = 0; d < 3; ++d)
+                if ((g.pbc >> d) & 1u) {
+                    if (g.dims[d] < 4) ok2 = false;
+                    if (!(tb[d] > 2.01 * rc)) ok2 = false;
+                }
+            const double u = 5.9604644775390625e-08;
+            double E = 64.0 * u * kappa * (lsum + rc);
+            double eps = 2.0 * rc * E + E * E;
+            double rc2d = (double)(cutoff * cutoff);
+            if (!(eps < 0.004 * rc2d)) ok2 = false;
+            if (ok2) {
+                pl.fast_pbc = 1;
+                pl.rc2_lo = (float)(rc2d - eps) * (1.0f - 2e-7f);
+                pl.rc2_hi = (float)(rc2d + eps) * (1.0f + 2e-7f);
+            }
+        }
         return;
     }
 }
@@ -927,7 +1095,7 @@ struct PlanKey {
     unsigned pbc;
     size_t n;
     float m[9];
-    int subdiv, brute;
+    int subdiv, brute, exact_pbc;
     double apc;
 };
 struct PlanCache {
@@ -1009,6 +1177,7 @@ static int get_plan_pbc(Ctx* c, float cutoff, uint8_t pbc, size_t n, Plan& out) 
         for (int col = 0; col < 3; ++col) k.m[r * 3 + col] = c->box.m[r][col];
     k.subdiv = c->opt_subdiv;
     k.brute = c->opt_force_brute;
+    k.exact_pbc = c->opt_exact_pbc;
     k.apc = c->opt_atoms_per_cell;
     PlanCache* pc = static_cast<PlanCache*>(c->plan_cache);
     if (!pc) {
@@ -1121,6 +1290,9 @@ int enqueue_cells_search(Ctx* c, const float* xyz, const unsigned long long* d_i
     P.cell_start = c->cell_start.as<unsigned>();
     P.g = g;
     P.rc2 = cutoff * cutoff;
+    P.rc2_lo = pl.rc2_lo;
+    P.rc2_hi = pl.rc2_hi;
+    P.fast_pbc = pl.fast_pbc;
     P.nrows = pl.nrows;
     memcpy(P.rows, pl.rows, sizeof(NbrRow) * pl.nrows);
     P.pairs = c->pairs.as<uint2>();

@@ -210,4 +210,27 @@ def test_config3_1m_triclinic_properties(mb):
     t.set_option("subdiv", 1)
     counts1, chk1 = t.search(1.2, f0=0, f1=1, checksums=True)
     assert counts1[0] == counts[0] and np.array_equal(chk1[0], chk[0])
+    # the shifted-image filter for wrapped cell pairs must decide exactly like the reference's
+    # PeriodicBox::distance_squared evaluated for every pair
+    t.set_option("subdiv", 0)
+    t.set_option("exact_pbc", 1)
+    counts2, chk2 = t.search(1.2, f0=0, f1=2, checksums=True)
+    assert np.array_equal(counts2, counts) and np.array_equal(chk2, chk)
     t.close()
+
+
+@pytest.mark.parametrize("exact", [0, 1])
+def test_single_pbc_big_box_filter_vs_exact_path(mb, exact):
+    """Boxes large enough for the wrapped-pair filter (>= 4 reference cells per dim), strays
+    included, against the oracle."""
+    M = (TRIC * np.float32(0.45)).astype(np.float32)
+    xyz = orc.synth_frame(SEED + 11, 0, 90000, M, stray_permille=20)
+    op, od, dims = oracle_single(1.2, xyz, box=M, pbc=7, nthreads=8)
+    assert min(dims) >= 4
+    gp, gd = run_single(mb, xyz, 1.2, box=M, dims=[True] * 3, exact_pbc=exact)
+    assert_same_pairs(gp, gd, op, od)
+    Mo = np.diag([9.7, 10.3, 11.1]).astype(np.float32)
+    xyz = orc.synth_frame(SEED + 12, 0, 100000, Mo, stray_permille=20)
+    op, od, dims = oracle_single(1.2, xyz, box=Mo, pbc=7, nthreads=8)
+    gp, gd = run_single(mb, xyz, 1.2, box=Mo, dims=[True] * 3, exact_pbc=exact)
+    assert_same_pairs(gp, gd, op, od)
