@@ -336,6 +336,13 @@ __device__ __forceinline__ void d2_pair(unsigned long long nx, unsigned long lon
     d1 = xadd(xadd(x1, y1), z1);
 }
 
+// Out-of-line copy of the exact periodic distance for the rare paths of the cell kernel (band
+// resolution, distance output of wrapped pairs): keeps the hot loop inside the instruction cache.
+__device__ __noinline__ float d2_pbc_call(const DevBox& bx, float ax, float ay, float az, float bxx, float byy,
+                                          float bzz, unsigned w) {
+    return d2_pbc(bx, ax, ay, az, bxx, byy, bzz, w);
+}
+
 // Emit the pairs of one neighbour atom per lane (bit j of `mask` = hit against home atom j).
 template <int MODE, bool PBCW>
 __device__ __forceinline__ void emit_hits(const SearchParams& P, const float4* __restrict__ home, unsigned mask,
@@ -348,7 +355,7 @@ __device__ __forceinline__ void emit_hits(const SearchParams& P, const float4* _
         const unsigned hid = __float_as_uint(h.w);
         stage[off] = make_uint2(min(hid, nid), max(hid, nid));
         if (MODE == 1) {
-            float d2 = PBCW ? d2_pbc(P.g.box, h.x, h.y, h.z, nb.x, nb.y, nb.z, w)
+            float d2 = PBCW ? d2_pbc_call(P.g.box, h.x, h.y, h.z, nb.x, nb.y, nb.z, w)
                             : d2_direct(h.x, h.y, h.z, nb.x, nb.y, nb.z);
             stage_d[off] = __fsqrt_rn(d2);
         }
@@ -362,11 +369,19 @@ __device__ __forceinline__ void emit_hits(const SearchParams& P, const float4* _
 //       2 wrapped cell pair, fast filter (shifted image + exact re-check in a band around cutoff^2),
 //       3 wrapped cell pair, exact PeriodicBox::distance_squared for every test.
 // MODE: 0 pairs, 1 pairs + distances, 2 count only
+// Not inlined on purpose: the kernel calls it from several places and the instruction cache (~32 KB)
+// must hold the whole hot loop; a first version that inlined every instantiation spent most of
+// its time in `no_instruction` stalls (profiles/ncu_search_r1a.txt).
+struct RunState {
+    int stage_n;
+    unsigned long long count;
+};
 template <int MODE, int KIND>
-__device__ __forceinline__ void process_run(const SearchParams& P, const float4* __restrict__ home, int nh,
-                                            int hb, unsigned s, unsigned e, unsigned w, unsigned wsgn,
-                                            uint2* stage, float* stage_d, int& stage_n,
-                                            unsigned long long& count, unsigned lane) {
+__device__ __noinline__ RunState process_run(const SearchParams& P, const float4* __restrict__ home, int nh,
+                                             int hb, unsigned s, unsigned e, unsigned w, unsigned wsgn,
+                                             uint2* stage, float* stage_d, RunState st, unsigned lane) {
+    int stage_n = st.stage_n;
+    unsigned long long count = st.count;
     const float rc2 = P.rc2;
     const float qnan = __int_as_float(0x7fc00000);
     float sx = 0.f, sy = 0.f, sz = 0.f;
@@ -392,24 +407,28 @@ __device__ __forceinline__ void process_run(const SearchParams& P, const float4*
             const unsigned long long nx = pk2(n0.x + sx, n1.x + sx), ny = pk2(n0.y + sy, n1.y + sy),
                                      nz = pk2(n0.z + sz, n1.z + sz);
             unsigned a0 = 0, a1 = 0;  // KIND 2: possible hits (superset), m0/m1 = certain hits
+            for (int g = 0; g < nh; g += 8) {
+                unsigned l0 = 0, l1 = 0, b0 = 0, b1 = 0;
 #pragma unroll
-            for (int j0 = 0; j0 < 32; j0 += 4) {
-                if (j0 >= nh) break;
-#pragma unroll
-                for (int jj = 0; jj < 4; ++jj) {
-                    const int j = j0 + jj;
-                    const float4 h = home[j];
+                for (int jj = 0; jj < 8; ++jj) {
+                    const float4 h = home[g + jj];
                     float d0, d1;
                     d2_pair(nx, ny, nz, h, d0, d1);
                     if (KIND == 0) {
-                        if (d0 <= rc2) m0 |= 1u << j;
-                        if (d1 <= rc2) m1 |= 1u << j;
+                        if (d0 <= rc2) l0 |= 1u << jj;
+                        if (d1 <= rc2) l1 |= 1u << jj;
                     } else {
-                        if (d0 <= P.rc2_lo) m0 |= 1u << j;
-                        if (d1 <= P.rc2_lo) m1 |= 1u << j;
-                        if (d0 <= P.rc2_hi) a0 |= 1u << j;
-                        if (d1 <= P.rc2_hi) a1 |= 1u << j;
+                        if (d0 <= P.rc2_lo) l0 |= 1u << jj;
+                        if (d1 <= P.rc2_lo) l1 |= 1u << jj;
+                        if (d0 <= P.rc2_hi) b0 |= 1u << jj;
+                        if (d1 <= P.rc2_hi) b1 |= 1u << jj;
                     }
+                }
+                m0 |= l0 << g;
+                m1 |= l1 << g;
+                if (KIND == 2) {
+                    a0 |= b0 << g;
+                    a1 |= b1 << g;
                 }
             }
             if (KIND == 2) {
@@ -421,13 +440,13 @@ __device__ __forceinline__ void process_run(const SearchParams& P, const float4*
                         const int j = 31 - __clz(a0);
                         a0 ^= 1u << j;
                         const float4 h = home[j];
-                        if (d2_pbc(P.g.box, h.x, h.y, h.z, n0.x, n0.y, n0.z, w) <= rc2) m0 |= 1u << j;
+                        if (d2_pbc_call(P.g.box, h.x, h.y, h.z, n0.x, n0.y, n0.z, w) <= rc2) m0 |= 1u << j;
                     }
                     while (a1) {
                         const int j = 31 - __clz(a1);
                         a1 ^= 1u << j;
                         const float4 h = home[j];
-                        if (d2_pbc(P.g.box, h.x, h.y, h.z, n1.x, n1.y, n1.z, w) <= rc2) m1 |= 1u << j;
+                        if (d2_pbc_call(P.g.box, h.x, h.y, h.z, n1.x, n1.y, n1.z, w) <= rc2) m1 |= 1u << j;
                     }
                 }
             }
@@ -437,8 +456,8 @@ __device__ __forceinline__ void process_run(const SearchParams& P, const float4*
                 const float4 h = home[j];
                 float d0, d1;
                 if (KIND == 3) {
-                    d0 = d2_pbc(P.g.box, h.x, h.y, h.z, n0.x, n0.y, n0.z, w);
-                    d1 = d2_pbc(P.g.box, h.x, h.y, h.z, n1.x, n1.y, n1.z, w);
+                    d0 = d2_pbc_call(P.g.box, h.x, h.y, h.z, n0.x, n0.y, n0.z, w);
+                    d1 = d2_pbc_call(P.g.box, h.x, h.y, h.z, n1.x, n1.y, n1.z, w);
                 } else {
                     d0 = d2_direct(h.x, h.y, h.z, n0.x, n0.y, n0.z);
                     d1 = d2_direct(h.x, h.y, h.z, n1.x, n1.y, n1.z);
@@ -477,6 +496,19 @@ __device__ __forceinline__ void process_run(const SearchParams& P, const float4*
             stage_n += t1;
         }
     }
+    return RunState{stage_n, count};
+}
+
+template <int MODE>
+__device__ __noinline__ RunState run_dispatch(const SearchParams& P, const float4* __restrict__ home, int nh, int hb,
+                                              unsigned s, unsigned e, unsigned w, unsigned wsgn, int kind,
+                                              uint2* stage, float* stage_d, RunState st, unsigned lane) {
+    switch (kind) {
+        case 0: return process_run<MODE, 0>(P, home, nh, hb, s, e, w, wsgn, stage, stage_d, st, lane);
+        case 1: return process_run<MODE, 1>(P, home, nh, hb, s, e, w, wsgn, stage, stage_d, st, lane);
+        case 2: return process_run<MODE, 2>(P, home, nh, hb, s, e, w, wsgn, stage, stage_d, st, lane);
+        default: return process_run<MODE, 3>(P, home, nh, hb, s, e, w, wsgn, stage, stage_d, st, lane);
+    }
 }
 
 // Is reference cell `cn` MASK-adjacent to `ch` along one dim, and is that adjacency a wrapped one?
@@ -499,7 +531,7 @@ __device__ __forceinline__ bool ref_adjacent(int ch, int cn, int dim, bool perio
 // broadcast (one LDS.128 per test column); the 32 lanes each own one neighbour atom of a
 // contiguous run of the sorted array, loaded as one coalesced float4 stream.
 template <int MODE>
-__global__ void __launch_bounds__(SEARCH_WARPS * 32) search_cells_kernel(const __grid_constant__ SearchParams P) {
+__global__ void __launch_bounds__(SEARCH_WARPS * 32, MODE == 1 ? 2 : 3) search_cells_kernel(const __grid_constant__ SearchParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const unsigned lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
     float4* home = reinterpret_cast<float4*>(smem_raw) + wid * 32;
@@ -512,8 +544,7 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32) search_cells_kernel(const _
                                                SEARCH_WARPS * STAGE_CAP * sizeof(uint2)) +
                       wid * STAGE_CAP;
     }
-    int stage_n = 0;
-    unsigned long long count = 0;
+    RunState st{0, 0ull};
     const GridSpec& g = P.g;
     const int fdx = g.fd[0], fdy = g.fd[1], fdz = g.fd[2];
     const unsigned ncells = (unsigned)(fdx * fdy * fdz);
@@ -536,8 +567,9 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32) search_cells_kernel(const _
                                                : make_float4(__int_as_float(0x7fc00000), 0.f, 0.f, 0.f);
             __syncwarp();
             // self cell: pairs inside the home cell, each once (sorted index order)
-            process_run<MODE, 1>(P, home, nh, (int)hb, hs, he, 0u, 0u, stage, stage_d, stage_n, count, lane);
+            st = run_dispatch<MODE>(P, home, nh, (int)hb, hs, he, 0u, 0u, 1, stage, stage_d, st, lane);
 
+#pragma unroll 1
             for (int r = 0; r < P.nrows; ++r) {
                 const NbrRow row = P.rows[r];
                 int ny = fy + row.dy, nz = fz + row.dz;
@@ -566,6 +598,7 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32) search_cells_kernel(const _
                 else if (xa <= xb) {
                     // both ends wrapped and a middle part: cannot happen when fdx >= 2R+1
                 }
+#pragma unroll 1
                 for (int sg = 0; sg < nseg; ++sg) {
                     int lo = seg_lo[sg], hi = seg_hi[sg];
                     if (same_row) lo = max(lo, fx + 1);
@@ -573,45 +606,45 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32) search_cells_kernel(const _
                     // walk the reference x-cells the segment covers; merge runs with equal flags
                     int run_lo = -1, run_hi = -1;
                     unsigned run_w = 0, run_s = 0;
-                    auto flush_run = [&]() {
-                        if (run_lo < 0) return;
-                        unsigned s = P.cell_start[row_base + run_lo], e = P.cell_start[row_base + run_hi + 1];
-                        if (s < e) {
-                            if (!run_w) process_run<MODE, 0>(P, home, nh, (int)hb, s, e, 0u, 0u, stage, stage_d, stage_n, count, lane);
-                            else if (P.fast_pbc) process_run<MODE, 2>(P, home, nh, (int)hb, s, e, run_w, run_s, stage, stage_d, stage_n, count, lane);
-                            else process_run<MODE, 3>(P, home, nh, (int)hb, s, e, run_w, run_s, stage, stage_d, stage_n, count, lane);
-                        }
-                        run_lo = -1;
-                    };
-                    for (int cxn = lo / g.k[0]; cxn <= hi / g.k[0]; ++cxn) {
-                        unsigned wx, sx;
-                        bool adj = ref_adjacent(cx, cxn, g.dims[0], perx, wx, sx);
-                        int a = max(lo, cxn * g.k[0]), b = min(hi, cxn * g.k[0] + g.k[0] - 1);
-                        unsigned w = wx | (wy << 1) | (wz << 2);
-                        unsigned sg = sx | (sy << 1) | (sz << 2);
-                        if (adj && run_lo >= 0 && w == run_w && ((sg ^ run_s) & w) == 0) {
+                    const int c_last = hi / g.k[0];
+                    // one extra (sentinel) iteration flushes the last run: a single call site
+#pragma unroll 1
+                    for (int cxn = lo / g.k[0]; cxn <= c_last + 1; ++cxn) {
+                        unsigned wx = 0, sx = 0;
+                        const bool adj = cxn <= c_last && ref_adjacent(cx, cxn, g.dims[0], perx, wx, sx);
+                        const int a = max(lo, cxn * g.k[0]), b = min(hi, cxn * g.k[0] + g.k[0] - 1);
+                        const unsigned w = wx | (wy << 1) | (wz << 2);
+                        const unsigned sg2 = sx | (sy << 1) | (sz << 2);
+                        if (adj && run_lo >= 0 && w == run_w && ((sg2 ^ run_s) & w) == 0) {
                             run_hi = b;
                             continue;
                         }
-                        flush_run();
+                        if (run_lo >= 0) {
+                            const unsigned s = P.cell_start[row_base + run_lo], e = P.cell_start[row_base + run_hi + 1];
+                            if (s < e) {
+                                const int kind = !run_w ? 0 : (P.fast_pbc ? 2 : 3);
+                                st = run_dispatch<MODE>(P, home, nh, (int)hb, s, e, run_w, run_s, kind, stage, stage_d, st, lane);
+                            }
+                            run_lo = -1;
+                        }
                         if (adj) {
                             run_lo = a;
                             run_hi = b;
                             run_w = w;
-                            run_s = sg;
+                            run_s = sg2;
                         }
                     }
-                    flush_run();
                 }
             }
         }
     }
     if (MODE == 2) {
+        unsigned long long count = st.count;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) count += __shfl_xor_sync(0xffffffffu, count, o);
         if (lane == 0 && count) atomicAdd(P.counter, count);
     } else {
-        warp_flush<MODE == 1>(stage, stage_d, stage_n, P, lane);
+        warp_flush<MODE == 1>(stage, stage_d, st.stage_n, P, lane);
     }
 }
 
