@@ -40,6 +40,7 @@ struct GridSpec {
     unsigned pbc;          // PbcDims bits
     int dims[3];           // reference Grid::dims
     int k[3];              // subdivision
+    unsigned kmagic[3];    // floor(2^32 / k) + 1 (unused for k == 1)
     int fd[3];             // fine dims
     float lower[3];        // non-periodic variant: bounds
     float dim_sz[3];
@@ -292,9 +293,11 @@ __device__ __forceinline__ void warp_flush(uint2* stage, float* stage_d, int& st
     if (lane == 0) base = atomicAdd(P.counter, (unsigned long long)stage_n);
     base = __shfl_sync(0xffffffffu, base, 0);
     if (base + (unsigned long long)stage_n <= P.pair_cap) {
-        for (int i = lane; i < stage_n; i += 32) {
-            P.pairs[base + i] = stage[i];
-            if (DIST) P.dists[base + i] = stage_d[i];
+        uint2* __restrict__ dst = P.pairs + base;
+        for (int i = lane; i < stage_n; i += 32) dst[i] = stage[i];
+        if (DIST) {
+            float* __restrict__ dd = P.dists + base;
+            for (int i = lane; i < stage_n; i += 32) dd[i] = stage_d[i];
         }
     }
     __syncwarp();
@@ -323,6 +326,11 @@ __device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigne
     asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
     return r;
 }
+__device__ __forceinline__ int bfind32(unsigned m) {
+    int r;
+    asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(m));
+    return r;
+}
 // squared distances of two neighbours (packed) to one home atom: (dx*dx + dy*dy) + dz*dz, unfused
 __device__ __forceinline__ void d2_pair(unsigned long long nx, unsigned long long ny, unsigned long long nz,
                                         const float4& h, float& d0, float& d1) {
@@ -343,173 +351,8 @@ __device__ __noinline__ float d2_pbc_call(const DevBox& bx, float ax, float ay, 
     return d2_pbc(bx, ax, ay, az, bxx, byy, bzz, w);
 }
 
-// Emit the pairs of one neighbour atom per lane (bit j of `mask` = hit against home atom j).
-template <int MODE, bool PBCW>
-__device__ __forceinline__ void emit_hits(const SearchParams& P, const float4* __restrict__ home, unsigned mask,
-                                          const float4& nb, unsigned w, int off, uint2* stage, float* stage_d) {
-    const unsigned nid = __float_as_uint(nb.w);
-    while (mask) {
-        const int j = 31 - __clz(mask);
-        mask ^= 1u << j;
-        const float4 h = home[j];
-        const unsigned hid = __float_as_uint(h.w);
-        stage[off] = make_uint2(min(hid, nid), max(hid, nid));
-        if (MODE == 1) {
-            float d2 = PBCW ? d2_pbc_call(P.g.box, h.x, h.y, h.z, nb.x, nb.y, nb.z, w)
-                            : d2_direct(h.x, h.y, h.z, nb.x, nb.y, nb.z);
-            stage_d[off] = __fsqrt_rn(d2);
-        }
-        ++off;
-    }
-}
-
-// One contiguous run [s,e) of neighbour atoms against the home batch.  Each lane owns TWO neighbour
-// atoms (64 per warp step, two coalesced float4 streams); home atoms are broadcast from shared memory.
-// KIND: 0 direct difference, 1 direct + self filter (home cell against itself),
-//       2 wrapped cell pair, fast filter (shifted image + exact re-check in a band around cutoff^2),
-//       3 wrapped cell pair, exact PeriodicBox::distance_squared for every test.
-// MODE: 0 pairs, 1 pairs + distances, 2 count only
-// Not inlined on purpose: the kernel calls it from several places and the instruction cache (~32 KB)
-// must hold the whole hot loop; a first version that inlined every instantiation spent most of
-// its time in `no_instruction` stalls (profiles/ncu_search_r1a.txt).
-struct RunState {
-    int stage_n;
-    unsigned long long count;
-};
-template <int MODE, int KIND>
-__device__ __noinline__ RunState process_run(const SearchParams& P, const float4* __restrict__ home, int nh,
-                                             int hb, unsigned s, unsigned e, unsigned w, unsigned wsgn,
-                                             uint2* stage, float* stage_d, RunState st, unsigned lane) {
-    int stage_n = st.stage_n;
-    unsigned long long count = st.count;
-    const float rc2 = P.rc2;
-    const float qnan = __int_as_float(0x7fc00000);
-    float sx = 0.f, sy = 0.f, sz = 0.f;
-    if (KIND == 2) {
-        // lattice shift that maps the neighbour image the reference's rounding selects:
-        // neighbour cell above the home cell (wsgn bit set) => n_d = +1 => subtract column d
-#pragma unroll
-        for (int d = 0; d < 3; ++d)
-            if ((w >> d) & 1u) {
-                float sg = ((wsgn >> d) & 1u) ? -1.0f : 1.0f;
-                sx += sg * P.g.box.m[d];
-                sy += sg * P.g.box.m[3 + d];
-                sz += sg * P.g.box.m[6 + d];
-            }
-    }
-    for (unsigned base = s; base < e; base += 64) {
-        const unsigned ni0 = base + lane, ni1 = base + 32 + lane;
-        float4 n0 = make_float4(qnan, 0.f, 0.f, 0.f), n1 = n0;  // NaN: never within cutoff
-        if (ni0 < e) n0 = __ldg(&P.sorted[ni0]);
-        if (ni1 < e) n1 = __ldg(&P.sorted[ni1]);
-        unsigned m0 = 0, m1 = 0;
-        if (KIND == 0 || KIND == 2) {
-            const unsigned long long nx = pk2(n0.x + sx, n1.x + sx), ny = pk2(n0.y + sy, n1.y + sy),
-                                     nz = pk2(n0.z + sz, n1.z + sz);
-            unsigned a0 = 0, a1 = 0;  // KIND 2: possible hits (superset), m0/m1 = certain hits
-            for (int g = 0; g < nh; g += 8) {
-                unsigned l0 = 0, l1 = 0, b0 = 0, b1 = 0;
-#pragma unroll
-                for (int jj = 0; jj < 8; ++jj) {
-                    const float4 h = home[g + jj];
-                    float d0, d1;
-                    d2_pair(nx, ny, nz, h, d0, d1);
-                    if (KIND == 0) {
-                        if (d0 <= rc2) l0 |= 1u << jj;
-                        if (d1 <= rc2) l1 |= 1u << jj;
-                    } else {
-                        if (d0 <= P.rc2_lo) l0 |= 1u << jj;
-                        if (d1 <= P.rc2_lo) l1 |= 1u << jj;
-                        if (d0 <= P.rc2_hi) b0 |= 1u << jj;
-                        if (d1 <= P.rc2_hi) b1 |= 1u << jj;
-                    }
-                }
-                m0 |= l0 << g;
-                m1 |= l1 << g;
-                if (KIND == 2) {
-                    a0 |= b0 << g;
-                    a1 |= b1 << g;
-                }
-            }
-            if (KIND == 2) {
-                a0 ^= m0;
-                a1 ^= m1;
-                if (__any_sync(0xffffffffu, (a0 | a1) != 0u)) {
-                    // within the rounding band of cutoff^2: decide with the reference's own arithmetic
-                    while (a0) {
-                        const int j = 31 - __clz(a0);
-                        a0 ^= 1u << j;
-                        const float4 h = home[j];
-                        if (d2_pbc_call(P.g.box, h.x, h.y, h.z, n0.x, n0.y, n0.z, w) <= rc2) m0 |= 1u << j;
-                    }
-                    while (a1) {
-                        const int j = 31 - __clz(a1);
-                        a1 ^= 1u << j;
-                        const float4 h = home[j];
-                        if (d2_pbc_call(P.g.box, h.x, h.y, h.z, n1.x, n1.y, n1.z, w) <= rc2) m1 |= 1u << j;
-                    }
-                }
-            }
-        } else {
-            const int nh4 = (nh + 3) & ~3;
-            for (int j = 0; j < nh4; ++j) {
-                const float4 h = home[j];
-                float d0, d1;
-                if (KIND == 3) {
-                    d0 = d2_pbc_call(P.g.box, h.x, h.y, h.z, n0.x, n0.y, n0.z, w);
-                    d1 = d2_pbc_call(P.g.box, h.x, h.y, h.z, n1.x, n1.y, n1.z, w);
-                } else {
-                    d0 = d2_direct(h.x, h.y, h.z, n0.x, n0.y, n0.z);
-                    d1 = d2_direct(h.x, h.y, h.z, n1.x, n1.y, n1.z);
-                }
-                bool h0 = d0 <= rc2, h1 = d1 <= rc2;
-                if (KIND == 1) {
-                    h0 = h0 && (ni0 > (unsigned)(hb + j));
-                    h1 = h1 && (ni1 > (unsigned)(hb + j));
-                }
-                m0 |= (h0 ? 1u : 0u) << j;
-                m1 |= (h1 ? 1u : 0u) << j;
-            }
-        }
-        const int c0 = __popc(m0), c1 = __popc(m1);
-        if (MODE == 2) {
-            count += c0 + c1;
-            continue;
-        }
-        // one scan for both halves: low 16 bits = first atom, high 16 bits = second atom
-        int inc = c0 | (c1 << 16);
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            int t = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= (unsigned)o) inc += t;
-        }
-        const int tot = __shfl_sync(0xffffffffu, inc, 31);
-        const int t0 = tot & 0xffff, t1 = tot >> 16;
-        if (t0) {
-            if (stage_n + t0 > STAGE_CAP) warp_flush<MODE == 1>(stage, stage_d, stage_n, P, lane);
-            emit_hits<MODE, (KIND >= 2)>(P, home, m0, n0, w, stage_n + (inc & 0xffff) - c0, stage, stage_d);
-            stage_n += t0;
-        }
-        if (t1) {
-            if (stage_n + t1 > STAGE_CAP) warp_flush<MODE == 1>(stage, stage_d, stage_n, P, lane);
-            emit_hits<MODE, (KIND >= 2)>(P, home, m1, n1, w, stage_n + (inc >> 16) - c1, stage, stage_d);
-            stage_n += t1;
-        }
-    }
-    return RunState{stage_n, count};
-}
-
-template <int MODE>
-__device__ __noinline__ RunState run_dispatch(const SearchParams& P, const float4* __restrict__ home, int nh, int hb,
-                                              unsigned s, unsigned e, unsigned w, unsigned wsgn, int kind,
-                                              uint2* stage, float* stage_d, RunState st, unsigned lane) {
-    switch (kind) {
-        case 0: return process_run<MODE, 0>(P, home, nh, hb, s, e, w, wsgn, stage, stage_d, st, lane);
-        case 1: return process_run<MODE, 1>(P, home, nh, hb, s, e, w, wsgn, stage, stage_d, st, lane);
-        case 2: return process_run<MODE, 2>(P, home, nh, hb, s, e, w, wsgn, stage, stage_d, st, lane);
-        default: return process_run<MODE, 3>(P, home, nh, hb, s, e, w, wsgn, stage, stage_d, st, lane);
-    }
-}
+// x / k for the small subdivision factors (k <= 8): magic = floor(2^32 / k) + 1, exact for x < 2^32 / k
+__device__ __forceinline__ int div_k(int x, int k, unsigned magic) { return k == 1 ? x : (int)__umulhi((unsigned)x, magic); }
 
 // Is reference cell `cn` MASK-adjacent to `ch` along one dim, and is that adjacency a wrapped one?
 // Valid when every periodic dim has >= 3 reference cells (the kernel's precondition), where each
@@ -527,28 +370,102 @@ __device__ __forceinline__ bool ref_adjacent(int ch, int cn, int dim, bool perio
     return false;
 }
 
-// One warp per home fine cell (dynamic work counter).  Home atoms sit in shared memory and are
-// broadcast (one LDS.128 per test column); the 32 lanes each own one neighbour atom of a
-// contiguous run of the sorted array, loaded as one coalesced float4 stream.
+// Runs of one neighbour row (dy,dz,[dxlo,dxhi]) of home fine cell (fx,fy,fz): contiguous x-ranges of
+// fine cells that lie in reference cells MASK-adjacent to the home reference cell, each with a
+// uniform wrapped-dims flag.  emit(first_cell, last_cell, flag) with flag = w | sgn << 3.
+template <class F>
+__device__ __forceinline__ void gen_row_runs(const GridSpec& g, int fx, int fy, int fz, int cx, int cy, int cz,
+                                             NbrRow row, F&& emit) {
+    const int fdx = g.fd[0], fdy = g.fd[1], fdz = g.fd[2];
+    const bool perx = g.pbc & 1u, pery = g.pbc & 2u, perz = g.pbc & 4u;
+    int ny = fy + row.dy, nz = fz + row.dz;
+    if (ny < 0) { if (!pery) return; ny += fdy; } else if (ny >= fdy) { if (!pery) return; ny -= fdy; }
+    if (nz < 0) { if (!perz) return; nz += fdz; } else if (nz >= fdz) { if (!perz) return; nz -= fdz; }
+    unsigned wy, wz, sy, sz;
+    if (!ref_adjacent(cy, div_k(ny, g.k[1], g.kmagic[1]), g.dims[1], pery, wy, sy)) return;
+    if (!ref_adjacent(cz, div_k(nz, g.k[2], g.kmagic[2]), g.dims[2], perz, wz, sz)) return;
+    const int row_base = (nz * fdy + ny) * fdx;
+    // x range, possibly split by the periodic boundary into <= 2 raw segments
+    int xa = fx + row.dxlo, xb = fx + row.dxhi;
+    int seg_lo0 = 0, seg_hi0 = -1, seg_lo1 = 0, seg_hi1 = -1;
+    if (xa < 0) {
+        if (perx) { seg_lo0 = xa + fdx; seg_hi0 = min(xb, -1) + fdx; }
+        xa = 0;
+    }
+    if (xb >= fdx) {
+        if (perx) { seg_lo1 = max(xa, fdx) - fdx; seg_hi1 = xb - fdx; }
+        xb = fdx - 1;
+    }
+    const int kx = g.k[0];
+#pragma unroll 1
+    for (int sg = 0; sg < 3; ++sg) {
+        const int lo = sg == 0 ? seg_lo0 : (sg == 1 ? seg_lo1 : xa);
+        const int hi = sg == 0 ? seg_hi0 : (sg == 1 ? seg_hi1 : xb);
+        if (lo > hi) continue;
+        int run_lo = -1, run_hi = -1;
+        unsigned run_f = 0;
+        const int c_first = div_k(lo, kx, g.kmagic[0]), c_last = div_k(hi, kx, g.kmagic[0]);
+#pragma unroll 1
+        for (int cxn = c_first; cxn <= c_last + 1; ++cxn) {  // one sentinel iteration flushes the last run
+            unsigned wx = 0, sx = 0;
+            const bool adj = cxn <= c_last && ref_adjacent(cx, cxn, g.dims[0], perx, wx, sx);
+            const int a = max(lo, cxn * kx), b = min(hi, cxn * kx + kx - 1);
+            const unsigned w = wx | (wy << 1) | (wz << 2);
+            const unsigned f = w | ((((sx | (sy << 1) | (sz << 2))) & w) << 3);
+            if (adj && run_lo >= 0 && f == run_f) {
+                run_hi = b;
+                continue;
+            }
+            if (run_lo >= 0) emit(row_base + run_lo, row_base + run_hi, run_f);
+            run_lo = -1;
+            if (adj) {
+                run_lo = a;
+                run_hi = b;
+                run_f = f;
+            }
+        }
+    }
+}
+
+constexpr int MAX_RUNS = 224;        // >= 1 + 32 rows * 6 runs
+constexpr unsigned RUN_SELF = 0x40u;  // flag bit: the home cell itself (pairs counted once by index order)
+
+// per-warp shared memory
+struct __align__(16) WarpShared {
+    float4 home[32];                 // home batch (position + id bits), NaN padded
+    unsigned rstart[MAX_RUNS];       // first atom (index into sorted4) of each run
+    unsigned rpos[MAX_RUNS + 4];     // stream position of each run (exclusive prefix of run lengths)
+    unsigned char rflag[MAX_RUNS];   // w | sgn << 3 | RUN_SELF
+};
+
+// One warp per home fine cell (dynamic work counter).
+//  Phase A  lanes work on different neighbour rows in parallel and build a table of runs: contiguous
+//           ranges of the sorted atom array (self cell, then direct runs, then wrapped runs).
+//  Phase B  the concatenation of the runs is one stream of candidate atoms; it is consumed 64 atoms
+//           per step (two per lane, two coalesced float4 loads), tested against the home atoms that
+//           are broadcast from shared memory (one LDS.128 per home atom), hits are kept as per-lane
+//           bit masks and expanded into the staging buffer afterwards.
+// MODE: 0 pairs, 1 pairs + distances, 2 count only
 template <int MODE>
-__global__ void __launch_bounds__(SEARCH_WARPS * 32, MODE == 1 ? 2 : 3) search_cells_kernel(const __grid_constant__ SearchParams P) {
+__global__ void __launch_bounds__(SEARCH_WARPS * 32, 2) search_cells_kernel(const __grid_constant__ SearchParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const unsigned lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
-    float4* home = reinterpret_cast<float4*>(smem_raw) + wid * 32;
-    uint2* stage = nullptr;
-    float* stage_d = nullptr;
-    if (MODE != 2) {
-        stage = reinterpret_cast<uint2*>(smem_raw + SEARCH_WARPS * 32 * sizeof(float4)) + wid * STAGE_CAP;
-        if (MODE == 1)
-            stage_d = reinterpret_cast<float*>(smem_raw + SEARCH_WARPS * 32 * sizeof(float4) +
-                                               SEARCH_WARPS * STAGE_CAP * sizeof(uint2)) +
-                      wid * STAGE_CAP;
-    }
-    RunState st{0, 0ull};
+    WarpShared& ws = reinterpret_cast<WarpShared*>(smem_raw)[wid];
+    uint2* stage = MODE != 2 ? reinterpret_cast<uint2*>(smem_raw + SEARCH_WARPS * sizeof(WarpShared)) + wid * STAGE_CAP
+                             : nullptr;
+    float* stage_d = MODE == 1 ? reinterpret_cast<float*>(smem_raw + SEARCH_WARPS * (sizeof(WarpShared) +
+                                                                                    STAGE_CAP * sizeof(uint2))) +
+                                     wid * STAGE_CAP
+                               : nullptr;
+    const float4* __restrict__ home = ws.home;
+    int stage_n = 0;
+    unsigned long long count = 0;
     const GridSpec& g = P.g;
     const int fdx = g.fd[0], fdy = g.fd[1], fdz = g.fd[2];
     const unsigned ncells = (unsigned)(fdx * fdy * fdz);
-    const bool perx = g.pbc & 1u, pery = g.pbc & 2u, perz = g.pbc & 4u;
+    const float rc2 = P.rc2;
+    const float qnan = __int_as_float(0x7fc00000);
+    const float finf = __int_as_float(0x7f800000);
 
     for (;;) {
         unsigned cell = 0;
@@ -558,93 +475,245 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32, MODE == 1 ? 2 : 3) search_c
         const unsigned hs = P.cell_start[cell], he = P.cell_start[cell + 1];
         if (hs == he) continue;
         const int fx = cell % fdx, fy = (cell / fdx) % fdy, fz = cell / (fdx * fdy);
-        const int cx = fx / g.k[0], cy = fy / g.k[1], cz = fz / g.k[2];
+        const int cx = div_k(fx, g.k[0], g.kmagic[0]), cy = div_k(fy, g.k[1], g.kmagic[1]),
+                  cz = div_k(fz, g.k[2], g.kmagic[2]);
 
-        for (unsigned hb = hs; hb < he; hb += 32) {
-            const int nh = min(32u, he - hb);
+        int row0 = 0;       // next neighbour row to put into the table
+        bool first = true;  // the first table starts with the self run
+#pragma unroll 1
+        do {
+            // ---------------- Phase A: fill the run table ----------------
+            unsigned nr = 0, T = 0;
             __syncwarp();
-            home[lane] = (lane < (unsigned)nh) ? __ldg(&P.sorted[hb + lane])
-                                               : make_float4(__int_as_float(0x7fc00000), 0.f, 0.f, 0.f);
-            __syncwarp();
-            // self cell: pairs inside the home cell, each once (sorted index order)
-            st = run_dispatch<MODE>(P, home, nh, (int)hb, hs, he, 0u, 0u, 1, stage, stage_d, st, lane);
-
-#pragma unroll 1
-            for (int r = 0; r < P.nrows; ++r) {
-                const NbrRow row = P.rows[r];
-                int ny = fy + row.dy, nz = fz + row.dz;
-                if (ny < 0) { if (!pery) continue; ny += fdy; } else if (ny >= fdy) { if (!pery) continue; ny -= fdy; }
-                if (nz < 0) { if (!perz) continue; nz += fdz; } else if (nz >= fdz) { if (!perz) continue; nz -= fdz; }
-                // each unordered cell pair is handled from its lower-indexed cell
-                const int rl_n = nz * fdy + ny, rl_h = fz * fdy + fy;
-                if (rl_n < rl_h) continue;
-                const bool same_row = rl_n == rl_h;
-                unsigned wy, wz, sy, sz;
-                if (!ref_adjacent(cy, ny / g.k[1], g.dims[1], pery, wy, sy)) continue;
-                if (!ref_adjacent(cz, nz / g.k[2], g.dims[2], perz, wz, sz)) continue;
-                const unsigned row_base = (unsigned)rl_n * (unsigned)fdx;
-                // x range, possibly split by the periodic boundary into <= 2 raw segments
-                int xa = fx + row.dxlo, xb = fx + row.dxhi;
-                int seg_lo[2], seg_hi[2], nseg = 0;
-                if (xa < 0) {
-                    if (perx) { seg_lo[nseg] = xa + fdx; seg_hi[nseg] = min(xb, -1) + fdx; ++nseg; }
-                    xa = 0;
+            if (first) {
+                if (lane == 0) {
+                    ws.rstart[0] = hs;
+                    ws.rpos[0] = 0;
+                    ws.rflag[0] = RUN_SELF;
                 }
-                if (xb >= fdx) {
-                    if (perx) { seg_lo[nseg] = max(xa, fdx) - fdx; seg_hi[nseg] = xb - fdx; ++nseg; }
-                    xb = fdx - 1;
-                }
-                if (xa <= xb && nseg < 2) { seg_lo[nseg] = xa; seg_hi[nseg] = xb; ++nseg; }
-                else if (xa <= xb) {
-                    // both ends wrapped and a middle part: cannot happen when fdx >= 2R+1
-                }
+                nr = 1;
+                T = he - hs;
+            }
 #pragma unroll 1
-                for (int sg = 0; sg < nseg; ++sg) {
-                    int lo = seg_lo[sg], hi = seg_hi[sg];
-                    if (same_row) lo = max(lo, fx + 1);
-                    if (lo > hi) continue;
-                    // walk the reference x-cells the segment covers; merge runs with equal flags
-                    int run_lo = -1, run_hi = -1;
-                    unsigned run_w = 0, run_s = 0;
-                    const int c_last = hi / g.k[0];
-                    // one extra (sentinel) iteration flushes the last run: a single call site
-#pragma unroll 1
-                    for (int cxn = lo / g.k[0]; cxn <= c_last + 1; ++cxn) {
-                        unsigned wx = 0, sx = 0;
-                        const bool adj = cxn <= c_last && ref_adjacent(cx, cxn, g.dims[0], perx, wx, sx);
-                        const int a = max(lo, cxn * g.k[0]), b = min(hi, cxn * g.k[0] + g.k[0] - 1);
-                        const unsigned w = wx | (wy << 1) | (wz << 2);
-                        const unsigned sg2 = sx | (sy << 1) | (sz << 2);
-                        if (adj && run_lo >= 0 && w == run_w && ((sg2 ^ run_s) & w) == 0) {
-                            run_hi = b;
-                            continue;
+            while (row0 < P.nrows) {
+                const int ri = row0 + (int)lane;
+                NbrRow row = P.rows[min(ri, P.nrows - 1)];
+                // pass 1: count runs and atoms per class (direct / wrapped)
+                unsigned nd = 0, nw = 0, ld = 0, lw = 0;
+                if (ri < P.nrows)
+                    gen_row_runs(g, fx, fy, fz, cx, cy, cz, row, [&](int c0, int c1, unsigned f) {
+                        unsigned len = P.cell_start[c1 + 1] - P.cell_start[c0];
+                        if (len) {
+                            if (f & 7u) { ++nw; lw += len; } else { ++nd; ld += len; }
                         }
-                        if (run_lo >= 0) {
-                            const unsigned s = P.cell_start[row_base + run_lo], e = P.cell_start[row_base + run_hi + 1];
-                            if (s < e) {
-                                const int kind = !run_w ? 0 : (P.fast_pbc ? 2 : 3);
-                                st = run_dispatch<MODE>(P, home, nh, (int)hb, s, e, run_w, run_s, kind, stage, stage_d, st, lane);
+                    });
+                // warp scans: counts packed (direct low 16, wrapped high 16), lengths separately
+                unsigned cn = nd | (nw << 16), cni = cn, ldi = ld, lwi = lw;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    unsigned t0 = __shfl_up_sync(0xffffffffu, cni, o), t1 = __shfl_up_sync(0xffffffffu, ldi, o),
+                             t2 = __shfl_up_sync(0xffffffffu, lwi, o);
+                    if (lane >= (unsigned)o) { cni += t0; ldi += t1; lwi += t2; }
+                }
+                const unsigned tot_c = __shfl_sync(0xffffffffu, cni, 31);
+                const unsigned tot_d = tot_c & 0xffffu, tot_w = tot_c >> 16;
+                const unsigned tot_ld = __shfl_sync(0xffffffffu, ldi, 31), tot_lw = __shfl_sync(0xffffffffu, lwi, 31);
+                if (nr + tot_d + tot_w > (unsigned)MAX_RUNS) break;  // table full: process it first
+                // pass 2: write this lane's runs (direct runs of the batch first, then wrapped ones)
+                unsigned sd = nr + (cni & 0xffffu) - nd, sw = nr + tot_d + (cni >> 16) - nw;
+                unsigned pd = T + ldi - ld, pw = T + tot_ld + lwi - lw;
+                if (ri < P.nrows)
+                    gen_row_runs(g, fx, fy, fz, cx, cy, cz, row, [&](int c0, int c1, unsigned f) {
+                        unsigned s = P.cell_start[c0], len = P.cell_start[c1 + 1] - s;
+                        if (len) {
+                            if (f & 7u) {
+                                ws.rstart[sw] = s; ws.rpos[sw] = pw; ws.rflag[sw] = (unsigned char)f;
+                                ++sw; pw += len;
+                            } else {
+                                ws.rstart[sd] = s; ws.rpos[sd] = pd; ws.rflag[sd] = (unsigned char)f;
+                                ++sd; pd += len;
                             }
-                            run_lo = -1;
                         }
-                        if (adj) {
-                            run_lo = a;
-                            run_hi = b;
-                            run_w = w;
-                            run_s = sg2;
+                    });
+                nr += tot_d + tot_w;
+                T += tot_ld + tot_lw;
+                row0 += 32;
+            }
+            if (lane == 0) ws.rpos[nr] = T;
+            __syncwarp();
+
+            // ---------------- Phase B: consume the stream ----------------
+#pragma unroll 1
+            for (unsigned hb = hs; hb < he; hb += 32) {
+                const int nh = min(32u, he - hb);
+                __syncwarp();
+                ws.home[lane] = (lane < (unsigned)nh) ? __ldg(&P.sorted[hb + lane]) : make_float4(qnan, 0.f, 0.f, 0.f);
+                __syncwarp();
+                unsigned cur0 = 0, cur1 = 0;
+#pragma unroll 1
+                for (unsigned c0 = 0; c0 < T; c0 += 64) {
+                    const unsigned p0 = c0 + lane, p1 = p0 + 32;
+                    float4 n0 = make_float4(qnan, 0.f, 0.f, 0.f), n1 = n0;  // NaN: never within cutoff
+                    unsigned f0 = 0, f1 = 0, a0i = 0, a1i = 0;
+                    if (p0 < T) {
+                        while (ws.rpos[cur0 + 1] <= p0) ++cur0;
+                        a0i = ws.rstart[cur0] + (p0 - ws.rpos[cur0]);
+                        f0 = ws.rflag[cur0];
+                        n0 = __ldg(&P.sorted[a0i]);
+                    }
+                    if (p1 < T) {
+                        cur1 = max(cur1, cur0);
+                        while (ws.rpos[cur1 + 1] <= p1) ++cur1;
+                        a1i = ws.rstart[cur1] + (p1 - ws.rpos[cur1]);
+                        f1 = ws.rflag[cur1];
+                        n1 = __ldg(&P.sorted[a1i]);
+                    }
+                    unsigned m0 = 0, m1 = 0;
+                    if (!__any_sync(0xffffffffu, (f0 | f1) != 0u)) {
+                        // ---- all 64 candidates come from un-wrapped cell pairs: direct difference ----
+                        const unsigned long long nx = pk2(n0.x, n1.x), ny = pk2(n0.y, n1.y), nz = pk2(n0.z, n1.z);
+#pragma unroll 1
+                        for (int gj = 0; gj < nh; gj += 4) {
+                            unsigned l0 = 0, l1 = 0;
+#pragma unroll
+                            for (int jj = 0; jj < 4; ++jj) {
+                                float d0, d1;
+                                d2_pair(nx, ny, nz, home[gj + jj], d0, d1);
+                                if (d0 <= rc2) l0 |= 1u << jj;
+                                if (d1 <= rc2) l1 |= 1u << jj;
+                            }
+                            m0 |= l0 << gj;
+                            m1 |= l1 << gj;
                         }
+                    } else {
+                        // ---- mixed step: self cell (index-order filter) and/or wrapped cell pairs.
+                        // Wrapped candidates are tested on the lattice-shifted image; outside the band
+                        // [lo,hi] around cutoff^2 that test is decisive, inside it (and always, when the
+                        // filter's preconditions do not hold: lo=-1, hi=inf) the reference's exact
+                        // PeriodicBox::distance_squared decides.
+                        float sx0 = 0.f, sy0 = 0.f, sz0 = 0.f, sx1 = 0.f, sy1 = 0.f, sz1 = 0.f;
+#pragma unroll
+                        for (int d = 0; d < 3; ++d) {
+                            const float bx = P.g.box.m[d], by = P.g.box.m[3 + d], bz = P.g.box.m[6 + d];
+                            if ((f0 >> d) & 1u) {
+                                const float sg = ((f0 >> (3 + d)) & 1u) ? -1.0f : 1.0f;
+                                sx0 += sg * bx; sy0 += sg * by; sz0 += sg * bz;
+                            }
+                            if ((f1 >> d) & 1u) {
+                                const float sg = ((f1 >> (3 + d)) & 1u) ? -1.0f : 1.0f;
+                                sx1 += sg * bx; sy1 += sg * by; sz1 += sg * bz;
+                            }
+                        }
+                        const bool w0 = (f0 & 7u) != 0u, w1 = (f1 & 7u) != 0u;
+                        const float lo0 = w0 ? (P.fast_pbc ? P.rc2_lo : -1.0f) : rc2, hi0 = w0 ? (P.fast_pbc ? P.rc2_hi : finf) : rc2;
+                        const float lo1 = w1 ? (P.fast_pbc ? P.rc2_lo : -1.0f) : rc2, hi1 = w1 ? (P.fast_pbc ? P.rc2_hi : finf) : rc2;
+                        const unsigned long long nx = pk2(n0.x + sx0, n1.x + sx1), ny = pk2(n0.y + sy0, n1.y + sy1),
+                                                 nz = pk2(n0.z + sz0, n1.z + sz1);
+                        unsigned b0 = 0, b1 = 0;  // possible hits (superset of the certain ones in m0/m1)
+#pragma unroll 1
+                        for (int gj = 0; gj < nh; gj += 4) {
+                            unsigned l0 = 0, l1 = 0, u0 = 0, u1 = 0;
+#pragma unroll
+                            for (int jj = 0; jj < 4; ++jj) {
+                                float d0, d1;
+                                d2_pair(nx, ny, nz, home[gj + jj], d0, d1);
+                                if (d0 <= lo0) l0 |= 1u << jj;
+                                if (d1 <= lo1) l1 |= 1u << jj;
+                                if (d0 <= hi0) u0 |= 1u << jj;
+                                if (d1 <= hi1) u1 |= 1u << jj;
+                            }
+                            m0 |= l0 << gj; m1 |= l1 << gj;
+                            b0 |= u0 << gj; b1 |= u1 << gj;
+                        }
+                        b0 ^= m0;
+                        b1 ^= m1;
+                        while (b0) {
+                            const int j = bfind32(b0);
+                            b0 ^= 1u << j;
+                            const float4 h = home[j];
+                            if (d2_pbc_call(P.g.box, h.x, h.y, h.z, n0.x, n0.y, n0.z, f0 & 7u) <= rc2) m0 |= 1u << j;
+                        }
+                        while (b1) {
+                            const int j = bfind32(b1);
+                            b1 ^= 1u << j;
+                            const float4 h = home[j];
+                            if (d2_pbc_call(P.g.box, h.x, h.y, h.z, n1.x, n1.y, n1.z, f1 & 7u) <= rc2) m1 |= 1u << j;
+                        }
+                        // home cell against itself: keep (home j, atom a) only for a > hb + j
+                        if (f0 & RUN_SELF) {
+                            const int lim = min(max((int)a0i - (int)hb, 0), 32);
+                            m0 &= lim >= 32 ? 0xffffffffu : ((1u << lim) - 1u);
+                        }
+                        if (f1 & RUN_SELF) {
+                            const int lim = min(max((int)a1i - (int)hb, 0), 32);
+                            m1 &= lim >= 32 ? 0xffffffffu : ((1u << lim) - 1u);
+                        }
+                    }
+                    const int c0n = __popc(m0), c1n = __popc(m1);
+                    if (MODE == 2) {
+                        count += c0n + c1n;
+                        continue;
+                    }
+                    // one scan for both atoms of the lane: low 16 bits = first, high 16 bits = second
+                    int inc = c0n | (c1n << 16);
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        int t = __shfl_up_sync(0xffffffffu, inc, o);
+                        if (lane >= (unsigned)o) inc += t;
+                    }
+                    const int tot = __shfl_sync(0xffffffffu, inc, 31);
+                    const int t0 = tot & 0xffff, t1 = tot >> 16;
+                    if (t0 + t1 == 0) continue;
+                    // expand the masks into the staging buffer (two passes only if both halves do not fit)
+                    const int npass = (t0 + t1 <= STAGE_CAP) ? 1 : 2;
+#pragma unroll 1
+                    for (int pass = 0; pass < npass; ++pass) {
+                        const int need = npass == 1 ? t0 + t1 : (pass == 0 ? t0 : t1);
+                        if (stage_n + need > STAGE_CAP) warp_flush<MODE == 1>(stage, stage_d, stage_n, P, lane);
+                        unsigned e0 = (npass == 1 || pass == 0) ? m0 : 0u;
+                        unsigned e1 = (npass == 1 || pass == 1) ? m1 : 0u;
+                        int off0 = stage_n + (inc & 0xffff) - c0n;
+                        int off1 = stage_n + (npass == 1 ? t0 : 0) + (inc >> 16) - c1n;
+                        const unsigned id0 = __float_as_uint(n0.w), id1 = __float_as_uint(n1.w);
+                        while (e0) {
+                            const int j = bfind32(e0);
+                            e0 ^= 1u << j;
+                            const float4 h = home[j];
+                            const unsigned hid = __float_as_uint(h.w);
+                            stage[off0] = make_uint2(min(hid, id0), max(hid, id0));
+                            if (MODE == 1) {
+                                float d2 = (f0 & 7u) ? d2_pbc_call(P.g.box, h.x, h.y, h.z, n0.x, n0.y, n0.z, f0 & 7u)
+                                                     : d2_direct(h.x, h.y, h.z, n0.x, n0.y, n0.z);
+                                stage_d[off0] = __fsqrt_rn(d2);
+                            }
+                            ++off0;
+                        }
+                        while (e1) {
+                            const int j = bfind32(e1);
+                            e1 ^= 1u << j;
+                            const float4 h = home[j];
+                            const unsigned hid = __float_as_uint(h.w);
+                            stage[off1] = make_uint2(min(hid, id1), max(hid, id1));
+                            if (MODE == 1) {
+                                float d2 = (f1 & 7u) ? d2_pbc_call(P.g.box, h.x, h.y, h.z, n1.x, n1.y, n1.z, f1 & 7u)
+                                                     : d2_direct(h.x, h.y, h.z, n1.x, n1.y, n1.z);
+                                stage_d[off1] = __fsqrt_rn(d2);
+                            }
+                            ++off1;
+                        }
+                        stage_n += need;
                     }
                 }
             }
-        }
+            first = false;
+        } while (row0 < P.nrows);
     }
     if (MODE == 2) {
-        unsigned long long count = st.count;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) count += __shfl_xor_sync(0xffffffffu, count, o);
         if (lane == 0 && count) atomicAdd(P.counter, count);
     } else {
-        warp_flush<MODE == 1>(stage, stage_d, st.stage_n, P, lane);
+        warp_flush<MODE == 1>(stage, stage_d, stage_n, P, lane);
     }
 }
 
@@ -966,6 +1035,7 @@ static void plan_cells(const Ctx* c, Plan& pl, float cutoff, size_t n) {
     pl.use_cells = false;
     for (int d = 0; d < 3; ++d) {
         g.k[d] = 1;
+        g.kmagic[d] = 0;
         g.fd[d] = g.dims[d];
     }
     pl.ncells = (size_t)g.dims[0] * g.dims[1] * g.dims[2];
@@ -1049,9 +1119,12 @@ static void plan_cells(const Ctx* c, Plan& pl, float cutoff, size_t n) {
         }
         // neighbour offset table: rows (dy,dz) with the contiguous dx range whose cells can hold an
         // atom within the cutoff of an atom of the home cell
+        // Only the positive half-space of offsets is kept (dz>0, or dz==0 and dy>0, or dz==dy==0 and
+        // dx>0): every unordered pair of distinct cells is then visited from exactly one side, with
+        // or without periodic wrapping (offsets are unique modulo the grid because fd >= 2R+1).
         int nrows = 0;
-        for (int dz = -R[2]; dz <= R[2]; ++dz)
-            for (int dy = -R[1]; dy <= R[1]; ++dy) {
+        for (int dz = 0; dz <= R[2]; ++dz)
+            for (int dy = (dz == 0 ? 0 : -R[1]); dy <= R[1]; ++dy) {
                 int lo = 127, hi = -128;
                 for (int dx = -R[0]; dx <= R[0]; ++dx) {
                     int delta[3] = {dx, dy, dz};
@@ -1060,6 +1133,7 @@ static void plan_cells(const Ctx* c, Plan& pl, float cutoff, size_t n) {
                         hi = std::max(hi, dx);
                     }
                 }
+                if (dz == 0 && dy == 0) lo = std::max(lo, 1);
                 if (lo <= hi) {
                     pl.rows[nrows].dy = (signed char)dy;
                     pl.rows[nrows].dz = (signed char)dz;
@@ -1071,6 +1145,7 @@ static void plan_cells(const Ctx* c, Plan& pl, float cutoff, size_t n) {
         pl.nrows = nrows;
         for (int d = 0; d < 3; ++d) {
             g.k[d] = k[d];
+            g.kmagic[d] = (unsigned)(0x100000000ull / (unsigned long long)k[d]) + 1u;
             g.fd[d] = g.dims[d] * k[d];
         }
         pl.ncells = ncells;
@@ -1277,7 +1352,7 @@ static int bin_set(Ctx* c, const float* xyz, const unsigned long long* d_ids, si
 
 template <int MODE>
 static int launch_search_cells(Ctx* c, const SearchParams& P) {
-    size_t smem = SEARCH_WARPS * 32 * sizeof(float4);
+    size_t smem = SEARCH_WARPS * sizeof(WarpShared);
     if (MODE != 2) smem += SEARCH_WARPS * STAGE_CAP * sizeof(uint2);
     if (MODE == 1) smem += SEARCH_WARPS * STAGE_CAP * sizeof(float);
     MB_CUDA(cudaFuncSetAttribute(search_cells_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
