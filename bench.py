@@ -187,6 +187,9 @@ def run_ours(args, wl):
 
     traj = mb.Trajectory(device=local)
     traj.synth(SEED, rank * F, F, n, box, mass_seed=SEED)  # rank r owns global frames [r*F, (r+1)*F)
+    for kv in filter(None, args.opts.split(",")):
+        key, val = kv.split("=")
+        traj.set_option(key, float(val))
     traj.set_option("profile", 1)
     ext = torch.cuda.ExternalStream(traj.stream(), device=local)
 
@@ -232,6 +235,14 @@ def run_ours(args, wl):
     k_n = traj.stat("search_kernel_launches")
     fps = world * F * args.steps / (ms / 1000.0)
 
+    if args.no_e2e:
+        if rank == 0:
+            print(json.dumps({"tuning": True, "opts": args.opts, "value": fps, "ms_per_frame": ms / (F * args.steps),
+                              "search_kernel_ms": k_ms / max(k_n, 1), "workload": args.workload}))
+        traj.close()
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
     # ---- end-to-end through the public per-call API with HOST buffers (pinned), rank-local -------
     from oracle import oracle_py as orc  # only to synthesise host-side input frames
     e2e_frames = min(F, 4)
@@ -327,6 +338,8 @@ def main():
     ap.add_argument("--workload", default="search1m", choices=sorted(WORKLOADS))
     ap.add_argument("--frames", type=int, default=0, help="resident frames per GPU (one step = one pass over them)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end (host buffer) leg (tuning runs only)")
+    ap.add_argument("--opts", default="", help="library tuning options, e.g. subdiv_x=3,slice_x=2 (tuning runs only)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     import __graft_entry__

@@ -103,7 +103,9 @@ int64_t mb_count_single(MbCtx* ctx, float cutoff, const uint64_t* ids, size_t n,
 /* ij: 2*P entries (usize pairs) ; dist: P entries or NULL */
 int mb_fill_pairs(MbCtx* ctx, uint64_t* ij, float* dist);
 int mb_fill_ids(MbCtx* ctx, uint64_t* ids);
-/* Device-side view of the last pair list: packed (uint32 i, uint32 j), P entries. */
+/* Device-side view of the last pair list: packed (uint32, uint32), P entries.  For a single-set
+   search the two ids of an entry are in no particular order (mb_fill_pairs and mb_pairs_checksum
+   canonicalise to i < j); for a double search entry = (i from set 1, j from set 2). */
 const void* mb_pairs_device(MbCtx* ctx, int64_t* n_pairs);
 /* Order-independent checksum of the last pair list computed on the device:
    out[0] = sum over pairs of mix64(i<<32|j) (wrapping), out[1] = xor of the same. */

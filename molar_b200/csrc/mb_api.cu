@@ -234,6 +234,10 @@ int mb_set_option(MbCtx* h, const char* key, double value) {
     if (!h || !key) return fail(MB_ERR_ARG, "null argument");
     Ctx& c = h->c;
     if (!strcmp(key, "subdiv")) c.opt_subdiv = (int)value;
+    else if (!strcmp(key, "subdiv_x")) c.opt_subdiv_xyz[0] = (int)value;
+    else if (!strcmp(key, "subdiv_y")) c.opt_subdiv_xyz[1] = (int)value;
+    else if (!strcmp(key, "subdiv_z")) c.opt_subdiv_xyz[2] = (int)value;
+    else if (!strcmp(key, "slice_x")) c.opt_slice_x = (int)value;
     else if (!strcmp(key, "force_brute")) c.opt_force_brute = (int)value;
     else if (!strcmp(key, "atoms_per_cell")) c.opt_atoms_per_cell = value;
     else if (!strcmp(key, "with_dist")) c.opt_with_dist = (int)value;

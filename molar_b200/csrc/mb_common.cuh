@@ -117,6 +117,8 @@ struct Ctx {
 
     // options
     int opt_subdiv = 0;       // 0 auto, else forced k for all dims
+    int opt_subdiv_xyz[3] = {0, 0, 0};  // per-dimension override of the tile subdivision
+    int opt_slice_x = 0;      // home tile = this many fine cells along x (0 = automatic)
     int opt_force_brute = 0;  // force the general all-pairs kernel
     double opt_atoms_per_cell = 12.0;
     int opt_with_dist = 1;

@@ -41,6 +41,7 @@ struct GridSpec {
     int dims[3];           // reference Grid::dims
     int k[3];              // subdivision
     unsigned kmagic[3];    // floor(2^32 / k) + 1 (unused for k == 1)
+    int hx;                // home tile = hx consecutive fine cells along x (hx divides k[0])
     int fd[3];             // fine dims
     float lower[3];        // non-periodic variant: bounds
     float dim_sz[3];
@@ -313,12 +314,24 @@ __device__ __forceinline__ unsigned long long pk2(float lo, float hi) {
     asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
     return r;
 }
+// same, but never rematerialised: used for the loop-invariant neighbour coordinates (ptxas otherwise
+// re-packs the register pair in front of every FADD2 of the inner loop)
+__device__ __forceinline__ unsigned long long pk2_once(float lo, float hi) {
+    unsigned long long r;
+    asm volatile("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
 __device__ __forceinline__ void upk2(unsigned long long u, float& lo, float& hi) {
     asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(u));
 }
 __device__ __forceinline__ unsigned long long sub2(unsigned long long a, unsigned long long b) {
     unsigned long long r;
     asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ unsigned long long add2(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
     return r;
 }
 __device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigned long long b) {
@@ -438,7 +451,7 @@ struct __align__(16) WarpShared {
     unsigned char rflag[MAX_RUNS];   // w | sgn << 3 | RUN_SELF
 };
 
-// One warp per home fine cell (dynamic work counter).
+// One warp per home tile = hx consecutive fine cells along x (dynamic work counter).
 //  Phase A  lanes work on different neighbour rows in parallel and build a table of runs: contiguous
 //           ranges of the sorted atom array (self cell, then direct runs, then wrapped runs).
 //  Phase B  the concatenation of the runs is one stream of candidate atoms; it is consumed 64 atoms
@@ -462,19 +475,23 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32, 2) search_cells_kernel(cons
     unsigned long long count = 0;
     const GridSpec& g = P.g;
     const int fdx = g.fd[0], fdy = g.fd[1], fdz = g.fd[2];
-    const unsigned ncells = (unsigned)(fdx * fdy * fdz);
+    const int hx = g.hx, tdx = fdx / hx;  // tiles per x-row
+    const unsigned ntiles = (unsigned)(tdx * fdy * fdz);
     const float rc2 = P.rc2;
     const float qnan = __int_as_float(0x7fc00000);
     const float finf = __int_as_float(0x7f800000);
 
     for (;;) {
-        unsigned cell = 0;
-        if (lane == 0) cell = (unsigned)atomicAdd(P.counter + 1, 1ull);
-        cell = __shfl_sync(0xffffffffu, cell, 0);
-        if (cell >= ncells) break;
-        const unsigned hs = P.cell_start[cell], he = P.cell_start[cell + 1];
+        unsigned tile = 0;
+        if (lane == 0) tile = (unsigned)atomicAdd(P.counter + 1, 1ull);
+        tile = __shfl_sync(0xffffffffu, tile, 0);
+        if (tile >= ntiles) break;
+        const int fx = (int)(tile % (unsigned)tdx) * hx, fy = (int)((tile / (unsigned)tdx) % (unsigned)fdy),
+                  fz = (int)(tile / (unsigned)(tdx * fdy));
+        const unsigned cell0 = (unsigned)(fx + fdx * (fy + fdy * fz));
+        const unsigned hs = P.cell_start[cell0], he = P.cell_start[cell0 + hx];
         if (hs == he) continue;
-        const int fx = cell % fdx, fy = (cell / fdx) % fdy, fz = cell / (fdx * fdy);
+        // the tile lies inside one reference cell (hx divides k[0])
         const int cx = div_k(fx, g.k[0], g.kmagic[0]), cy = div_k(fy, g.k[1], g.kmagic[1]),
                   cz = div_k(fz, g.k[2], g.kmagic[2]);
 
@@ -571,7 +588,11 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32, 2) search_cells_kernel(cons
                     unsigned m0 = 0, m1 = 0;
                     if (!__any_sync(0xffffffffu, (f0 | f1) != 0u)) {
                         // ---- all 64 candidates come from un-wrapped cell pairs: direct difference ----
-                        const unsigned long long nx = pk2(n0.x, n1.x), ny = pk2(n0.y, n1.y), nz = pk2(n0.z, n1.z);
+                        // x + 0 is exact: the FADD2 only serves to give each packed coordinate its own aligned
+                        // register pair (ptxas otherwise re-packs the halves in front of every use)
+                        const unsigned long long zz2 = pk2(0.f, 0.f);
+                        const unsigned long long nx = add2(pk2(n0.x, n1.x), zz2), ny = add2(pk2(n0.y, n1.y), zz2),
+                                                 nz = add2(pk2(n0.z, n1.z), zz2);
 #pragma unroll 1
                         for (int gj = 0; gj < nh; gj += 4) {
                             unsigned l0 = 0, l1 = 0;
@@ -607,8 +628,9 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32, 2) search_cells_kernel(cons
                         const bool w0 = (f0 & 7u) != 0u, w1 = (f1 & 7u) != 0u;
                         const float lo0 = w0 ? (P.fast_pbc ? P.rc2_lo : -1.0f) : rc2, hi0 = w0 ? (P.fast_pbc ? P.rc2_hi : finf) : rc2;
                         const float lo1 = w1 ? (P.fast_pbc ? P.rc2_lo : -1.0f) : rc2, hi1 = w1 ? (P.fast_pbc ? P.rc2_hi : finf) : rc2;
-                        const unsigned long long nx = pk2(n0.x + sx0, n1.x + sx1), ny = pk2(n0.y + sy0, n1.y + sy1),
-                                                 nz = pk2(n0.z + sz0, n1.z + sz1);
+                        const unsigned long long nx = add2(pk2(n0.x, n1.x), pk2(sx0, sx1)),
+                                                 ny = add2(pk2(n0.y, n1.y), pk2(sy0, sy1)),
+                                                 nz = add2(pk2(n0.z, n1.z), pk2(sz0, sz1));
                         unsigned b0 = 0, b1 = 0;  // possible hits (superset of the certain ones in m0/m1)
 #pragma unroll 1
                         for (int gj = 0; gj < nh; gj += 4) {
@@ -672,34 +694,33 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32, 2) search_cells_kernel(cons
                         if (stage_n + need > STAGE_CAP) warp_flush<MODE == 1>(stage, stage_d, stage_n, P, lane);
                         unsigned e0 = (npass == 1 || pass == 0) ? m0 : 0u;
                         unsigned e1 = (npass == 1 || pass == 1) ? m1 : 0u;
-                        int off0 = stage_n + (inc & 0xffff) - c0n;
-                        int off1 = stage_n + (npass == 1 ? t0 : 0) + (inc >> 16) - c1n;
+                        uint2* sp0 = stage + (stage_n + (inc & 0xffff) - c0n);
+                        uint2* sp1 = stage + (stage_n + (npass == 1 ? t0 : 0) + (inc >> 16) - c1n);
+                        float* dp0 = MODE == 1 ? stage_d + (sp0 - stage) : nullptr;
+                        float* dp1 = MODE == 1 ? stage_d + (sp1 - stage) : nullptr;
                         const unsigned id0 = __float_as_uint(n0.w), id1 = __float_as_uint(n1.w);
+                        const unsigned* hid = reinterpret_cast<const unsigned*>(home) + 3;  // .w of home[j]
                         while (e0) {
                             const int j = bfind32(e0);
                             e0 ^= 1u << j;
-                            const float4 h = home[j];
-                            const unsigned hid = __float_as_uint(h.w);
-                            stage[off0] = make_uint2(min(hid, id0), max(hid, id0));
+                            *sp0++ = make_uint2(hid[4 * j], id0);
                             if (MODE == 1) {
+                                const float4 h = home[j];
                                 float d2 = (f0 & 7u) ? d2_pbc_call(P.g.box, h.x, h.y, h.z, n0.x, n0.y, n0.z, f0 & 7u)
                                                      : d2_direct(h.x, h.y, h.z, n0.x, n0.y, n0.z);
-                                stage_d[off0] = __fsqrt_rn(d2);
+                                *dp0++ = __fsqrt_rn(d2);
                             }
-                            ++off0;
                         }
                         while (e1) {
                             const int j = bfind32(e1);
                             e1 ^= 1u << j;
-                            const float4 h = home[j];
-                            const unsigned hid = __float_as_uint(h.w);
-                            stage[off1] = make_uint2(min(hid, id1), max(hid, id1));
+                            *sp1++ = make_uint2(hid[4 * j], id1);
                             if (MODE == 1) {
+                                const float4 h = home[j];
                                 float d2 = (f1 & 7u) ? d2_pbc_call(P.g.box, h.x, h.y, h.z, n1.x, n1.y, n1.z, f1 & 7u)
                                                      : d2_direct(h.x, h.y, h.z, n1.x, n1.y, n1.z);
-                                stage_d[off1] = __fsqrt_rn(d2);
+                                *dp1++ = __fsqrt_rn(d2);
                             }
-                            ++off1;
                         }
                         stage_n += need;
                     }
@@ -925,11 +946,16 @@ __device__ __forceinline__ unsigned long long mix64(unsigned long long x) {
     return x;
 }
 __global__ void __launch_bounds__(256) checksum_kernel(const uint2* __restrict__ pairs, unsigned long long n,
-                                                       unsigned long long* __restrict__ out2) {
+                                                       int canonical, unsigned long long* __restrict__ out2) {
     unsigned long long s = 0, x = 0;
     for (unsigned long long k = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; k < n;
          k += (unsigned long long)gridDim.x * blockDim.x) {
         uint2 p = pairs[k];
+        if (canonical && p.x > p.y) {  // single-set pairs are stored unordered: hash (min,max)
+            unsigned t = p.x;
+            p.x = p.y;
+            p.y = t;
+        }
         unsigned long long h = mix64(((unsigned long long)p.x << 32) | p.y);
         s += h;
         x ^= h;
@@ -958,15 +984,17 @@ static inline int dims_from_extent(float ext, float cutoff) {
 
 // minimum of |M (delta + u)|^2 over u in [-1,1]^3 (distance between two equal parallelepiped cells
 // offset by the integer vector delta): enumerate the 27 active sets of the box-constrained QP.
-static double min_cell_dist2(const double M[3][3], const int delta[3]) {
+// `hx`: the home side spans hx cells along x (cells [0,hx)), the neighbour side is cell delta.
+static double min_cell_dist2(const double M[3][3], const int delta[3], int hx = 1) {
     double best = 1e300;
+    const double ulo[3] = {-(double)hx, -1.0, -1.0};
     for (int cfg = 0; cfg < 27; ++cfg) {
-        int st[3] = {cfg % 3, (cfg / 3) % 3, cfg / 9};  // 0: free, 1: -1, 2: +1
+        int st[3] = {cfg % 3, (cfg / 3) % 3, cfg / 9};  // 0: free, 1: lower bound, 2: upper bound
         double fixed[3] = {0, 0, 0};
         int freev[3], nf = 0;
         for (int d = 0; d < 3; ++d) {
             if (st[d] == 0) freev[nf++] = d;
-            else fixed[d] = (double)delta[d] + (st[d] == 1 ? -1.0 : 1.0);
+            else fixed[d] = (double)delta[d] + (st[d] == 1 ? ulo[d] : 1.0);
         }
         // r0 = M * (fixed part + delta for free vars)
         double base[3] = {0, 0, 0};
@@ -1004,7 +1032,7 @@ static double min_cell_dist2(const double M[3][3], const int delta[3]) {
             if (ok)
                 for (int a = 0; a < nf; ++a) {
                     u[a] = aug[a][nf] / aug[a][a];
-                    if (u[a] < -1.0 - 1e-12 || u[a] > 1.0 + 1e-12) ok = false;
+                    if (u[a] < ulo[freev[a]] - 1e-12 || u[a] > 1.0 + 1e-12) ok = false;
                 }
         }
         if (!ok) continue;
@@ -1038,6 +1066,7 @@ static void plan_cells(const Ctx* c, Plan& pl, float cutoff, size_t n) {
         g.kmagic[d] = 0;
         g.fd[d] = g.dims[d];
     }
+    g.hx = 1;
     pl.ncells = (size_t)g.dims[0] * g.dims[1] * g.dims[2];
     if (c->opt_force_brute) return;
     if (n < 4096) return;  // all-pairs is cheaper than five launches
@@ -1089,10 +1118,17 @@ static void plan_cells(const Ctx* c, Plan& pl, float cutoff, size_t n) {
             --k[dmax];
         }
     }
-    for (int attempt = 0; attempt < 8; ++attempt) {
+    // optional per-dimension overrides and the x slicing of the home tile
+    if (c->opt_subdiv_xyz[0] > 0) k[0] = std::min(c->opt_subdiv_xyz[0], 8);
+    if (c->opt_subdiv_xyz[1] > 0) k[1] = std::min(c->opt_subdiv_xyz[1], 8);
+    if (c->opt_subdiv_xyz[2] > 0) k[2] = std::min(c->opt_subdiv_xyz[2], 8);
+    int hx = c->opt_slice_x > 0 ? std::min(c->opt_slice_x, 8) : 1;
+    for (int attempt = 0; attempt < 16; ++attempt) {
+        // fine-cell lattice: tiles of k[] per reference cell, each tile sliced hx times along x
+        const int kf[3] = {k[0] * hx, k[1], k[2]};
         double Mf[3][3];
         for (int r = 0; r < 3; ++r)
-            for (int col = 0; col < 3; ++col) Mf[r][col] = Mref[r][col] / k[col];
+            for (int col = 0; col < 3; ++col) Mf[r][col] = Mref[r][col] / kf[col];
         double tf[3];
         thickness(Mf, tf);
         int R[3];
@@ -1100,16 +1136,21 @@ static void plan_cells(const Ctx* c, Plan& pl, float cutoff, size_t n) {
         for (int d = 0; d < 3; ++d) {
             R[d] = (int)std::floor(rc_cull / tf[d]) + 1;
             // never need to look past the adjacent reference cells
-            R[d] = std::min(R[d], 2 * k[d] - 1);
+            R[d] = std::min(R[d], 2 * kf[d] - 1);
             if (R[d] < 1) R[d] = 1;
-            int fdd = g.dims[d] * k[d];
+            int fdd = g.dims[d] * kf[d];
             bool per = g.periodic_variant && ((g.pbc >> d) & 1u);
-            if (R[d] > MAX_REACH) ok = false;
-            if (per && fdd < 2 * R[d] + 1) ok = false;
+            if (d > 0 && R[d] > MAX_REACH) ok = false;
+            if (d == 0 && R[d] + hx > 100) ok = false;
+            if (per && fdd < 2 * (R[d] + (d == 0 ? hx : 0)) + 1) ok = false;
         }
-        size_t ncells = (size_t)g.dims[0] * k[0] * g.dims[1] * k[1] * g.dims[2] * k[2];
+        size_t ncells = (size_t)g.dims[0] * kf[0] * g.dims[1] * kf[1] * g.dims[2] * kf[2];
         if (ncells > ((size_t)1 << 27)) ok = false;
         if (!ok) {
+            if (hx > 1) {
+                --hx;
+                continue;
+            }
             int dmax = 0;
             for (int d = 1; d < 3; ++d)
                 if (k[d] > k[dmax]) dmax = d;
@@ -1117,23 +1158,24 @@ static void plan_cells(const Ctx* c, Plan& pl, float cutoff, size_t n) {
             --k[dmax];
             continue;
         }
-        // neighbour offset table: rows (dy,dz) with the contiguous dx range whose cells can hold an
-        // atom within the cutoff of an atom of the home cell
-        // Only the positive half-space of offsets is kept (dz>0, or dz==0 and dy>0, or dz==dy==0 and
-        // dx>0): every unordered pair of distinct cells is then visited from exactly one side, with
-        // or without periodic wrapping (offsets are unique modulo the grid because fd >= 2R+1).
+        // Neighbour offset table: rows (dy,dz) with the contiguous range of fine cells [dxlo,dxhi]
+        // (relative to the first cell of the home tile) that can hold an atom within the cutoff of
+        // an atom of the home tile.  Only the positive half-space of offsets is kept (dz>0, or dz==0
+        // and dy>0, or the home row itself to the right of the tile): every unordered pair of atoms
+        // in different tiles is then visited from exactly one side, with or without periodic
+        // wrapping (offsets are unique modulo the grid because fd >= 2(R+hx)+1).
         int nrows = 0;
         for (int dz = 0; dz <= R[2]; ++dz)
             for (int dy = (dz == 0 ? 0 : -R[1]); dy <= R[1]; ++dy) {
                 int lo = 127, hi = -128;
-                for (int dx = -R[0]; dx <= R[0]; ++dx) {
+                for (int dx = -R[0]; dx <= hx - 1 + R[0]; ++dx) {
                     int delta[3] = {dx, dy, dz};
-                    if (min_cell_dist2(Mf, delta) <= rc_cull * rc_cull) {
+                    if (min_cell_dist2(Mf, delta, hx) <= rc_cull * rc_cull) {
                         lo = std::min(lo, dx);
                         hi = std::max(hi, dx);
                     }
                 }
-                if (dz == 0 && dy == 0) lo = std::max(lo, 1);
+                if (dz == 0 && dy == 0) lo = std::max(lo, hx);
                 if (lo <= hi) {
                     pl.rows[nrows].dy = (signed char)dy;
                     pl.rows[nrows].dz = (signed char)dz;
@@ -1144,10 +1186,11 @@ static void plan_cells(const Ctx* c, Plan& pl, float cutoff, size_t n) {
             }
         pl.nrows = nrows;
         for (int d = 0; d < 3; ++d) {
-            g.k[d] = k[d];
-            g.kmagic[d] = (unsigned)(0x100000000ull / (unsigned long long)k[d]) + 1u;
-            g.fd[d] = g.dims[d] * k[d];
+            g.k[d] = kf[d];
+            g.kmagic[d] = (unsigned)(0x100000000ull / (unsigned long long)kf[d]) + 1u;
+            g.fd[d] = g.dims[d] * kf[d];
         }
+        g.hx = hx;
         pl.ncells = ncells;
         pl.use_cells = true;
         // Shifted-image filter for wrapped cell pairs (process_run KIND 2).  Sound when
@@ -1203,7 +1246,7 @@ struct PlanKey {
     unsigned pbc;
     size_t n;
     float m[9];
-    int subdiv, brute, exact_pbc;
+    int subdiv, brute, exact_pbc, sx, sy, sz, slice;
     double apc;
 };
 struct PlanCache {
@@ -1286,6 +1329,10 @@ static int get_plan_pbc(Ctx* c, float cutoff, uint8_t pbc, size_t n, Plan& out) 
     k.subdiv = c->opt_subdiv;
     k.brute = c->opt_force_brute;
     k.exact_pbc = c->opt_exact_pbc;
+    k.sx = c->opt_subdiv_xyz[0];
+    k.sy = c->opt_subdiv_xyz[1];
+    k.sz = c->opt_subdiv_xyz[2];
+    k.slice = c->opt_slice_x;
     k.apc = c->opt_atoms_per_cell;
     PlanCache* pc = static_cast<PlanCache*>(c->plan_cache);
     if (!pc) {
@@ -1661,7 +1708,7 @@ int batch_search_impl(Ctx* c, float cutoff, uint8_t pbc, size_t f0, size_t f1, i
             MB_TRY(enqueue_cells_search(c, xyz, nullptr, n, pl, cutoff, kmode, d_cnt + 2 * f));
             unsigned long long cnt = h_cnt[2 * f];
             int blocks = (int)std::min<unsigned long long>((cnt + 255) / 256 + 1, (unsigned long long)c->sm_count * 16);
-            checksum_kernel<<<blocks, 256, 0, c->stream>>>(c->pairs.as<uint2>(), cnt, d_chk + 2 * f);
+            checksum_kernel<<<blocks, 256, 0, c->stream>>>(c->pairs.as<uint2>(), cnt, 1, d_chk + 2 * f);
             c->launches++;
         }
         MB_CUDA(cudaMemcpyAsync(checksums2, d_chk, nf * 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
@@ -1742,9 +1789,17 @@ int mb_fill_pairs(MbCtx* h, uint64_t* ij, float* dist) {
             size_t m = std::min(chunk, P - off);
             MB_CUDA(cudaMemcpyAsync(hp, c.pairs.as<uint2>() + off, m * sizeof(uint2), cudaMemcpyDeviceToHost, c.stream));
             MB_CUDA(cudaStreamSynchronize(c.stream));
-            for (size_t k = 0; k < m; ++k) {
-                ij[2 * (off + k)] = hp[k].x;
-                ij[2 * (off + k) + 1] = hp[k].y;
+            if (c.last.kind == 1) {  // single search: canonical i < j (the device list is unordered)
+                for (size_t k = 0; k < m; ++k) {
+                    unsigned a = hp[k].x, b = hp[k].y;
+                    ij[2 * (off + k)] = a < b ? a : b;
+                    ij[2 * (off + k) + 1] = a < b ? b : a;
+                }
+            } else {
+                for (size_t k = 0; k < m; ++k) {
+                    ij[2 * (off + k)] = hp[k].x;
+                    ij[2 * (off + k) + 1] = hp[k].y;
+                }
             }
         }
     }
@@ -1786,7 +1841,7 @@ int mb_pairs_checksum(MbCtx* h, uint64_t out2[2]) {
     MB_CUDA(cudaMemsetAsync(d2, 0, 2 * sizeof(unsigned long long), c.stream));
     unsigned long long cnt = (unsigned long long)c.last.count;
     int blocks = (int)std::min<unsigned long long>((cnt + 255) / 256 + 1, (unsigned long long)c.sm_count * 16);
-    checksum_kernel<<<blocks, 256, 0, c.stream>>>(c.pairs.as<uint2>(), cnt, d2);
+    checksum_kernel<<<blocks, 256, 0, c.stream>>>(c.pairs.as<uint2>(), cnt, c.last.kind == 1 ? 1 : 0, d2);
     c.launches++;
     MB_CUDA(cudaMemcpyAsync(out2, d2, 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, c.stream));
     MB_CUDA(cudaStreamSynchronize(c.stream));
