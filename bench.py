@@ -205,8 +205,22 @@ def run_ours(args, wl):
             dist.barrier()
         torch.cuda.synchronize()
 
+    dev = torch.device("cuda", local)
+    ncol = {"search": 1, "fit": 1, "pipeline": 5}[kind]
+    scal = torch.zeros((F, ncol), dtype=torch.float64, device=dev)       # per-frame scalars of this rank
+    scal_host = torch.zeros((F, ncol), dtype=torch.float64).pin_memory()
+    gathered = torch.empty((world * F, ncol), dtype=torch.float64, device=dev)
+
+    def gather(res):
+        # per-frame scalars -> every rank (NCCL over NVLink; the only collective on the path)
+        scal_host.copy_(torch.from_numpy(np.asarray(res, dtype=np.float64).reshape(F, ncol)))
+        scal.copy_(scal_host, non_blocking=True)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, scal)
+
     for _ in range(max(args.warmup, 3)):
         res = step()
+    gather(res)  # warm the torch allocator / NCCL communicator outside the timed region
     traj.set_option("profile", 1)  # reset the kernel-time accumulators
     l0 = traj.launch_count()
     clocks = ClockSampler(local)
@@ -217,11 +231,8 @@ def run_ours(args, wl):
     e0.record(ext)
     for _ in range(args.steps):
         res = step()
-    # per-frame scalars -> every rank (NCCL over NVLink; the only collective on the path)
-    scal = torch.as_tensor(np.asarray(res, dtype=np.float64).reshape(F, -1), device=f"cuda:{local}")
-    if world > 1:
-        gathered = torch.empty((world * F, scal.shape[1]), dtype=torch.float64, device=f"cuda:{local}")
-        dist.all_gather_into_tensor(gathered, scal)
+    gather(res)
+    torch.cuda.current_stream().synchronize()
     e1.record(ext)
     barrier()
     ms = e0.elapsed_time(e1)

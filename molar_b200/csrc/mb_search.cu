@@ -21,6 +21,8 @@
 // uniform per (home fine cell, neighbour run) — nothing but the distance test is left per pair.
 #include <algorithm>
 #include <cfloat>
+#include <chrono>
+#include <cstdlib>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -32,7 +34,7 @@ namespace mb {
 constexpr unsigned DROPPED = 0xFFFFFFFFu;
 constexpr int MAX_REACH = 7;
 constexpr int MAX_ROWS = (2 * MAX_REACH + 1) * (2 * MAX_REACH + 1);
-constexpr int STAGE_CAP = 1024;  // pairs staged per warp before a flush (>= 32*32)
+constexpr int STAGE_CAP = 512;  // pairs staged per warp before a flush (>= 16 lanes * 32 home atoms)
 constexpr int SEARCH_WARPS = 8;
 
 struct GridSpec {
@@ -460,7 +462,7 @@ struct __align__(16) WarpShared {
 //           bit masks and expanded into the staging buffer afterwards.
 // MODE: 0 pairs, 1 pairs + distances, 2 count only
 template <int MODE>
-__global__ void __launch_bounds__(SEARCH_WARPS * 32, 2) search_cells_kernel(const __grid_constant__ SearchParams P) {
+__global__ void __launch_bounds__(SEARCH_WARPS * 32, 3) search_cells_kernel(const __grid_constant__ SearchParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const unsigned lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
     WarpShared& ws = reinterpret_cast<WarpShared*>(smem_raw)[wid];
@@ -686,16 +688,35 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32, 2) search_cells_kernel(cons
                     const int tot = __shfl_sync(0xffffffffu, inc, 31);
                     const int t0 = tot & 0xffff, t1 = tot >> 16;
                     if (t0 + t1 == 0) continue;
-                    // expand the masks into the staging buffer (two passes only if both halves do not fit)
-                    const int npass = (t0 + t1 <= STAGE_CAP) ? 1 : 2;
+                    // Expand the masks into the staging buffer.  Normally one pass; if the step found more
+                    // pairs than the buffer holds, per half (<= 1024) or per half and 16-lane group (<= 512).
+                    const int i0 = inc & 0xffff, i1 = inc >> 16;  // inclusive prefixes per half
+                    const int g15 = __shfl_sync(0xffffffffu, inc, 15);
+                    const int q0 = g15 & 0xffff, q1 = g15 >> 16;  // hits of lanes 0..15 per half
+                    const int npass = (t0 + t1 <= STAGE_CAP) ? 1 : ((t0 <= STAGE_CAP && t1 <= STAGE_CAP) ? 2 : 4);
 #pragma unroll 1
                     for (int pass = 0; pass < npass; ++pass) {
-                        const int need = npass == 1 ? t0 + t1 : (pass == 0 ? t0 : t1);
+                        bool use0 = true, use1 = true;
+                        int base0 = 0, base1 = t0, need = t0 + t1;
+                        if (npass == 2) {
+                            use0 = pass == 0;
+                            use1 = pass == 1;
+                            base1 = 0;
+                            need = pass ? t1 : t0;
+                        } else if (npass == 4) {
+                            const int hh = pass >> 1, grp = pass & 1;
+                            const bool act = (int)(lane >> 4) == grp;
+                            use0 = act && hh == 0;
+                            use1 = act && hh == 1;
+                            base0 = grp ? -q0 : 0;
+                            base1 = grp ? -q1 : 0;
+                            need = hh ? (grp ? t1 - q1 : q1) : (grp ? t0 - q0 : q0);
+                        }
                         if (stage_n + need > STAGE_CAP) warp_flush<MODE == 1>(stage, stage_d, stage_n, P, lane);
-                        unsigned e0 = (npass == 1 || pass == 0) ? m0 : 0u;
-                        unsigned e1 = (npass == 1 || pass == 1) ? m1 : 0u;
-                        uint2* sp0 = stage + (stage_n + (inc & 0xffff) - c0n);
-                        uint2* sp1 = stage + (stage_n + (npass == 1 ? t0 : 0) + (inc >> 16) - c1n);
+                        unsigned e0 = use0 ? m0 : 0u;
+                        unsigned e1 = use1 ? m1 : 0u;
+                        uint2* sp0 = stage + (stage_n + base0 + i0 - c0n);
+                        uint2* sp1 = stage + (stage_n + base1 + i1 - c1n);
                         float* dp0 = MODE == 1 ? stage_d + (sp0 - stage) : nullptr;
                         float* dp1 = MODE == 1 ? stage_d + (sp1 - stage) : nullptr;
                         const unsigned id0 = __float_as_uint(n0.w), id1 = __float_as_uint(n1.w);
@@ -1680,7 +1701,9 @@ int batch_search_impl(Ctx* c, float cutoff, uint8_t pbc, size_t f0, size_t f1, i
     unsigned long long* d_chk = d_cnt + 2 * nf;
     if (checksums2) MB_CUDA(cudaMemsetAsync(d_chk, 0, nf * 2 * sizeof(unsigned long long), c->stream));
     std::vector<unsigned long long> h_cnt(2 * nf);
+    const bool dbg = getenv("MB_DEBUG_TIMING") != nullptr;
     for (int attempt = 0; attempt < 2; ++attempt) {
+        auto t_a = std::chrono::steady_clock::now();
         for (size_t f = 0; f < nf; ++f) {
             const float* xyz = c->batch.as<float>() + (f0 + f) * n * 3;
             MB_TRY(enqueue_cells_search(c, xyz, nullptr, n, pl, cutoff, kmode, d_cnt + 2 * f));
@@ -1690,9 +1713,16 @@ int batch_search_impl(Ctx* c, float cutoff, uint8_t pbc, size_t f0, size_t f1, i
                 // -> simpler: checksum over min(count, cap) via a tiny indirection kernel below
             }
         }
+        auto t_b = std::chrono::steady_clock::now();
         MB_CUDA(cudaMemcpyAsync(h_cnt.data(), d_cnt, 2 * nf * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
         MB_CUDA(cudaStreamSynchronize(c->stream));
+        auto t_c = std::chrono::steady_clock::now();
         c->harvest_profile();
+        if (dbg)
+            fprintf(stderr, "[mb] batch_search attempt %d: enqueue %.3f ms, wait %.3f ms, frames %zu, cap %zu, ncells %zu k=(%d,%d,%d) hx=%d rows=%d\n",
+                    attempt, std::chrono::duration<double, std::milli>(t_b - t_a).count(),
+                    std::chrono::duration<double, std::milli>(t_c - t_b).count(), nf, c->pair_cap, pl.ncells,
+                    pl.g.k[0], pl.g.k[1], pl.g.k[2], pl.g.hx, pl.nrows);
         unsigned long long mx = 0;
         for (size_t f = 0; f < nf; ++f) mx = std::max(mx, h_cnt[2 * f]);
         if (kmode == 2 || mx <= c->pair_cap) break;

@@ -219,6 +219,30 @@ def test_config3_1m_triclinic_properties(mb):
     t.close()
 
 
+def test_single_pbc_dense_system_multipass_emission(mb):
+    """600 atoms/nm^3: one 64-candidate step finds more pairs than the per-warp staging buffer holds,
+    so the masks are expanded in several passes."""
+    M = np.diag([3.7, 3.8, 3.9]).astype(np.float32)
+    xyz = orc.synth_frame(SEED + 13, 0, 32000, M, stray_permille=10)
+    op, od, dims = oracle_single(1.2, xyz, box=M, pbc=7, nthreads=8)
+    assert list(dims) == [3, 3, 3]
+    for opts in ({}, {"subdiv": 1}, {"with_dist": 0}):
+        s = mb.System(xyz, box=M)
+        for k, v in opts.items():
+            s.set_option(k, v)
+        if opts.get("with_dist", 1):
+            pairs, dist = mb.distance_search(1.2, s(), dims=[True] * 3)
+            gp, gd = gpu_canonical(pairs, dist)
+            assert_same_pairs(gp, gd, op, od)
+        else:
+            cnt = mb._capi.check(s._lib.mb_search_single(s._h, 1.2, None, len(xyz), 7))
+            pairs = np.empty((cnt, 2), np.uint64)
+            mb._capi.check(s._lib.mb_fill_pairs(s._h, pairs.ctypes.data, None))
+            gp = orc.canonical_pairs(pairs)
+            assert len(gp) == cnt and np.array_equal(gp, op)
+        s.close()
+
+
 @pytest.mark.parametrize("exact", [0, 1])
 def test_single_pbc_big_box_filter_vs_exact_path(mb, exact):
     """Boxes large enough for the wrapped-pair filter (>= 4 reference cells per dim), strays
