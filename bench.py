@@ -185,8 +185,10 @@ def run_ours(args, wl):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n, box, F, kind = wl["n_atoms"], wl["box"], args.frames or wl["frames"], wl["kind"]
 
+    import shard
     traj = mb.Trajectory(device=local)
-    traj.synth(SEED, rank * F, F, n, box, mass_seed=SEED)  # rank r owns global frames [r*F, (r+1)*F)
+    f_first, f_last = shard.frame_block(rank, F)  # rank r owns global frames [r*F, (r+1)*F)
+    traj.synth(SEED, f_first, F, n, box, mass_seed=SEED)
     for kv in filter(None, args.opts.split(",")):
         key, val = kv.split("=")
         traj.set_option(key, float(val))
@@ -207,16 +209,13 @@ def run_ours(args, wl):
 
     dev = torch.device("cuda", local)
     ncol = {"search": 1, "fit": 1, "pipeline": 5}[kind]
-    scal = torch.zeros((F, ncol), dtype=torch.float64, device=dev)       # per-frame scalars of this rank
     scal_host = torch.zeros((F, ncol), dtype=torch.float64).pin_memory()
     gathered = torch.empty((world * F, ncol), dtype=torch.float64, device=dev)
 
     def gather(res):
         # per-frame scalars -> every rank (NCCL over NVLink; the only collective on the path)
-        scal_host.copy_(torch.from_numpy(np.asarray(res, dtype=np.float64).reshape(F, ncol)))
-        scal.copy_(scal_host, non_blocking=True)
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, scal)
+        return shard.gather_rows(np.asarray(res, dtype=np.float64).reshape(F, ncol), world, device=dev,
+                                 out=gathered, stage=scal_host)
 
     for _ in range(max(args.warmup, 3)):
         res = step()

@@ -120,7 +120,7 @@ struct Ctx {
     int opt_subdiv_xyz[3] = {0, 0, 0};  // per-dimension override of the tile subdivision
     int opt_slice_x = 0;      // home tile = this many fine cells along x (0 = automatic)
     int opt_force_brute = 0;  // force the general all-pairs kernel
-    double opt_atoms_per_cell = 12.0;
+    double opt_atoms_per_cell = 8.0;  // minimum mean population of a home tile
     int opt_with_dist = 1;
     int opt_exact_pbc = 0;    // 1: wrapped cell pairs always use the exact PeriodicBox path (no filter)
     int opt_profile = 0;      // record CUDA events around every search-kernel launch

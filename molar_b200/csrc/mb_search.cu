@@ -1124,7 +1124,7 @@ static void plan_cells(const Ctx* c, Plan& pl, float cutoff, size_t n) {
     int k[3];
     for (int d = 0; d < 3; ++d) {
         if (c->opt_subdiv > 0) k[d] = c->opt_subdiv;
-        else k[d] = (int)std::floor(tref[d] / (0.5 * rc) + 0.5);
+        else k[d] = (int)std::floor(tref[d] / (0.42 * rc) + 0.5);  // tile edge ~0.4-0.55 cutoff (swept on B200)
         k[d] = std::max(1, std::min(k[d], 8));
     }
     // keep enough atoms per fine cell for the home loop to amortise its per-run overhead
@@ -1143,7 +1143,7 @@ static void plan_cells(const Ctx* c, Plan& pl, float cutoff, size_t n) {
     if (c->opt_subdiv_xyz[0] > 0) k[0] = std::min(c->opt_subdiv_xyz[0], 8);
     if (c->opt_subdiv_xyz[1] > 0) k[1] = std::min(c->opt_subdiv_xyz[1], 8);
     if (c->opt_subdiv_xyz[2] > 0) k[2] = std::min(c->opt_subdiv_xyz[2], 8);
-    int hx = c->opt_slice_x > 0 ? std::min(c->opt_slice_x, 8) : 1;
+    int hx = c->opt_slice_x > 0 ? std::min(c->opt_slice_x, 8) : 3;  // x slices per home tile (swept on B200)
     for (int attempt = 0; attempt < 16; ++attempt) {
         // fine-cell lattice: tiles of k[] per reference cell, each tile sliced hx times along x
         const int kf[3] = {k[0] * hx, k[1], k[2]};
