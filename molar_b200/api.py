@@ -57,6 +57,8 @@ class System:
         if not self._h:
             raise MolarB200Error(_capi.MB_ERR_CUDA, _capi.last_error())
         self._n = 0
+        self._version = 0        # bumped whenever the device frame changes
+        self._frame2_of = None   # (other system id, its version) currently staged as frame2
         self.box = None
         self.set_state(coords, box)
         if masses is not None:
@@ -86,6 +88,7 @@ class System:
         b9 = box.colmajor9.ctypes.data_as(f32p) if box is not None else None
         check(self._lib.mb_set_frame(self._h, xyz.ctypes.data, xyz.shape[0], b9))
         self._n = xyz.shape[0]
+        self._version += 1
 
     def set_masses(self, masses):
         m = np.ascontiguousarray(masses, dtype=np.float32).reshape(-1)
@@ -153,14 +156,18 @@ class Sel:
         t3 = np.ascontiguousarray(tr.t, dtype=np.float64)
         p, n = self._ids()
         check(self.sys._lib.mb_apply_transform(self.sys._h, p, n, R9.ctypes.data_as(f64p), t3.ctypes.data_as(f64p)))
+        self.sys._version += 1
 
 
 def _same_or_frame2(sel1, sel2):
     """sel2 may live in another System (the reference structure): stage its frame as frame2."""
     if sel2.sys is sel1.sys:
         return 0
-    xyz2 = sel2.sys.coords()
-    check(sel1.sys._lib.mb_set_frame2(sel1.sys._h, xyz2.ctypes.data, xyz2.shape[0]))
+    tag = (id(sel2.sys), sel2.sys._version)
+    if sel1.sys._frame2_of != tag:  # re-stage only when the other system's frame changed
+        xyz2 = sel2.sys.coords()
+        check(sel1.sys._lib.mb_set_frame2(sel1.sys._h, xyz2.ctypes.data, xyz2.shape[0]))
+        sel1.sys._frame2_of = tag
     return 1
 
 

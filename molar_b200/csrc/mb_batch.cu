@@ -165,10 +165,8 @@ int mb_batch_pipeline(MbCtx* h, float cutoff, uint8_t pbc_dims, size_t f0, size_
     size_t part_bytes = nf * (size_t)nb * 5 * sizeof(double);
     size_t cnt_bytes = nf * 2 * sizeof(unsigned long long);
     size_t need = tick_bytes + rows8_bytes + part_bytes + cnt_bytes;
-    bool fresh = need > c.batch_tmp.cap;
     MB_TRY(c.batch_tmp.reserve(need));
     // batch_tmp is shared with batch_search's counters: tickets must be clean on entry
-    (void)fresh;
     MB_CUDA(cudaMemsetAsync(c.batch_tmp.p, 0, tick_bytes, c.stream));
     char* base = static_cast<char*>(c.batch_tmp.p);
     unsigned* tickets = reinterpret_cast<unsigned*>(base);
@@ -189,6 +187,7 @@ int mb_batch_pipeline(MbCtx* h, float cutoff, uint8_t pbc_dims, size_t f0, size_
     c.batch_row_doubles = 5;
     if (out) MB_CUDA(cudaMemcpyAsync(out, c.batch_scalars.p, nf * 5 * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
     MB_CUDA(cudaStreamSynchronize(c.stream));
+    c.harvest_profile();
     return MB_OK;
 }
 
