@@ -462,7 +462,7 @@ struct __align__(16) WarpShared {
 //           bit masks and expanded into the staging buffer afterwards.
 // MODE: 0 pairs, 1 pairs + distances, 2 count only
 template <int MODE>
-__global__ void __launch_bounds__(SEARCH_WARPS * 32, 3) search_cells_kernel(const __grid_constant__ SearchParams P) {
+__global__ void __launch_bounds__(SEARCH_WARPS * 32, 4) search_cells_kernel(const __grid_constant__ SearchParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const unsigned lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
     WarpShared& ws = reinterpret_cast<WarpShared*>(smem_raw)[wid];
