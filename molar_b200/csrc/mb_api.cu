@@ -217,6 +217,9 @@ void mb_close(MbCtx* h) {
     for (DevBuf* b : bufs) b->release();
     free_plan_cache(&c);
     if (c.h_pinned) cudaFreeHost(c.h_pinned);
+    for (int i = 0; i < 2; ++i)
+        if (c.aux_stream[i]) cudaStreamDestroy(c.aux_stream[i]);
+    if (c.aux_event) cudaEventDestroy(c.aux_event);
     cudaStreamDestroy(c.stream);
     delete h;
 }

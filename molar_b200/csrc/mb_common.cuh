@@ -80,6 +80,8 @@ struct SearchResult {
 struct Ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t aux_stream[2] = {nullptr, nullptr};  // batch_fit alternates frame groups over these
+    cudaEvent_t aux_event = nullptr;
     int sm_count = 148;
     uint64_t launches = 0;
 

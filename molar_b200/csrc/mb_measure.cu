@@ -172,7 +172,7 @@ __device__ __forceinline__ void fit_finalize(const double* res, const double o1[
 }
 
 template <bool SEP2>
-__global__ void __launch_bounds__(RED_THREADS) fit_moments_kernel(const float* __restrict__ xyz1_base, size_t stride1,
+__global__ void __launch_bounds__(RED_THREADS, 3) fit_moments_kernel(const float* __restrict__ xyz1_base, size_t stride1,
                                                                   const unsigned long long* __restrict__ ids1,
                                                                   const float* __restrict__ xyz2,
                                                                   const unsigned long long* __restrict__ ids2, int n,
@@ -404,30 +404,49 @@ int batch_fit_impl(Ctx* c, size_t ref_frame, size_t f0, size_t f1, int superpose
     MB_CUDA(cudaMemcpyAsync(c->batch_ref.p, c->batch.as<float>() + ref_frame * n * 3, n * 3 * sizeof(float),
                             cudaMemcpyDeviceToDevice, c->stream));
     const float* ref = c->batch_ref.as<float>();
-    // group frames so that a group (moments pass + superposition pass) stays L2-resident
+    // Group frames so that a group (moments pass + superposition pass) stays L2-resident, and
+    // alternate groups over two streams so that the serial tail of one group's kernels (last-block
+    // reduction + 3x3 SVD on one thread) overlaps the streaming part of the other group's.
     const size_t frame_bytes = n * 12;
-    size_t group = std::max<size_t>(1, std::min<size_t>(nf, (size_t)(48u << 20) / std::max<size_t>(frame_bytes, 1)));
-    group = std::min<size_t>(group, 4096);
+    size_t group = std::max<size_t>(1, std::min<size_t>(nf, (size_t)(40u << 20) / std::max<size_t>(frame_bytes, 1)));
+    group = std::min<size_t>(group, 2048);
     int nb = (int)std::max<size_t>(1, std::min<size_t>((n + RED_THREADS * 8 - 1) / (RED_THREADS * 8),
-                                                      std::max<size_t>(1, (size_t)c->sm_count * 4 / group)));
+                                                      std::max<size_t>(1, (size_t)c->sm_count * 6 / group)));
+    constexpr int NS = 2;
+    for (int i = 0; i < NS; ++i)
+        if (!c->aux_stream[i]) MB_CUDA(cudaStreamCreateWithFlags(&c->aux_stream[i], cudaStreamNonBlocking));
+    if (!c->aux_event) MB_CUDA(cudaEventCreateWithFlags(&c->aux_event, cudaEventDisableTiming));
     RedScratch s;
-    // tickets: 2 per frame slot (fit, superpose); results: 16 doubles per frame for the whole range + rmsd
-    MB_TRY(red_scratch(c, 2 * group, (size_t)group * nb * 16 + (size_t)group * nb, nf * 17, &s));
+    // per stream: tickets for 2 kernels x group frames, partials for both kernels;
+    // results: 16 doubles per frame for the whole range + rmsd
+    const size_t part_per_stream = (size_t)group * nb * 17;
+    MB_TRY(red_scratch(c, (size_t)NS * 2 * group, (size_t)NS * part_per_stream, nf * 17, &s));
     double* fitres = s.results;
     double* d_rmsd = s.results + nf * 16;
-    double* part_fit = s.partials;
-    double* part_sup = s.partials + (size_t)group * nb * 16;
-    for (size_t g0 = 0; g0 < nf; g0 += group) {
+    // the aux streams start after everything already queued on the context stream (the ref copy)
+    MB_CUDA(cudaEventRecord(c->aux_event, c->stream));
+    for (int i = 0; i < NS; ++i) MB_CUDA(cudaStreamWaitEvent(c->aux_stream[i], c->aux_event, 0));
+    size_t gi = 0;
+    for (size_t g0 = 0; g0 < nf; g0 += group, ++gi) {
+        const int si = (int)(gi % NS);
+        cudaStream_t st = c->aux_stream[si];
         size_t gn = std::min(group, nf - g0);
         float* base = c->batch.as<float>() + (f0 + g0) * n * 3;
-        fit_moments_kernel<false><<<dim3(nb, (unsigned)gn), RED_THREADS, 0, c->stream>>>(
-            base, n * 3, nullptr, ref, nullptr, (int)n, c->masses.as<float>(), 0, part_fit, s.tickets,
-            fitres + g0 * 16);
-        superpose_rmsd_kernel<<<dim3(nb, (unsigned)gn), RED_THREADS, 0, c->stream>>>(
-            base, n * 3, ref, (int)n, fitres + g0 * 16, superpose, part_sup, s.tickets + group, d_rmsd + g0);
+        double* part_fit = s.partials + (size_t)si * part_per_stream;
+        double* part_sup = part_fit + (size_t)group * nb * 16;
+        unsigned* tick = s.tickets + (size_t)si * 2 * group;
+        fit_moments_kernel<false><<<dim3(nb, (unsigned)gn), RED_THREADS, 0, st>>>(
+            base, n * 3, nullptr, ref, nullptr, (int)n, c->masses.as<float>(), 0, part_fit, tick, fitres + g0 * 16);
+        superpose_rmsd_kernel<<<dim3(nb, (unsigned)gn), RED_THREADS, 0, st>>>(
+            base, n * 3, ref, (int)n, fitres + g0 * 16, superpose, part_sup, tick + group, d_rmsd + g0);
         c->launches += 2;
     }
     MB_CUDA(cudaGetLastError());
+    // join: the context stream continues after both aux streams
+    for (int i = 0; i < NS; ++i) {
+        MB_CUDA(cudaEventRecord(c->aux_event, c->aux_stream[i]));
+        MB_CUDA(cudaStreamWaitEvent(c->stream, c->aux_event, 0));
+    }
     if (rmsd_out) {
         MB_CUDA(cudaMemcpyAsync(rmsd_out, d_rmsd, nf * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     }
