@@ -317,6 +317,191 @@ __global__ void __launch_bounds__(RED_THREADS) superpose_rmsd_kernel(float* __re
 }
 
 // ---------------------------------------------------------------------------------------------
+// Fused, persistent Kabsch fit + superposition + RMSD over a block of device-resident frames
+// (config 4).  One cooperative launch; the grid is exactly the number of co-resident CTAs.  CTA b
+// owns slice b (a contiguous atom range) of EVERY frame:
+//   * the slice of the reference frame and of the mass column is staged in shared memory once;
+//   * the slice of frame f is brought in by ONE 1-D TMA bulk copy (cp.async.bulk + mbarrier),
+//     three buffers deep, so HBM latency is hidden behind the f64 arithmetic of the previous frame;
+//   * pass 1 accumulates the Kabsch moments from shared memory, the per-frame partials are folded
+//     by the last CTA to arrive, which also runs the 3x3 SVD and publishes (R,t) with a release flag;
+//   * pass 2 of frame f is delayed by one frame (so the SVD latency is hidden), transforms the
+//     slice in place in shared memory, accumulates sum |Rp+t-ref|^2 and writes the slice back with one
+//     TMA bulk store.
+// HBM traffic per frame: 12 B/atom read + 12 B/atom written — the algorithmic minimum.
+// ---------------------------------------------------------------------------------------------
+constexpr int FUSED_THREADS = 256;
+constexpr int FUSED_NBUF = 3;
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    unsigned ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void bulk_load(void* dst_smem, const void* src_gmem, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_store(void* dst_gmem, const void* src_smem, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)),
+                 "r"(bytes)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+struct FusedParams {
+    float* frames;        // [nf][n][3], superposed in place
+    const float* ref;     // [n][3]
+    const float* masses;  // [n]
+    int n, nf, slice;     // atoms per slice (multiple of 4)
+    int superpose;
+    double* part_fit;     // [nf][grid][16]
+    double* part_sup;     // [nf][grid]
+    unsigned* tick_fit;   // [nf]
+    unsigned* tick_sup;   // [nf]
+    unsigned* flag;       // [nf]  1 when fitres[f] is valid
+    double* fitres;       // [nf][16]
+    double* rmsd;         // [nf]
+};
+
+__global__ void __launch_bounds__(FUSED_THREADS, 2) fit_fused_kernel(const FusedParams P) {
+    extern __shared__ __align__(128) unsigned char fsm[];
+    const int slice = P.slice;
+    float* buf[FUSED_NBUF];
+    for (int i = 0; i < FUSED_NBUF; ++i) buf[i] = reinterpret_cast<float*>(fsm) + (size_t)i * slice * 3;
+    float* sref = reinterpret_cast<float*>(fsm) + (size_t)FUSED_NBUF * slice * 3;
+    float* smass = sref + (size_t)slice * 3;
+    __shared__ __align__(8) unsigned long long bar[FUSED_NBUF];
+    __shared__ double res[16];
+    __shared__ double sRt[12];
+
+    const int b = blockIdx.x, nblk = gridDim.x;
+    const int a0 = b * slice;
+    const int cnt = max(0, min(slice, P.n - a0));  // atoms of this CTA's slice
+    const unsigned bytes = (unsigned)cnt * 12u;
+    const int tid = threadIdx.x;
+
+    if (tid == 0) {
+        for (int i = 0; i < FUSED_NBUF; ++i) mbar_init(&bar[i], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // reference slice + masses: resident for the whole kernel
+    for (int i = tid; i < cnt * 3; i += FUSED_THREADS) sref[i] = P.ref[(size_t)a0 * 3 + i];
+    for (int i = tid; i < cnt; i += FUSED_THREADS) smass[i] = P.masses[a0 + i];
+    __syncthreads();
+    auto prefetch = [&](int f) {
+        if (tid == 0 && cnt > 0 && f < P.nf) {
+            unsigned long long* br = &bar[f % FUSED_NBUF];
+            mbar_expect_tx(br, bytes);
+            bulk_load(buf[f % FUSED_NBUF], P.frames + ((size_t)f * P.n + a0) * 3, bytes, br);
+        }
+    };
+    prefetch(0);
+    prefetch(1);
+    const double o2x = P.ref[0], o2y = P.ref[1], o2z = P.ref[2];  // pivot of the reference frame: atom 0
+
+    auto pass2 = [&](int f) {
+        // wait for (R,t) of frame f
+        if (tid == 0) {
+            const volatile unsigned* fl = P.flag + f;
+            while (*fl == 0u) { }
+            __threadfence();
+        }
+        __syncthreads();
+        if (tid < 12) sRt[tid] = __ldcg(&P.fitres[(size_t)f * 16 + tid]);
+        __syncthreads();
+        double R[9], t[3];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) R[i] = sRt[i];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) t[i] = sRt[9 + i];
+        float* x = buf[f % FUSED_NBUF];
+        double v[1] = {0.0};
+        for (int i = tid; i < cnt; i += FUSED_THREADS) {
+            const double px0 = x[3 * i], py0 = x[3 * i + 1], pz0 = x[3 * i + 2];
+            const double px = R[0] * px0 + R[1] * py0 + R[2] * pz0 + t[0];
+            const double py = R[3] * px0 + R[4] * py0 + R[5] * pz0 + t[1];
+            const double pz = R[6] * px0 + R[7] * py0 + R[8] * pz0 + t[2];
+            const double dx = px - (double)sref[3 * i], dy = py - (double)sref[3 * i + 1], dz = pz - (double)sref[3 * i + 2];
+            v[0] += dx * dx + dy * dy + dz * dz;
+            if (P.superpose) {
+                x[3 * i] = (float)px;
+                x[3 * i + 1] = (float)py;
+                x[3 * i + 2] = (float)pz;
+            }
+        }
+        if (P.superpose) {
+            fence_async_smem();  // make the generic-proxy writes visible to the bulk store
+            __syncthreads();
+            if (tid == 0 && cnt > 0) bulk_store(P.frames + ((size_t)f * P.n + a0) * 3, x, bytes);
+        }
+        __shared__ double r2[1];
+        if (grid_reduce<1, FUSED_THREADS>(v, P.part_sup + (size_t)f * nblk, P.tick_sup + f, b, nblk, r2)) {
+            if (tid == 0) P.rmsd[f] = sqrt(r2[0] / (double)P.n);
+        }
+        // the buffer may be refilled (async proxy) only after the bulk store has finished reading it
+        // and after every thread's generic-proxy accesses to it are ordered before the refill
+        if (tid == 0 && P.superpose) bulk_store_wait_read();
+        fence_async_smem();
+        __syncthreads();
+    };
+
+    for (int f = 0; f < P.nf; ++f) {
+        float* x = buf[f % FUSED_NBUF];
+        if (cnt > 0) mbar_wait(&bar[f % FUSED_NBUF], (unsigned)((f / FUSED_NBUF) & 1));
+        // ---- pass 1: Kabsch moments of this slice (pivots: atom 0 of the frame / of the reference)
+        const float* fr0 = P.frames + (size_t)f * P.n * 3;
+        const double o1x = __ldcg(fr0), o1y = __ldcg(fr0 + 1), o1z = __ldcg(fr0 + 2);
+        double v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = 0.0;
+        for (int i = tid; i < cnt; i += FUSED_THREADS) {
+            const double m = smass[i];
+            const double q1x = (double)x[3 * i] - o1x, q1y = (double)x[3 * i + 1] - o1y, q1z = (double)x[3 * i + 2] - o1z;
+            const double q2x = (double)sref[3 * i] - o2x, q2y = (double)sref[3 * i + 1] - o2y, q2z = (double)sref[3 * i + 2] - o2z;
+            v[0] += m;
+            v[1] += m * q1x; v[2] += m * q1y; v[3] += m * q1z;
+            const double wx = m * q2x, wy = m * q2y, wz = m * q2z;
+            v[4] += wx; v[5] += wy; v[6] += wz;
+            v[7] += wx * q1x;  v[8] += wx * q1y;  v[9] += wx * q1z;
+            v[10] += wy * q1x; v[11] += wy * q1y; v[12] += wy * q1z;
+            v[13] += wz * q1x; v[14] += wz * q1y; v[15] += wz * q1z;
+        }
+        if (grid_reduce<16, FUSED_THREADS>(v, P.part_fit + (size_t)f * nblk * 16, P.tick_fit + f, b, nblk, res)) {
+            if (tid == 0) {
+                const double o1[3] = {o1x, o1y, o1z}, o2[3] = {o2x, o2y, o2z};
+                fit_finalize<false>(res, o1, o2, 0, P.fitres + (size_t)f * 16);
+                __threadfence();
+                atomicExch(P.flag + f, 1u);
+            }
+        }
+        __syncthreads();
+        // ---- pass 2 of the previous frame (its SVD ran while this CTA was busy with pass 1 above)
+        if (f > 0) pass2(f - 1);
+        prefetch(f + 2);  // f == 0: the third buffer; else the buffer pass2(f-1) just released
+    }
+    pass2(P.nf - 1);
+}
+
+// ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
 static int upload_ids(Ctx* c, DevBuf& buf, const uint64_t* ids, size_t n, const unsigned long long** out) {
@@ -404,6 +589,55 @@ int batch_fit_impl(Ctx* c, size_t ref_frame, size_t f0, size_t f1, int superpose
     MB_CUDA(cudaMemcpyAsync(c->batch_ref.p, c->batch.as<float>() + ref_frame * n * 3, n * 3 * sizeof(float),
                             cudaMemcpyDeviceToDevice, c->stream));
     const float* ref = c->batch_ref.as<float>();
+    // ---- fused persistent path (TMA-staged slices; 12 B/atom read + 12 B/atom written per frame) ----
+    {
+        int occ = 0;
+        const int sm = c->sm_count;
+        // try 2 CTAs/SM first, then 1
+        for (int want = 2; want >= 1 && !c->opt_no_fused_fit; --want) {
+            int grid = sm * want;
+            int slice = (int)(((n + grid - 1) / grid + 3) / 4 * 4);
+            size_t smem = (size_t)slice * (FUSED_NBUF + 1) * 12 + (size_t)slice * 4;
+            if (smem > (size_t)(want == 2 ? 100 : 200) * 1024) continue;
+            if ((n % 4) != 0 || (reinterpret_cast<uintptr_t>(c->batch.p) & 15u)) break;
+            MB_CUDA(cudaFuncSetAttribute(fit_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            MB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fit_fused_kernel, FUSED_THREADS, smem));
+            if (occ < want) continue;
+            const size_t chunk = std::min<size_t>(nf, 256);
+            RedScratch s;
+            MB_TRY(red_scratch(c, 3 * chunk, chunk * (size_t)grid * 17, nf * 17, &s));
+            double* fitres = s.results;
+            double* d_rmsd = s.results + nf * 16;
+            for (size_t g0 = 0; g0 < nf; g0 += chunk) {
+                const size_t gn = std::min(chunk, nf - g0);
+                FusedParams P;
+                P.frames = c->batch.as<float>() + (f0 + g0) * n * 3;
+                P.ref = ref;
+                P.masses = c->masses.as<float>();
+                P.n = (int)n;
+                P.nf = (int)gn;
+                P.slice = slice;
+                P.superpose = superpose;
+                P.part_fit = s.partials;
+                P.part_sup = s.partials + chunk * (size_t)grid * 16;
+                P.tick_fit = s.tickets;
+                P.tick_sup = s.tickets + chunk;
+                P.flag = s.tickets + 2 * chunk;
+                P.fitres = fitres + g0 * 16;
+                P.rmsd = d_rmsd + g0;
+                MB_CUDA(cudaMemsetAsync(P.flag, 0, gn * sizeof(unsigned), c->stream));
+                void* args[] = {&P};
+                MB_CUDA(cudaLaunchCooperativeKernel((const void*)fit_fused_kernel, dim3(grid), dim3(FUSED_THREADS), args,
+                                                    smem, c->stream));
+                c->launches++;
+            }
+            if (rmsd_out)
+                MB_CUDA(cudaMemcpyAsync(rmsd_out, d_rmsd, nf * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+            MB_CUDA(cudaStreamSynchronize(c->stream));
+            return MB_OK;
+        }
+    }
+    // ---- two-kernel path (any n, any alignment) ----
     // Group frames so that a group (moments pass + superposition pass) stays L2-resident, and
     // alternate groups over two streams so that the serial tail of one group's kernels (last-block
     // reduction + 3x3 SVD on one thread) overlaps the streaming part of the other group's.

@@ -144,6 +144,36 @@ def test_batch_fit_config4_shape(mb):
     t.close()
 
 
+@pytest.mark.parametrize("n,nf", [(100_000, 9), (99_999, 4), (2048, 5)])
+def test_batch_fit_fused_vs_two_kernel_path(mb, n, nf):
+    """The persistent TMA-staged kernel and the generic two-kernel path must agree with the oracle
+    (n % 4 != 0 takes the generic path by construction)."""
+    m = orc.synth_masses(SEED, n)
+    ref = orc.synth_frame(SEED, 0, n, TRIC)
+    out = {}
+    for no_fused in (0, 1):
+        t = mb.Trajectory()
+        t.synth(SEED, 0, nf, n, TRIC, mass_seed=SEED)
+        t.set_option("no_fused_fit", no_fused)
+        before = t.frame(nf - 1)
+        r = t.fit(ref_frame=0, superpose=True)
+        rc, R, tt = orc.fit_transform(before, m, None, ref, m, None)
+        exp = orc.apply_transform_f64(before, None, R, tt)
+        exp_r = np.sqrt(((exp - ref) ** 2).sum(1).mean())
+        assert abs(r[nf - 1] - exp_r) <= RTOL * exp_r + 1e-9
+        assert np.allclose(t.frame(nf - 1), exp, rtol=RTOL, atol=2e-6)
+        out[no_fused] = (r, t.frame(1))
+        # fit only (no superposition) leaves the frames untouched
+        t2 = mb.Trajectory()
+        t2.synth(SEED, 0, 2, n, TRIC, mass_seed=SEED)
+        t2.set_option("no_fused_fit", no_fused)
+        r2 = t2.fit(ref_frame=0, superpose=False)
+        assert np.array_equal(t2.frame(1), orc.synth_frame(SEED, 1, n, TRIC)) and abs(r2[1] - r[1]) <= 1e-9 * r[1]
+        t.close()
+        t2.close()
+    assert np.allclose(out[0][0], out[1][0], rtol=1e-10) and np.allclose(out[0][1], out[1][1], atol=1e-6)
+
+
 def test_batch_pipeline_config5_shape(mb):
     n, nf = 200_000, 3
     box = (TRIC * np.float32(0.6)).astype(np.float32)
