@@ -331,7 +331,7 @@ __global__ void __launch_bounds__(RED_THREADS) superpose_rmsd_kernel(float* __re
 // HBM traffic per frame: 12 B/atom read + 12 B/atom written — the algorithmic minimum.
 // ---------------------------------------------------------------------------------------------
 constexpr int FUSED_THREADS = 256;
-constexpr int FUSED_NBUF = 3;
+constexpr int FUSED_NBUF = 4;
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
@@ -382,6 +382,30 @@ struct FusedParams {
     double* rmsd;         // [nf]
 };
 
+// block-level sum of K doubles per thread -> sh_out[K] (valid in all threads after return)
+template <int K>
+__device__ __forceinline__ void block_sum(double (&v)[K], double* sh_out) {
+    __shared__ double shw[FUSED_THREADS / 32][K];
+    const unsigned lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        double x = v[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        if (lane == 0) shw[wid][k] = x;
+    }
+    __syncthreads();
+    if (threadIdx.x < K) {
+        double x = 0;
+#pragma unroll
+        for (int w = 0; w < FUSED_THREADS / 32; ++w) x += shw[w][threadIdx.x];
+        sh_out[threadIdx.x] = x;
+    }
+    __syncthreads();
+}
+
+constexpr int FUSED_DELAY = 2;  // pass 2 of frame f runs during iteration f + FUSED_DELAY
+
 __global__ void __launch_bounds__(FUSED_THREADS, 2) fit_fused_kernel(const FusedParams P) {
     extern __shared__ __align__(128) unsigned char fsm[];
     const int slice = P.slice;
@@ -392,12 +416,14 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) fit_fused_kernel(const Fused
     __shared__ __align__(8) unsigned long long bar[FUSED_NBUF];
     __shared__ double res[16];
     __shared__ double sRt[12];
+    __shared__ double r2[1];
 
     const int b = blockIdx.x, nblk = gridDim.x;
     const int a0 = b * slice;
     const int cnt = max(0, min(slice, P.n - a0));  // atoms of this CTA's slice
     const unsigned bytes = (unsigned)cnt * 12u;
     const int tid = threadIdx.x;
+    const unsigned lane = tid & 31u, wid = tid >> 5;
 
     if (tid == 0) {
         for (int i = 0; i < FUSED_NBUF; ++i) mbar_init(&bar[i], 1);
@@ -414,12 +440,11 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) fit_fused_kernel(const Fused
             bulk_load(buf[f % FUSED_NBUF], P.frames + ((size_t)f * P.n + a0) * 3, bytes, br);
         }
     };
-    prefetch(0);
-    prefetch(1);
+    for (int f = 0; f < FUSED_NBUF - FUSED_DELAY; ++f) prefetch(f);
     const double o2x = P.ref[0], o2y = P.ref[1], o2z = P.ref[2];  // pivot of the reference frame: atom 0
 
     auto pass2 = [&](int f) {
-        // wait for (R,t) of frame f
+        // wait for (R,t) of frame f (published FUSED_DELAY frames ago by that frame's finisher CTA)
         if (tid == 0) {
             const volatile unsigned* fl = P.flag + f;
             while (*fl == 0u) { }
@@ -448,18 +473,15 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) fit_fused_kernel(const Fused
                 x[3 * i + 2] = (float)pz;
             }
         }
-        if (P.superpose) {
-            fence_async_smem();  // make the generic-proxy writes visible to the bulk store
-            __syncthreads();
-            if (tid == 0 && cnt > 0) bulk_store(P.frames + ((size_t)f * P.n + a0) * 3, x, bytes);
+        if (P.superpose) fence_async_smem();  // generic-proxy writes -> visible to the bulk store
+        block_sum<1>(v, r2);                  // (contains the __syncthreads the store needs)
+        if (tid == 0) {
+            P.part_sup[(size_t)f * nblk + b] = r2[0];  // folded in block order by finish_rmsd_kernel
+            if (P.superpose && cnt > 0) {
+                bulk_store(P.frames + ((size_t)f * P.n + a0) * 3, x, bytes);
+                bulk_store_wait_read();  // the buffer may be refilled only after the store has read it
+            }
         }
-        __shared__ double r2[1];
-        if (grid_reduce<1, FUSED_THREADS>(v, P.part_sup + (size_t)f * nblk, P.tick_sup + f, b, nblk, r2)) {
-            if (tid == 0) P.rmsd[f] = sqrt(r2[0] / (double)P.n);
-        }
-        // the buffer may be refilled (async proxy) only after the bulk store has finished reading it
-        // and after every thread's generic-proxy accesses to it are ordered before the refill
-        if (tid == 0 && P.superpose) bulk_store_wait_read();
         fence_async_smem();
         __syncthreads();
     };
@@ -485,20 +507,54 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) fit_fused_kernel(const Fused
             v[10] += wy * q1x; v[11] += wy * q1y; v[12] += wy * q1z;
             v[13] += wz * q1x; v[14] += wz * q1y; v[15] += wz * q1z;
         }
-        if (grid_reduce<16, FUSED_THREADS>(v, P.part_fit + (size_t)f * nblk * 16, P.tick_fit + f, b, nblk, res)) {
+        block_sum<16>(v, res);
+        // publish this CTA's partial and arrive WITHOUT waiting for the counter's old value: only the
+        // frame's finisher CTA (role rotates: f % grid) ever waits on the ticket
+        if (tid < 16) P.part_fit[((size_t)f * nblk + b) * 16 + tid] = res[tid];
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) atomicAdd(P.tick_fit + f, 1u);
+        if (b == f % nblk) {
+            if (tid == 0) {
+                const volatile unsigned* tk = P.tick_fit + f;
+                while (*tk < (unsigned)nblk) { }
+                __threadfence();
+            }
+            __syncthreads();
+            const double* part = P.part_fit + (size_t)f * nblk * 16;
+            for (int k = (int)wid; k < 16; k += FUSED_THREADS / 32) {
+                double xsum = 0;
+                for (int bb = (int)lane; bb < nblk; bb += 32) xsum += __ldcg(&part[(size_t)bb * 16 + k]);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) xsum += __shfl_xor_sync(0xffffffffu, xsum, o);
+                if (lane == 0) res[k] = xsum;
+            }
+            __syncthreads();
             if (tid == 0) {
                 const double o1[3] = {o1x, o1y, o1z}, o2[3] = {o2x, o2y, o2z};
                 fit_finalize<false>(res, o1, o2, 0, P.fitres + (size_t)f * 16);
                 __threadfence();
                 atomicExch(P.flag + f, 1u);
+                P.tick_fit[f] = 0;  // re-arm
             }
+            __syncthreads();
         }
-        __syncthreads();
-        // ---- pass 2 of the previous frame (its SVD ran while this CTA was busy with pass 1 above)
-        if (f > 0) pass2(f - 1);
-        prefetch(f + 2);  // f == 0: the third buffer; else the buffer pass2(f-1) just released
+        // ---- pass 2 of an earlier frame (its fold + SVD ran while the grid moved on)
+        if (f >= FUSED_DELAY) pass2(f - FUSED_DELAY);
+        prefetch(f + FUSED_NBUF - FUSED_DELAY);  // into the buffer released just now (or still unused)
     }
-    pass2(P.nf - 1);
+    for (int f = max(0, P.nf - FUSED_DELAY); f < P.nf; ++f) pass2(f);
+}
+
+// rmsd[f] = sqrt(sum_b part[f][b] / n), partials folded in block order (deterministic)
+__global__ void __launch_bounds__(32) finish_rmsd_kernel(const double* __restrict__ part, int nblk, int n,
+                                                         double* __restrict__ rmsd) {
+    const int f = blockIdx.x;
+    double x = 0;
+    for (int b = threadIdx.x; b < nblk; b += 32) x += part[(size_t)f * nblk + b];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    if (threadIdx.x == 0) rmsd[f] = sqrt(x / (double)n);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -598,7 +654,7 @@ int batch_fit_impl(Ctx* c, size_t ref_frame, size_t f0, size_t f1, int superpose
             int grid = sm * want;
             int slice = (int)(((n + grid - 1) / grid + 3) / 4 * 4);
             size_t smem = (size_t)slice * (FUSED_NBUF + 1) * 12 + (size_t)slice * 4;
-            if (smem > (size_t)(want == 2 ? 100 : 200) * 1024) continue;
+            if (smem > (size_t)(want == 2 ? 110 : 220) * 1024) continue;
             if ((n % 4) != 0 || (reinterpret_cast<uintptr_t>(c->batch.p) & 15u)) break;
             MB_CUDA(cudaFuncSetAttribute(fit_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             MB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fit_fused_kernel, FUSED_THREADS, smem));
@@ -629,7 +685,8 @@ int batch_fit_impl(Ctx* c, size_t ref_frame, size_t f0, size_t f1, int superpose
                 void* args[] = {&P};
                 MB_CUDA(cudaLaunchCooperativeKernel((const void*)fit_fused_kernel, dim3(grid), dim3(FUSED_THREADS), args,
                                                     smem, c->stream));
-                c->launches++;
+                finish_rmsd_kernel<<<(unsigned)gn, 32, 0, c->stream>>>(P.part_sup, grid, (int)n, P.rmsd);
+                c->launches += 2;
             }
             if (rmsd_out)
                 MB_CUDA(cudaMemcpyAsync(rmsd_out, d_rmsd, nf * sizeof(double), cudaMemcpyDeviceToHost, c->stream));

@@ -133,10 +133,15 @@ __device__ __forceinline__ bool grid_reduce(double (&v)[K], double* __restrict__
     __syncthreads();
     if (!is_last) return false;
     __threadfence();
-    if (threadIdx.x < K) {
+    // Fold the per-block partials with the whole block: warp w takes components w, w+nwarps, ...;
+    // lane l sums blocks l, l+32, ... in order, then a fixed shuffle tree.  (A first version let K
+    // threads walk all blocks serially: ~300 dependent L2 latencies on the critical path of every frame.)
+    for (int k = (int)wid; k < K; k += THREADS / 32) {
         double x = 0;
-        for (int b = 0; b < nblk; ++b) x += __ldcg(&partials[(size_t)b * K + threadIdx.x]);
-        sh_result[threadIdx.x] = x;
+        for (int b = (int)lane; b < nblk; b += 32) x += __ldcg(&partials[(size_t)b * K + k]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        if (lane == 0) sh_result[k] = x;
     }
     if (threadIdx.x == 0) *ticket = 0;  // re-arm for the next launch
     __syncthreads();
