@@ -245,7 +245,7 @@ int mb_set_option(MbCtx* h, const char* key, double value) {
     else if (!strcmp(key, "atoms_per_cell")) c.opt_atoms_per_cell = value;
     else if (!strcmp(key, "with_dist")) c.opt_with_dist = (int)value;
     else if (!strcmp(key, "exact_pbc")) c.opt_exact_pbc = (int)value;
-    else if (!strcmp(key, "no_fused_fit")) c.opt_no_fused_fit = (int)value;
+    else if (!strcmp(key, "fused_fit")) c.opt_fused_fit = (int)value;
     else if (!strcmp(key, "profile")) {
         c.opt_profile = (int)value;
         c.prof_search_ms = 0.0;

@@ -124,7 +124,7 @@ struct Ctx {
     int opt_force_brute = 0;  // force the general all-pairs kernel
     double opt_atoms_per_cell = 8.0;  // minimum mean population of a home tile
     int opt_with_dist = 1;
-    int opt_no_fused_fit = 0;  // 1: batch_fit uses the two-kernel path even when the fused kernel applies
+    int opt_fused_fit = 0;  // 1: batch_fit uses the persistent TMA-staged kernel (slower than the two-kernel path so far)
     int opt_exact_pbc = 0;    // 1: wrapped cell pairs always use the exact PeriodicBox path (no filter)
     int opt_profile = 0;      // record CUDA events around every search-kernel launch
     std::vector<cudaEvent_t> prof_events;  // begin/end pairs not yet harvested

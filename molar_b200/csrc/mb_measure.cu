@@ -263,7 +263,9 @@ __global__ void __launch_bounds__(RED_THREADS) superpose_rmsd_kernel(float* __re
                                                                      double* __restrict__ partials,
                                                                      unsigned* __restrict__ tickets,
                                                                      double* __restrict__ rmsd_out) {
-    const int frame = blockIdx.y;
+    // frames are visited in REVERSE launch order: the moments pass that ran just before this kernel
+    // left the last frames of the group in L2, so they are re-read from there instead of HBM
+    const int frame = gridDim.y - 1 - blockIdx.y;
     float* xyz = xyz_base + (size_t)frame * stride;
     const double* fr = fitres + (size_t)frame * 16;
     double R[9], t[3];
@@ -650,7 +652,7 @@ int batch_fit_impl(Ctx* c, size_t ref_frame, size_t f0, size_t f1, int superpose
         int occ = 0;
         const int sm = c->sm_count;
         // try 2 CTAs/SM first, then 1
-        for (int want = 2; want >= 1 && !c->opt_no_fused_fit; --want) {
+        for (int want = 2; want >= 1 && c->opt_fused_fit; --want) {
             int grid = sm * want;
             int slice = (int)(((n + grid - 1) / grid + 3) / 4 * 4);
             size_t smem = (size_t)slice * (FUSED_NBUF + 1) * 12 + (size_t)slice * 4;
@@ -699,10 +701,14 @@ int batch_fit_impl(Ctx* c, size_t ref_frame, size_t f0, size_t f1, int superpose
     // alternate groups over two streams so that the serial tail of one group's kernels (last-block
     // reduction + 3x3 SVD on one thread) overlaps the streaming part of the other group's.
     const size_t frame_bytes = n * 12;
-    size_t group = std::max<size_t>(1, std::min<size_t>(nf, (size_t)(40u << 20) / std::max<size_t>(frame_bytes, 1)));
+    // Large groups: each launch must carry enough bytes per thread to reach HBM speed (a 6-frame group
+    // sized for L2 residency ran at 1.3 TB/s: launch ramp + reduction tail dominated).  The
+    // superposition pass re-reads the group in reverse order, so its first ~90 MB still hit L2.
+    size_t group = std::max<size_t>(1, std::min<size_t>(nf, (size_t)(768u << 20) / std::max<size_t>(frame_bytes, 1)));
     group = std::min<size_t>(group, 2048);
+    (void)frame_bytes;
     int nb = (int)std::max<size_t>(1, std::min<size_t>((n + RED_THREADS * 8 - 1) / (RED_THREADS * 8),
-                                                      std::max<size_t>(1, (size_t)c->sm_count * 6 / group)));
+                                                      std::max<size_t>(4, (size_t)c->sm_count * 8 / group)));
     constexpr int NS = 2;
     for (int i = 0; i < NS; ++i)
         if (!c->aux_stream[i]) MB_CUDA(cudaStreamCreateWithFlags(&c->aux_stream[i], cudaStreamNonBlocking));

@@ -154,7 +154,7 @@ def test_batch_fit_fused_vs_two_kernel_path(mb, n, nf):
     for no_fused in (0, 1):
         t = mb.Trajectory()
         t.synth(SEED, 0, nf, n, TRIC, mass_seed=SEED)
-        t.set_option("no_fused_fit", no_fused)
+        t.set_option("fused_fit", 1 - no_fused)
         before = t.frame(nf - 1)
         r = t.fit(ref_frame=0, superpose=True)
         rc, R, tt = orc.fit_transform(before, m, None, ref, m, None)
@@ -166,7 +166,7 @@ def test_batch_fit_fused_vs_two_kernel_path(mb, n, nf):
         # fit only (no superposition) leaves the frames untouched
         t2 = mb.Trajectory()
         t2.synth(SEED, 0, 2, n, TRIC, mass_seed=SEED)
-        t2.set_option("no_fused_fit", no_fused)
+        t2.set_option("fused_fit", 1 - no_fused)
         r2 = t2.fit(ref_frame=0, superpose=False)
         assert np.array_equal(t2.frame(1), orc.synth_frame(SEED, 1, n, TRIC)) and abs(r2[1] - r[1]) <= 1e-9 * r[1]
         t.close()
