@@ -38,7 +38,7 @@ WORKLOADS = {
                      desc="1M-atom triclinic box, 1.2 nm neighbour-pair enumeration (configs[2])"),
     "search100k": dict(n_atoms=100_000, box=ORTHO, frames=128, kind="search",
                        desc="100k-atom orthorhombic box, 1.2 nm neighbour search (configs[1])"),
-    "fit500k": dict(n_atoms=500_000, box=TRIC, frames=64, kind="fit",
+    "fit500k": dict(n_atoms=500_000, box=TRIC, frames=256, kind="fit",
                     desc="500k-atom Kabsch fit + superposition + RMSD to frame 0 (configs[3])"),
     "pipeline1m": dict(n_atoms=1_000_000, box=TRIC, frames=16, kind="pipeline",
                        desc="1M-atom COM + gyration + 1.2 nm contact count (configs[4])"),
