@@ -45,6 +45,15 @@ WORKLOADS = {
 }
 
 
+def measured_traffic(workload):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return float(json.load(f)[workload]["dram_bytes_per_launch"])
+    except Exception:
+        return None
+
+
 def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -314,7 +323,7 @@ def run_ours(args, wl):
                        if F * n * 12 > 126e6 else "pair output per frame exceeds L2; inputs re-streamed",
                        "parallelism": f"frames sharded over {world} GPU(s)"},
             "roofline": {"bound": "hbm", "kernel": kern, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": which,
+                         "frac": achieved / peak, "traffic": measured_traffic(args.workload), "peak_source": which,
                          "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": k_avg_ms,
                          "kernel_share_of_step": (k_ms / ms) if kind != "fit" else 1.0},
             "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": 12 * n, "d2h_bytes_per_step": d2h,
