@@ -215,6 +215,12 @@ void mb_close(MbCtx* h) {
                       &c.cell_start, &c.scan_tmp, &c.pairs, &c.dists, &c.flags, &c.out_ids, &c.counters,
                       &c.reduce_tmp, &c.batch, &c.batch_scalars, &c.batch_tmp, &c.batch_ref};
     for (DevBuf* b : bufs) b->release();
+    for (SearchSlot& sl : c.alt) {
+        DevBuf* sb[] = {&sl.tmp4a, &sl.cellid_a, &sl.rank_a, &sl.cell_count, &sl.cell_start, &sl.sorted4, &sl.scan_tmp,
+                        &sl.pairs, &sl.dists};
+        for (DevBuf* b : sb) b->release();
+        if (sl.stream) cudaStreamDestroy(sl.stream);
+    }
     free_plan_cache(&c);
     if (c.h_pinned) cudaFreeHost(c.h_pinned);
     for (int i = 0; i < 2; ++i)
@@ -246,6 +252,7 @@ int mb_set_option(MbCtx* h, const char* key, double value) {
     else if (!strcmp(key, "with_dist")) c.opt_with_dist = (int)value;
     else if (!strcmp(key, "exact_pbc")) c.opt_exact_pbc = (int)value;
     else if (!strcmp(key, "fused_fit")) c.opt_fused_fit = (int)value;
+    else if (!strcmp(key, "batch_streams")) c.opt_batch_streams = (int)value;
     else if (!strcmp(key, "profile")) {
         c.opt_profile = (int)value;
         c.prof_search_ms = 0.0;

@@ -77,6 +77,15 @@ struct SearchResult {
     uint64_t grid_dims[3] = {0, 0, 0};
 };
 
+// One set of per-frame search scratch + output + the stream it is used on.  The context's own
+// members (tmp4a, ..., pairs, stream) are "slot 0"; batch_search installs the alternates by swapping
+// them in, so consecutive frames are pre-processed and searched on different streams.
+struct SearchSlot {
+    DevBuf tmp4a, cellid_a, rank_a, cell_count, cell_start, sorted4, scan_tmp, pairs, dists;
+    size_t pair_cap = 0;
+    cudaStream_t stream = nullptr;
+};
+
 struct Ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -116,6 +125,8 @@ struct Ctx {
     DevBuf reduce_tmp;      // per-block partials
     SearchResult last;
     size_t pair_cap = 0;
+    SearchSlot alt[2];        // alternate slots for batch_search (streams created lazily)
+    int installed_slot = 0;   // which slot currently lives in the members above
 
     // options
     int opt_subdiv = 0;       // 0 auto, else forced k for all dims
@@ -124,6 +135,7 @@ struct Ctx {
     int opt_force_brute = 0;  // force the general all-pairs kernel
     double opt_atoms_per_cell = 8.0;  // minimum mean population of a home tile
     int opt_with_dist = 1;
+    int opt_batch_streams = 0;  // streams (slots) batch_search alternates frames over; 0 = automatic
     int opt_fused_fit = 0;  // 1: batch_fit uses the persistent TMA-staged kernel (slower than the two-kernel path so far)
     int opt_exact_pbc = 0;    // 1: wrapped cell pairs always use the exact PeriodicBox path (no filter)
     int opt_profile = 0;      // record CUDA events around every search-kernel launch

@@ -1683,6 +1683,27 @@ static int search_two_sets(Ctx* c, float cutoff, const uint64_t* ids1, size_t n1
 }
 
 // ---- batch entry (device-resident frames, PBC variant; no host sync per frame) ---------------
+static void swap_slot(Ctx* c, SearchSlot& sl) {
+    std::swap(c->tmp4a, sl.tmp4a);
+    std::swap(c->cellid_a, sl.cellid_a);
+    std::swap(c->rank_a, sl.rank_a);
+    std::swap(c->cell_count, sl.cell_count);
+    std::swap(c->cell_start, sl.cell_start);
+    std::swap(c->sorted4, sl.sorted4);
+    std::swap(c->scan_tmp, sl.scan_tmp);
+    std::swap(c->pairs, sl.pairs);
+    std::swap(c->dists, sl.dists);
+    std::swap(c->pair_cap, sl.pair_cap);
+    std::swap(c->stream, sl.stream);
+}
+// make slot `s` (0 = the context's own) the one the members refer to
+static void install_slot(Ctx* c, int s) {
+    if (c->installed_slot == s) return;
+    if (c->installed_slot != 0) swap_slot(c, c->alt[c->installed_slot - 1]);
+    if (s != 0) swap_slot(c, c->alt[s - 1]);
+    c->installed_slot = s;
+}
+
 int batch_search_impl(Ctx* c, float cutoff, uint8_t pbc, size_t f0, size_t f1, int mode, int64_t* counts,
                       uint64_t* checksums2) {
     if (!c->batch.p || f1 > c->batch_frames || f0 >= f1) return fail(MB_ERR_ARG, "batch_search: bad frame range");
@@ -1694,45 +1715,74 @@ int batch_search_impl(Ctx* c, float cutoff, uint8_t pbc, size_t f0, size_t f1, i
     if (!pl.use_cells) return fail(MB_ERR_ARG, "batch_search: grid is degenerate for the cell kernel (dims %d %d %d)",
                                    pl.g.dims[0], pl.g.dims[1], pl.g.dims[2]);
     const int kmode = mode == 1 ? 2 : 0;
-    if (kmode != 2) MB_TRY(ensure_pair_capacity(c, std::max(estimate_pairs(pl, n, n, cutoff, true), c->pair_cap), false));
+    // Frames alternate over NS slots (scratch + pair buffer + stream each): the bin/scan/scatter of
+    // frame f+1 overlaps the search of frame f, and for small frames the tail of one search kernel
+    // (fewer home tiles than resident warps) is back-filled by the next frame's.
+    const int NS = c->opt_batch_streams > 0 ? std::min(c->opt_batch_streams, 3) : (n <= 300000 ? 3 : 2);
+    install_slot(c, 0);
+    cudaStream_t main_stream = c->stream;
+    for (int s = 1; s < NS; ++s)
+        if (!c->alt[s - 1].stream) MB_CUDA(cudaStreamCreateWithFlags(&c->alt[s - 1].stream, cudaStreamNonBlocking));
+    if (!c->aux_event) MB_CUDA(cudaEventCreateWithFlags(&c->aux_event, cudaEventDisableTiming));
+    const size_t want = kmode != 2 ? estimate_pairs(pl, n, n, cutoff, true) : 0;
+    if (kmode != 2)
+        for (int s = 0; s < NS; ++s) {
+            install_slot(c, s);
+            MB_TRY(ensure_pair_capacity(c, std::max(want, c->pair_cap), false));
+        }
+    install_slot(c, 0);
     // per-frame counters: [2*f] pairs, [2*f+1] work ; checksums after them
     MB_TRY(c->batch_tmp.reserve(nf * 4 * sizeof(unsigned long long)));
     unsigned long long* d_cnt = c->batch_tmp.as<unsigned long long>();
     unsigned long long* d_chk = d_cnt + 2 * nf;
-    if (checksums2) MB_CUDA(cudaMemsetAsync(d_chk, 0, nf * 2 * sizeof(unsigned long long), c->stream));
+    if (checksums2) MB_CUDA(cudaMemsetAsync(d_chk, 0, nf * 2 * sizeof(unsigned long long), main_stream));
     std::vector<unsigned long long> h_cnt(2 * nf);
     const bool dbg = getenv("MB_DEBUG_TIMING") != nullptr;
     for (int attempt = 0; attempt < 2; ++attempt) {
         auto t_a = std::chrono::steady_clock::now();
+        // alternates start after everything already queued on the context stream
+        MB_CUDA(cudaEventRecord(c->aux_event, main_stream));
+        for (int s = 1; s < NS; ++s) MB_CUDA(cudaStreamWaitEvent(c->alt[s - 1].stream, c->aux_event, 0));
         for (size_t f = 0; f < nf; ++f) {
+            install_slot(c, (int)(f % NS));
             const float* xyz = c->batch.as<float>() + (f0 + f) * n * 3;
-            MB_TRY(enqueue_cells_search(c, xyz, nullptr, n, pl, cutoff, kmode, d_cnt + 2 * f));
-            if (checksums2 && kmode != 2) {
-                // pair count is only known on the device: the kernel reads it from the counter
-                // (launched with a grid that covers the capacity; threads past the count exit)
-                // -> simpler: checksum over min(count, cap) via a tiny indirection kernel below
+            int rc = enqueue_cells_search(c, xyz, nullptr, n, pl, cutoff, kmode, d_cnt + 2 * f);
+            if (rc < 0) {
+                install_slot(c, 0);
+                return rc;
             }
         }
+        install_slot(c, 0);
+        for (int s = 1; s < NS; ++s) {
+            MB_CUDA(cudaEventRecord(c->aux_event, c->alt[s - 1].stream));
+            MB_CUDA(cudaStreamWaitEvent(main_stream, c->aux_event, 0));
+        }
         auto t_b = std::chrono::steady_clock::now();
-        MB_CUDA(cudaMemcpyAsync(h_cnt.data(), d_cnt, 2 * nf * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
-        MB_CUDA(cudaStreamSynchronize(c->stream));
+        MB_CUDA(cudaMemcpyAsync(h_cnt.data(), d_cnt, 2 * nf * sizeof(unsigned long long), cudaMemcpyDeviceToHost, main_stream));
+        MB_CUDA(cudaStreamSynchronize(main_stream));
         auto t_c = std::chrono::steady_clock::now();
         c->harvest_profile();
         if (dbg)
-            fprintf(stderr, "[mb] batch_search attempt %d: enqueue %.3f ms, wait %.3f ms, frames %zu, cap %zu, ncells %zu k=(%d,%d,%d) hx=%d rows=%d\n",
+            fprintf(stderr, "[mb] batch_search attempt %d: enqueue %.3f ms, wait %.3f ms, frames %zu, cap %zu, ncells %zu k=(%d,%d,%d) hx=%d rows=%d streams=%d\n",
                     attempt, std::chrono::duration<double, std::milli>(t_b - t_a).count(),
                     std::chrono::duration<double, std::milli>(t_c - t_b).count(), nf, c->pair_cap, pl.ncells,
-                    pl.g.k[0], pl.g.k[1], pl.g.k[2], pl.g.hx, pl.nrows);
+                    pl.g.k[0], pl.g.k[1], pl.g.k[2], pl.g.hx, pl.nrows, NS);
         unsigned long long mx = 0;
         for (size_t f = 0; f < nf; ++f) mx = std::max(mx, h_cnt[2 * f]);
-        if (kmode == 2 || mx <= c->pair_cap) break;
-        MB_TRY(ensure_pair_capacity(c, (size_t)mx + mx / 16 + 1024, false));
+        size_t min_cap = c->pair_cap;
+        for (int s = 1; s < NS; ++s) min_cap = std::min(min_cap, c->alt[s - 1].pair_cap);
+        if (kmode == 2 || mx <= min_cap) break;
+        for (int s = 0; s < NS; ++s) {
+            install_slot(c, s);
+            MB_TRY(ensure_pair_capacity(c, (size_t)mx + mx / 16 + 1024, false));
+        }
+        install_slot(c, 0);
     }
     if (counts)
         for (size_t f = 0; f < nf; ++f) counts[f] = (int64_t)h_cnt[2 * f];
     if (checksums2 && kmode != 2) {
-        // verification path (not the timed one): redo frame by frame with a sync so the checksum
-        // kernel knows the pair count
+        // verification path (not the timed one): redo frame by frame on the context stream so the
+        // checksum kernel knows the pair count
         for (size_t f = 0; f < nf; ++f) {
             const float* xyz = c->batch.as<float>() + (f0 + f) * n * 3;
             MB_TRY(enqueue_cells_search(c, xyz, nullptr, n, pl, cutoff, kmode, d_cnt + 2 * f));
@@ -1743,6 +1793,14 @@ int batch_search_impl(Ctx* c, float cutoff, uint8_t pbc, size_t f0, size_t f1, i
         }
         MB_CUDA(cudaMemcpyAsync(checksums2, d_chk, nf * 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
         MB_CUDA(cudaStreamSynchronize(c->stream));
+    } else if (kmode != 2) {
+        // the pair list of the LAST frame must be the one mb_fill_pairs / mb_pairs_device see
+        const int sl = (int)((nf - 1) % NS);
+        if (sl != 0) {
+            std::swap(c->pairs, c->alt[sl - 1].pairs);
+            std::swap(c->dists, c->alt[sl - 1].dists);
+            std::swap(c->pair_cap, c->alt[sl - 1].pair_cap);
+        }
     }
     c->last.kind = kmode == 2 ? 4 : 1;
     c->last.count = (int64_t)h_cnt[2 * (nf - 1)];

@@ -193,6 +193,30 @@ def test_config2_100k_orthorhombic_exact(mb):
     assert_same_pairs(gp, gd, op, od)
 
 
+def test_batch_search_streams_and_last_pairs(mb):
+    """Frames alternate over several stream slots; counts, checksums and the pair list of the last
+    frame must not depend on the number of slots, and must equal the oracle's."""
+    M = (TRIC * np.float32(0.4)).astype(np.float32)
+    n, nf = 60000, 5
+    res = {}
+    for ns in (1, 2, 3):
+        t = mb.Trajectory()
+        t.synth(SEED, 0, nf, n, M, stray_permille=5)
+        t.set_option("batch_streams", ns)
+        counts = t.search(1.2)
+        pairs = orc.canonical_pairs(t.last_pairs())
+        counts2, chk = t.search(1.2, checksums=True)
+        assert np.array_equal(counts, counts2)
+        res[ns] = (counts, chk, pairs)
+        t.close()
+    for ns in (2, 3):
+        assert np.array_equal(res[ns][0], res[1][0]) and np.array_equal(res[ns][1], res[1][1])
+        assert np.array_equal(res[ns][2], res[1][2])
+    xyz = orc.synth_frame(SEED, nf - 1, n, M, stray_permille=5)
+    op, od, dims = oracle_single(1.2, xyz, box=M, pbc=7, nthreads=8)
+    assert np.array_equal(res[2][2], op) and res[2][0][-1] == len(op)
+
+
 def test_config3_1m_triclinic_properties(mb):
     """1M atoms: too slow for the oracle inside the test budget, so size-independent properties:
     count-only == enumerated count; the order-independent checksum and count do not depend on the
