@@ -157,28 +157,27 @@ int mb_batch_pipeline(MbCtx* h, float cutoff, uint8_t pbc_dims, size_t f0, size_
     if (!c.masses.p || c.n_masses < c.batch_atoms) return fail(MB_ERR_STATE, "masses not set for the batch");
     MB_CUDA(cudaSetDevice(c.device));
     const size_t n = c.batch_atoms, nf = f1 - f0;
-    // scratch: [tickets 64 KB][rows8 nf*8][partials nf*nb*5] in batch_tmp ; counters 2*nf u64 after
+    // moments scratch lives in pipe_tmp: [tickets 64 KB][rows8 nf*8][partials nf*nb*5];
+    // the contact counts come from batch_search (count-only mode), whose per-frame device counters
+    // stay in batch_tmp at stride 2
     int nb = (int)std::max<size_t>(1, std::min<size_t>((n + 256 * 8 - 1) / (256 * 8), 64));
     size_t tick_bytes = 64 * 1024;
     if (nf * sizeof(unsigned) > tick_bytes) return fail(MB_ERR_ARG, "batch_pipeline: at most 16384 frames per call");
     size_t rows8_bytes = nf * 8 * sizeof(double);
     size_t part_bytes = nf * (size_t)nb * 5 * sizeof(double);
-    size_t cnt_bytes = nf * 2 * sizeof(unsigned long long);
-    size_t need = tick_bytes + rows8_bytes + part_bytes + cnt_bytes;
-    MB_TRY(c.batch_tmp.reserve(need));
-    // batch_tmp is shared with batch_search's counters: tickets must be clean on entry
-    MB_CUDA(cudaMemsetAsync(c.batch_tmp.p, 0, tick_bytes, c.stream));
-    char* base = static_cast<char*>(c.batch_tmp.p);
+    size_t need = tick_bytes + rows8_bytes + part_bytes;
+    bool fresh = need > c.pipe_tmp.cap;
+    MB_TRY(c.pipe_tmp.reserve(need));
+    if (fresh) MB_CUDA(cudaMemsetAsync(c.pipe_tmp.p, 0, tick_bytes, c.stream));  // tickets re-arm themselves
+    char* base = static_cast<char*>(c.pipe_tmp.p);
     unsigned* tickets = reinterpret_cast<unsigned*>(base);
     double* rows8 = reinterpret_cast<double*>(base + tick_bytes);
     double* partials = reinterpret_cast<double*>(base + tick_bytes + rows8_bytes);
-    unsigned long long* counters = reinterpret_cast<unsigned long long*>(base + tick_bytes + rows8_bytes + part_bytes);
     MB_TRY(c.batch_scalars.reserve(nf * 5 * sizeof(double)));
     MB_TRY(enqueue_batch_moments(&c, f0, f1, rows8, partials, tickets, nb));
-    for (size_t f = 0; f < nf; ++f) {
-        const float* xyz = c.batch.as<float>() + (f0 + f) * n * 3;
-        MB_TRY(enqueue_count_frame(&c, xyz, n, cutoff, pbc_dims & 7, counters + 2 * f));
-    }
+    // count-only neighbour search of every frame, frames alternating over the stream slots
+    MB_TRY(batch_search_impl(&c, cutoff, pbc_dims & 7, f0, f1, 1, nullptr, nullptr));
+    const unsigned long long* counters = c.batch_tmp.as<unsigned long long>();
     assemble_rows_kernel<<<(unsigned)((nf + 127) / 128), 128, 0, c.stream>>>(rows8, counters, (int)nf,
                                                                             c.batch_scalars.as<double>());
     c.launches++;

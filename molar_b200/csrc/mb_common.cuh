@@ -150,7 +150,7 @@ struct Ctx {
     bool batch_has_box = false;
     DevBuf batch_scalars;  // rows of doubles
     size_t batch_rows = 0, batch_row_doubles = 0;
-    DevBuf batch_tmp, batch_ref;
+    DevBuf batch_tmp, batch_ref, pipe_tmp;
 
     // memoised search plan (owned by mb_search.cu)
     void* plan_cache = nullptr;
