@@ -266,11 +266,16 @@ def run_ours(args, wl):
     from oracle import oracle_py as orc  # only to synthesise host-side input frames
     e2e_frames = min(F, 4)
     host = [torch.from_numpy(orc.synth_frame(SEED, rank * F + f, n, box)).pin_memory() for f in range(e2e_frames)]
-    sysm = mb.System(host[0].numpy(), masses=orc.synth_masses(SEED, n), box=box)
-    refsys = mb.System(host[0].numpy(), masses=orc.synth_masses(SEED, n), box=box) if kind == "fit" else None
+    sysm = mb.System(host[0].numpy(), masses=orc.synth_masses(SEED, n), box=box, device=local)
+    refsys = (mb.System(host[0].numpy(), masses=orc.synth_masses(SEED, n), box=box, device=local)
+              if kind == "fit" else None)
+
+    e2e_t = {"set": 0.0, "call": 0.0}
 
     def e2e_once(x):
+        ta = time.perf_counter()
         sysm.set_state(x.numpy(), box)  # H2D of the frame (12 B/atom) from pinned memory
+        e2e_t["set"] += time.perf_counter() - ta
         if kind == "search":
             lib, h = sysm._lib, sysm._h
             return mb._capi.check(lib.mb_search_single(h, CUTOFF, None, n, 7))  # D2H: the pair count
@@ -293,6 +298,9 @@ def run_ours(args, wl):
             e2e_once(x)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    if os.environ.get("MB_DEBUG_TIMING"):
+        sys.stderr.write(f"[bench] rank {rank}: e2e {e2e_s * 1e3:.1f} ms for {reps * e2e_frames} calls, "
+                         f"set_state {e2e_t['set'] * 1e3:.1f} ms\n")
     if world > 1:
         t = torch.tensor([e2e_s], device=f"cuda:{local}", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
