@@ -12,6 +12,7 @@
  *   mb_search_single      distance_search_single[_pbc]                    distance_search.rs:892-954
  *   mb_search_double      distance_search_double[_pbc]                    distance_search.rs:659-754
  *   mb_search_within      distance_search_within[_pbc]                    distance_search.rs:519-598
+ *   mb_search_double_vdw  distance_search_double_vdw[_pbc]                distance_search.rs:767-879
  *   mb_center_of_mass     Measure::center_of_mass                         measure.rs:60-75
  *   mb_gyration           Measure::gyration                               measure.rs:78-87,561-570
  *   mb_rmsd               rmsd / rmsd_mw                                  measure.rs:485-504,538-558
@@ -92,6 +93,11 @@ int64_t mb_search_single(MbCtx* ctx, float cutoff, const uint64_t* ids, size_t n
 /* set 2 positions are taken from frame2 when use_frame2 != 0, else from the current frame */
 int64_t mb_search_double(MbCtx* ctx, float cutoff, const uint64_t* ids1, size_t n1,
                          const uint64_t* ids2, size_t n2, int use_frame2, uint8_t pbc_dims);
+/* van der Waals contact search: pair (i,j) is reported when d <= vdw1[i] + vdw2[j] + EPSILON.  vdw1/vdw2
+   hold one radius per SELECTED atom (host arrays of n1 / n2 floats); as in the reference the reported
+   indices are LOCAL (positions within the two selections), fetched with mb_fill_pairs. */
+int64_t mb_search_double_vdw(MbCtx* ctx, const uint64_t* ids1, size_t n1, const float* vdw1,
+                             const uint64_t* ids2, size_t n2, const float* vdw2, int use_frame2, uint8_t pbc_dims);
 /* lower3/upper3: grid bounds of the non-periodic variant, as the caller of
    distance_search_within passes them (selection/ast.rs:598-610); ignored when pbc_dims != 0;
    NULL => bounds of set 1 padded by cutoff + EPSILON (what the `within` AST node does). */

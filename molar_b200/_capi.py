@@ -30,6 +30,7 @@ SIGNATURES = {
     "mb_set_frame2": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "mb_search_single": (C.c_int64, [C.c_void_p, C.c_float, u64p, C.c_size_t, C.c_uint8]),
     "mb_search_double": (C.c_int64, [C.c_void_p, C.c_float, u64p, C.c_size_t, u64p, C.c_size_t, C.c_int, C.c_uint8]),
+    "mb_search_double_vdw": (C.c_int64, [C.c_void_p, u64p, C.c_size_t, f32p, u64p, C.c_size_t, f32p, C.c_int, C.c_uint8]),
     "mb_search_within": (C.c_int64, [C.c_void_p, C.c_float, u64p, C.c_size_t, u64p, C.c_size_t, C.c_int, C.c_uint8,
                                      f32p, f32p]),
     "mb_count_single": (C.c_int64, [C.c_void_p, C.c_float, u64p, C.c_size_t, C.c_uint8]),

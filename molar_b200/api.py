@@ -51,7 +51,7 @@ class IsometryTransform:
 
 
 class System:
-    def __init__(self, coords, masses=None, box=None, device=0):
+    def __init__(self, coords, masses=None, box=None, device=0, vdw=None):
         self._lib = _capi.load()
         self._h = self._lib.mb_open(device)
         if not self._h:
@@ -63,6 +63,7 @@ class System:
         self.set_state(coords, box)
         if masses is not None:
             self.set_masses(masses)
+        self.vdw = None if vdw is None else np.ascontiguousarray(vdw, dtype=np.float32)  # per-atom vdW radii
 
     # -- lifetime --
     def close(self):
@@ -176,10 +177,31 @@ def distance_search(cutoff, data1, data2=None, dims=None):
 
     The pair SET equals the reference's; order is unspecified (the reference's order is rayon's).
     Single-selection pairs are canonical i<j and de-duplicated."""
-    if isinstance(cutoff, str):
-        raise NotImplementedError("'vdw' cutoff is outside the accelerated path (SURVEY.md §8f)")
     s = data1.sys
     pbc = _pbc_bits(dims)
+    if isinstance(cutoff, str):
+        # pymolar: cutoff == "vdw" -> distance_search_double_vdw[_pbc] on the atoms' vdW radii, local
+        # indices converted to global afterwards (molar_python/src/lib.rs:311-349)
+        if cutoff != "vdw":
+            raise TypeError(f"Unknown cutoff type {cutoff}")
+        if data2 is None:
+            raise NotImplementedError("VdW distance search is not yet supported for single selection")
+        if pbc and s.box is None:
+            raise MolarB200Error(_capi.MB_ERR_NO_PBC, "pbc operation without periodic box")
+        v1 = np.ascontiguousarray(data1.sys.vdw[data1.get_index().astype(np.int64)], dtype=np.float32)
+        v2 = np.ascontiguousarray(data2.sys.vdw[data2.get_index().astype(np.int64)], dtype=np.float32)
+        use2 = _same_or_frame2(data1, data2)
+        p1, n1 = data1._ids()
+        p2, n2 = data2._ids()
+        cnt = check(s._lib.mb_search_double_vdw(s._h, p1, n1, v1.ctypes.data_as(f32p), p2, n2,
+                                                v2.ctypes.data_as(f32p), use2, pbc))
+        pairs = np.empty((cnt, 2), np.uint64)
+        dist = np.empty(cnt, np.float32)
+        if cnt:
+            check(s._lib.mb_fill_pairs(s._h, pairs.ctypes.data, dist.ctypes.data))
+            pairs[:, 0] = data1.get_index()[pairs[:, 0].astype(np.int64)]
+            pairs[:, 1] = data2.get_index()[pairs[:, 1].astype(np.int64)]
+        return pairs, dist
     if pbc and s.box is None:
         raise MolarB200Error(_capi.MB_ERR_NO_PBC, "pbc operation without periodic box")
     p1, n1 = data1._ids()

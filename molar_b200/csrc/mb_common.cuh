@@ -117,6 +117,7 @@ struct Ctx {
     // search scratch
     DevBuf tmp4a, tmp4b;    // binned atoms (float4: eff pos + id bits), unsorted
     DevBuf cellid_a, cellid_b, rank_a;
+    DevBuf vdw_a, vdw_b;          // vdW radii of the two selections (vdW search)
     DevBuf refcell_a, refcell_b;  // packed reference cell coords (u64) for the general kernel
     DevBuf sorted4;         // atoms sorted by fine cell
     DevBuf cell_count, cell_start, scan_tmp;

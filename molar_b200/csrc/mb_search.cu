@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(256) bin_atoms_kernel(const float* __restrict_
                                                         GridSpec g, float4* __restrict__ out4,
                                                         unsigned* __restrict__ cellid, unsigned* __restrict__ rank,
                                                         unsigned* __restrict__ cell_count,
-                                                        unsigned long long* __restrict__ refcell) {
+                                                        unsigned long long* __restrict__ refcell, int local_ids) {
     int kidx = blockIdx.x * blockDim.x + threadIdx.x;
     bool valid = kidx < n;
     unsigned cell = DROPPED;
@@ -170,7 +170,8 @@ __global__ void __launch_bounds__(256) bin_atoms_kernel(const float* __restrict_
         if (valid) rank[kidx] = base + __popc(peers & ((1u << lane) - 1u));
     }
     if (valid) {
-        out4[kidx] = make_float4(ex, ey, ez, __uint_as_float(gid));
+        // vdW searches report LOCAL indices (distance_search.rs:791-792): tag with the position in the selection
+        out4[kidx] = make_float4(ex, ey, ez, __uint_as_float(local_ids ? (unsigned)kidx : gid));
         cellid[kidx] = cell;
         if (refcell)
             refcell[kidx] = cell == DROPPED ? ~0ull
@@ -784,13 +785,15 @@ struct BruteParams {
     unsigned long long* counter;
     unsigned char* flags;
     int count_only;
+    const float* avdw;  // vdW mode: radii per selected atom of set A / B (indexed by the local id in .w), else NULL
+    const float* bvdw;
 };
 
 // Set of wrapped-dims flags under which search_plan lists the (unordered) reference cell pair
 // {ca, cb}; the pair is a hit if ANY of them passes (the reference then simply emits it more than
 // once).  Handles dims[d] in {1,2}, where the same cell pair is reached both directly and wrapped.
 __device__ __forceinline__ bool general_pair_test(const BruteParams& P, float4 a, unsigned long long ra, float4 b,
-                                                  unsigned long long rb, float& d2min) {
+                                                  unsigned long long rb, float rc2, float& d2min) {
     unsigned opt0 = 0, opt1 = 0;
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
@@ -810,7 +813,7 @@ __device__ __forceinline__ bool general_pair_test(const BruteParams& P, float4 a
         // w is allowed if every set bit is in opt1 and every clear bit is in opt0
         if ((w & ~opt1) || ((~w & 7u) & ~opt0)) continue;
         float d2 = w ? d2_pbc(P.box, a.x, a.y, a.z, b.x, b.y, b.z, w) : d2_direct(a.x, a.y, a.z, b.x, b.y, b.z);
-        if (d2 <= P.rc2) {
+        if (d2 <= rc2) {
             hit = true;
             d2min = fminf(d2min, d2);
         }
@@ -838,6 +841,7 @@ __global__ void __launch_bounds__(BRUTE_THREADS) brute_kernel(const __grid_const
     unsigned long long ra = ivalid ? P.aref[i] : ~0ull;
     const bool alive = ivalid && ra != ~0ull;
     bool found = false;
+    const float va = (P.avdw && ivalid) ? P.avdw[__float_as_uint(a.w)] : 0.f;
 
     // blockIdx.y strides over tiles of set B
     for (int t0 = blockIdx.y * BRUTE_TILE; t0 < P.nb; t0 += gridDim.y * BRUTE_TILE) {
@@ -856,7 +860,15 @@ __global__ void __launch_bounds__(BRUTE_THREADS) brute_kernel(const __grid_const
             unsigned long long rb = tbr[jj];
             bool hit = false;
             float d2 = 0.f;
-            if (alive && rb != ~0ull && !(P.mode == 0 && t0 + jj <= i)) hit = general_pair_test(P, a, ra, tb4[jj], rb, d2);
+            if (alive && rb != ~0ull && !(P.mode == 0 && t0 + jj <= i)) {
+                float rc2 = P.rc2;
+                if (P.avdw) {
+                    // cutoff = vdw1[i] + vdw2[j] + EPSILON ; d2 <= cutoff*cutoff  (distance_search.rs:392-393,423-425)
+                    const float cut = xadd(xadd(va, P.bvdw[__float_as_uint(tb4[jj].w)]), FLT_EPSILON);
+                    rc2 = xmul(cut, cut);
+                }
+                hit = general_pair_test(P, a, ra, tb4[jj], rb, rc2, d2);
+            }
             if (P.mode == 2) {
                 found |= hit;
                 continue;
@@ -1404,7 +1416,8 @@ static int ensure_pair_capacity(Ctx* c, size_t want, bool with_dist) {
 }
 
 static int bin_set(Ctx* c, const float* xyz, const unsigned long long* d_ids, size_t n, const GridSpec& g,
-                   DevBuf& tmp4, DevBuf& cellid, DevBuf* rank, unsigned* cell_count, DevBuf* refcell) {
+                   DevBuf& tmp4, DevBuf& cellid, DevBuf* rank, unsigned* cell_count, DevBuf* refcell,
+                   int local_ids = 0) {
     MB_TRY(tmp4.reserve(n * sizeof(float4)));
     MB_TRY(cellid.reserve(n * sizeof(unsigned)));
     if (rank) MB_TRY(rank->reserve(n * sizeof(unsigned)));
@@ -1412,7 +1425,7 @@ static int bin_set(Ctx* c, const float* xyz, const unsigned long long* d_ids, si
     int blocks = (int)((n + 255) / 256);
     bin_atoms_kernel<<<blocks, 256, 0, c->stream>>>(xyz, d_ids, (int)n, g, tmp4.as<float4>(), cellid.as<unsigned>(),
                                                    rank ? rank->as<unsigned>() : nullptr, cell_count,
-                                                   refcell ? refcell->as<unsigned long long>() : nullptr);
+                                                   refcell ? refcell->as<unsigned long long>() : nullptr, local_ids);
     c->launches++;
     MB_CUDA(cudaGetLastError());
     return MB_OK;
@@ -1482,8 +1495,11 @@ int enqueue_cells_search(Ctx* c, const float* xyz, const unsigned long long* d_i
 
 static int enqueue_brute(Ctx* c, const Plan& pl, float cutoff, int mode, int with_dist, int count_only, size_t na,
                          size_t nb, const float4* a4, const unsigned long long* aref, const float4* b4,
-                         const unsigned long long* bref, unsigned long long* d_counter) {
+                         const unsigned long long* bref, unsigned long long* d_counter,
+                         const float* avdw = nullptr, const float* bvdw = nullptr) {
     BruteParams P;
+    P.avdw = avdw;
+    P.bvdw = bvdw;
     P.a4 = a4;
     P.aref = aref;
     P.na = (int)na;
@@ -1589,8 +1605,17 @@ int search_single_impl(Ctx* c, float cutoff, const uint64_t* ids, size_t n, uint
 // double / within: general kernel over two binned sets
 static int search_two_sets(Ctx* c, float cutoff, const uint64_t* ids1, size_t n1, const uint64_t* ids2, size_t n2,
                            int use_frame2, uint8_t pbc, int within, const float* lower3, const float* upper3,
-                           int64_t* count_out) {
+                           int64_t* count_out, const float* vdw1 = nullptr, const float* vdw2 = nullptr) {
     if (!c->d_xyz) return fail(MB_ERR_STATE, "no frame set");
+    const bool vdw = vdw1 && vdw2;
+    if (vdw) {
+        // grid cutoff = max(vdw1) + max(vdw2) + EPSILON   (distance_search.rs:781-783,845-847)
+        if (n1 == 0 || n2 == 0) return fail(MB_ERR_ARG, "vdw search: empty selection");
+        float m1 = vdw1[0], m2 = vdw2[0];
+        for (size_t k = 1; k < n1; ++k) m1 = std::fmax(m1, vdw1[k]);
+        for (size_t k = 1; k < n2; ++k) m2 = std::fmax(m2, vdw2[k]);
+        cutoff = (m1 + m2) + FLT_EPSILON;
+    }
     if (!(cutoff > 0.0f)) return fail(MB_ERR_ARG, "cutoff must be positive");
     MB_CUDA(cudaSetDevice(c->device));
     const float* xyz2 = use_frame2 ? c->xyz2.as<float>() : c->d_xyz;
@@ -1636,8 +1661,17 @@ static int search_two_sets(Ctx* c, float cutoff, const uint64_t* ids1, size_t n1
         pl.g.fd[d] = pl.g.dims[d];
     }
     const bool with_dist = !within && c->opt_with_dist;
-    MB_TRY(bin_set(c, c->d_xyz, d_ids1, n1, pl.g, c->tmp4a, c->cellid_a, nullptr, nullptr, &c->refcell_a));
-    MB_TRY(bin_set(c, xyz2, d_ids2, n2, pl.g, c->tmp4b, c->cellid_b, nullptr, nullptr, &c->refcell_b));
+    const float *d_vdw1 = nullptr, *d_vdw2 = nullptr;
+    if (vdw) {
+        MB_TRY(c->vdw_a.reserve(n1 * sizeof(float)));
+        MB_TRY(c->vdw_b.reserve(n2 * sizeof(float)));
+        MB_CUDA(cudaMemcpyAsync(c->vdw_a.p, vdw1, n1 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+        MB_CUDA(cudaMemcpyAsync(c->vdw_b.p, vdw2, n2 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+        d_vdw1 = c->vdw_a.as<float>();
+        d_vdw2 = c->vdw_b.as<float>();
+    }
+    MB_TRY(bin_set(c, c->d_xyz, d_ids1, n1, pl.g, c->tmp4a, c->cellid_a, nullptr, nullptr, &c->refcell_a, vdw ? 1 : 0));
+    MB_TRY(bin_set(c, xyz2, d_ids2, n2, pl.g, c->tmp4b, c->cellid_b, nullptr, nullptr, &c->refcell_b, vdw ? 1 : 0));
     unsigned long long found = 0;
     if (within) {
         MB_TRY(c->flags.reserve(n1 + 16));
@@ -1667,7 +1701,7 @@ static int search_two_sets(Ctx* c, float cutoff, const uint64_t* ids1, size_t n1
             MB_CUDA(cudaMemsetAsync(d_counter, 0, 2 * sizeof(unsigned long long), c->stream));
             MB_TRY(enqueue_brute(c, pl, cutoff, 1, with_dist, 0, n1, n2, c->tmp4a.as<float4>(),
                                  c->refcell_a.as<unsigned long long>(), c->tmp4b.as<float4>(),
-                                 c->refcell_b.as<unsigned long long>(), d_counter));
+                                 c->refcell_b.as<unsigned long long>(), d_counter, d_vdw1, d_vdw2));
             MB_CUDA(cudaMemcpyAsync(&found, d_counter, sizeof(found), cudaMemcpyDeviceToHost, c->stream));
             MB_CUDA(cudaStreamSynchronize(c->stream));
             if (found <= c->pair_cap) break;
@@ -1842,6 +1876,15 @@ int64_t mb_search_double(MbCtx* h, float cutoff, const uint64_t* ids1, size_t n1
     if (!h) return fail(MB_ERR_ARG, "null context");
     int64_t cnt = 0;
     int rc = search_two_sets(&h->c, cutoff, ids1, n1, ids2, n2, use_frame2, pbc_dims & 7, 0, nullptr, nullptr, &cnt);
+    return rc < 0 ? rc : cnt;
+}
+
+int64_t mb_search_double_vdw(MbCtx* h, const uint64_t* ids1, size_t n1, const float* vdw1, const uint64_t* ids2,
+                             size_t n2, const float* vdw2, int use_frame2, uint8_t pbc_dims) {
+    if (!h || !vdw1 || !vdw2) return fail(MB_ERR_ARG, "null argument");
+    int64_t cnt = 0;
+    int rc = search_two_sets(&h->c, 1.0f, ids1, n1, ids2, n2, use_frame2, pbc_dims & 7, 0, nullptr, nullptr, &cnt, vdw1,
+                             vdw2);
     return rc < 0 ? rc : cnt;
 }
 

@@ -277,11 +277,15 @@ struct Grid {
         }
     }
     // :120-142
-    void populate(const float* xyz, const uint64_t* ids, size_t n, const Vf& lower, const Vf& upper) {
+    // local_ids: entries carry the LOCAL index k (the vdW searches iterate `0..vdw.len()`,
+    // distance_search.rs:791-792,852-853) instead of the global atom index
+    void populate(const float* xyz, const uint64_t* ids, size_t n, const Vf& lower, const Vf& upper,
+                  bool local_ids = false) {
         Vf dim_sz = sub(upper, lower);
         for (size_t k = 0; k < n; ++k) {
-            size_t id = ids ? (size_t)ids[k] : k;
-            const Vf* pos = reinterpret_cast<const Vf*>(xyz) + id;
+            size_t gid = ids ? (size_t)ids[k] : k;
+            size_t id = local_ids ? k : gid;
+            const Vf* pos = reinterpret_cast<const Vf*>(xyz) + gid;
             size_t loc[3] = {0, 0, 0};
             bool skip = false;
             for (int d = 0; d < 3; ++d) {
@@ -297,13 +301,15 @@ struct Grid {
         }
     }
     // :144-210
-    void populate_pbc(const float* xyz, const uint64_t* ids, size_t n, const Boxf& bx, uint8_t pbc_dims) {
+    void populate_pbc(const float* xyz, const uint64_t* ids, size_t n, const Boxf& bx, uint8_t pbc_dims,
+                      bool local_ids = false) {
         std::vector<std::pair<size_t, size_t>> wrapped_ind;
         wrapped_pos.clear();
         wrapped_pos.reserve(64);
         for (size_t k = 0; k < n; ++k) {
-            size_t id = ids ? (size_t)ids[k] : k;
-            const Vf* pos = reinterpret_cast<const Vf*>(xyz) + id;
+            size_t gid = ids ? (size_t)ids[k] : k;
+            size_t id = local_ids ? k : gid;
+            const Vf* pos = reinterpret_cast<const Vf*>(xyz) + gid;
             Vf rel = matvec(bx.inv, *pos);
             size_t loc[3] = {0, 0, 0};
             bool correct = true, skip = false;
@@ -429,6 +435,20 @@ void search_cell_pair_double(float cutoff2, const Grid& g1, const Grid& g2, size
             float d2 = (pbox && wrapped != 0) ? distance_squared(*pbox, *a[i].pos, *b[j].pos, wrapped)
                                               : norm_squared(sub(*b[j].pos, *a[i].pos));
             if (d2 <= cutoff2) found.push_back({a[i].id, b[j].id, std::sqrt(d2)});
+        }
+}
+
+// :375-430  (vdw1/vdw2 indexed by the local ids stored in the grids)
+void search_cell_pair_double_vdw(const Grid& g1, const Grid& g2, size_t c1, size_t c2, uint8_t wrapped,
+                                 const float* vdw1, const float* vdw2, const Boxf* pbox, std::vector<Triple>& found) {
+    const auto& a = g1.cells[c1];
+    const auto& b = g2.cells[c2];
+    for (size_t i = 0; i < a.size(); ++i)
+        for (size_t j = 0; j < b.size(); ++j) {
+            float d2 = (pbox && wrapped != 0) ? distance_squared(*pbox, *a[i].pos, *b[j].pos, wrapped)
+                                              : norm_squared(sub(*b[j].pos, *a[i].pos));
+            float cutoff = vdw1[a[i].id] + vdw2[b[j].id] + std::numeric_limits<float>::epsilon();
+            if (d2 <= cutoff * cutoff) found.push_back({a[i].id, b[j].id, std::sqrt(d2)});
         }
 }
 
@@ -715,6 +735,51 @@ OrcResult* orc_search_within_pbc(float cutoff, const float* xyz1, const uint64_t
     res->ids = run_plan<size_t>(plan, nthreads, [&](const PlanEntry& p, std::vector<size_t>& out) {
         search_cell_pair_within(c2, g1, g2, p.c1, p.c2, p.wrapped, &box->b, out);
         search_cell_pair_within(c2, g1, g2, p.c2, p.c1, p.wrapped, &box->b, out);
+    });
+    for (int d = 0; d < 3; ++d) res->dims[d] = sz[d];
+    return res;
+}
+
+// distance_search.rs:767-879 (box == NULL or pbc_dims == 0: the non-periodic variant :767-814)
+OrcResult* orc_search_double_vdw(const float* xyz1, const uint64_t* ids1, size_t n1, const float* vdw1,
+                                 const float* xyz2, const uint64_t* ids2, size_t n2, const float* vdw2,
+                                 const OrcBox* box, uint8_t pbc_dims, int nthreads) {
+    auto* res = new OrcResult;
+    float m1 = vdw1[0], m2 = vdw2[0];
+    for (size_t k = 1; k < n1; ++k) m1 = std::fmax(m1, vdw1[k]);  // iter().cloned().reduce(Float::max)
+    for (size_t k = 1; k < n2; ++k) m2 = std::fmax(m2, vdw2[k]);
+    const float cutoff = m1 + m2 + F_EPS;
+    Grid g1, g2;
+    size_t sz[3];
+    const bool periodic = box && pbc_dims;
+    Vf l, u;
+    if (periodic) {
+        Grid::dims_from_cutoff_and_extents(cutoff, lab_extents(box->b), sz);
+    } else {
+        Vf l1, u1, l2, u2;
+        compute_min_max(xyz1, ids1, n1, l1, u1);
+        compute_min_max(xyz2, ids2, n2, l2, u2);
+        for (int d = 0; d < 3; ++d) {
+            l[d] = std::min(l1[d], l2[d]);
+            u[d] = std::max(u1[d], u2[d]);
+        }
+        pad_bounds(cutoff, l, u);
+        Grid::dims_from_cutoff_and_extents(cutoff, sub(u, l), sz);
+    }
+    g1.init(sz);
+    g2.init(sz);
+    if (periodic) {
+        g1.populate_pbc(xyz1, ids1, n1, box->b, pbc_dims, true);
+        g2.populate_pbc(xyz2, ids2, n2, box->b, pbc_dims, true);
+    } else {
+        g1.populate(xyz1, ids1, n1, l, u, true);
+        g2.populate(xyz2, ids2, n2, l, u, true);
+    }
+    auto plan = search_plan(g1, &g2, periodic ? pbc_dims : PBC_NONE);
+    const Boxf* pb = periodic ? &box->b : nullptr;
+    res->triples = run_plan<Triple>(plan, nthreads, [&](const PlanEntry& p, std::vector<Triple>& out) {
+        search_cell_pair_double_vdw(g1, g2, p.c1, p.c2, p.wrapped, vdw1, vdw2, pb, out);
+        search_cell_pair_double_vdw(g1, g2, p.c2, p.c1, p.wrapped, vdw1, vdw2, pb, out);
     });
     for (int d = 0; d < 3; ++d) res->dims[d] = sz[d];
     return res;

@@ -69,6 +69,12 @@ OrcResult* orc_search_within(float cutoff, const float* xyz1, const uint64_t* id
 OrcResult* orc_search_within_pbc(float cutoff, const float* xyz1, const uint64_t* ids1, size_t n1,
                                  const float* xyz2, const uint64_t* ids2, size_t n2,
                                  const OrcBox* box, uint8_t pbc_dims, int nthreads); /* :560-598 */
+/* van der Waals search (distance_search.rs:767-879): per-pair cutoff vdw1[i]+vdw2[j]+EPSILON, grid cutoff
+   max(vdw1)+max(vdw2)+EPSILON; vdw arrays are per SELECTED atom and the returned indices are LOCAL
+   (position within the selection), as in the reference.  box==NULL or pbc_dims==0: non-periodic. */
+OrcResult* orc_search_double_vdw(const float* xyz1, const uint64_t* ids1, size_t n1, const float* vdw1,
+                                 const float* xyz2, const uint64_t* ids2, size_t n2, const float* vdw2,
+                                 const OrcBox* box, uint8_t pbc_dims, int nthreads);
 /* Measure::min_max (measure.rs:22-36) followed by the +-cutoff+EPS padding the `within`
    AST node applies (selection/ast.rs:598-600). */
 void orc_within_bounds(float cutoff, const float* xyz, const uint64_t* ids, size_t n,

@@ -66,6 +66,9 @@ def lib():
         L.orc_search_within_pbc.restype = C.c_void_p
         L.orc_search_within_pbc.argtypes = [C.c_float, _f32p, _u64p, C.c_size_t, _f32p, _u64p, C.c_size_t,
                                             C.c_void_p, C.c_uint8, C.c_int]
+        L.orc_search_double_vdw.restype = C.c_void_p
+        L.orc_search_double_vdw.argtypes = [_f32p, _u64p, C.c_size_t, _f32p, _f32p, _u64p, C.c_size_t, _f32p,
+                                            C.c_void_p, C.c_uint8, C.c_int]
         L.orc_within_bounds.argtypes = [C.c_float, _f32p, _u64p, C.c_size_t, _f32p, _f32p]
         for suf, fp in (("f32", _f32p), ("f64", _f64p)):
             getattr(L, "orc_center_of_mass_" + suf).argtypes = [_f32p, _f32p, _u64p, C.c_size_t, fp]
@@ -203,6 +206,22 @@ def search_double(cutoff, xyz1, ids1, xyz2, ids2, box=None, pbc=0, nthreads=1):
         h = lib().orc_search_double_pbc(cutoff, p1, ip1, n1, p2, ip2, n2, box.h, pbc, nthreads)
     else:
         h = lib().orc_search_double(cutoff, p1, ip1, n1, p2, ip2, n2, nthreads)
+    return _take_pairs(h)
+
+
+def search_double_vdw(xyz1, ids1, vdw1, xyz2, ids2, vdw2, box=None, pbc=0, nthreads=1):
+    """Raw reference output with LOCAL indices (ij[n,2], d[n], grid dims)."""
+    x1, p1 = _f32(xyz1)
+    x2, p2 = _f32(xyz2)
+    i1, ip1 = _ids(ids1)
+    i2, ip2 = _ids(ids2)
+    v1, vp1 = _f32(vdw1)
+    v2, vp2 = _f32(vdw2)
+    n1 = len(i1) if i1 is not None else x1.size // 3
+    n2 = len(i2) if i2 is not None else x2.size // 3
+    assert len(v1) == n1 and len(v2) == n2
+    h = lib().orc_search_double_vdw(p1, ip1, n1, vp1, p2, ip2, n2, vp2, box.h if (box is not None and pbc) else None,
+                                    pbc, nthreads)
     return _take_pairs(h)
 
 

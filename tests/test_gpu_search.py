@@ -150,6 +150,31 @@ def test_double_search_vs_oracle(mb):
         assert_same_pairs(gp, gd, op, od)
 
 
+@pytest.mark.parametrize("pbc", [0, 7])
+def test_double_vdw_search_vs_oracle(mb, pbc):
+    """distance_search_double_vdw[_pbc] (distance_search.rs:767-879) through the pymolar-style
+    `distance_search("vdw", sel1, sel2)`: local indices converted to global like pymolar does."""
+    M = np.diag([4.0, 4.2, 4.4]).astype(np.float32)
+    n = 9000
+    xyz = orc.synth_frame(SEED + 21, 0, n, M, stray_permille=10)
+    rng = np.random.default_rng(3)
+    vdw = (0.12 + 0.1 * rng.random(n)).astype(np.float32)
+    ids1 = np.arange(0, n, 2, dtype=np.uint64)
+    ids2 = np.arange(1, n, 3, dtype=np.uint64)
+    box = orc.Box(matrix=M)
+    ij, d, dims = orc.search_double_vdw(xyz, ids1, vdw[ids1.astype(int)], xyz, ids2, vdw[ids2.astype(int)],
+                                        box if pbc else None, pbc, 4)
+    op, od = orc.ordered_pairs(ij, d)
+    op = np.stack([ids1[op[:, 0].astype(int)], ids2[op[:, 1].astype(int)]], 1)
+    s = mb.System(xyz, box=M, vdw=vdw)
+    pairs, dist = mb.distance_search("vdw", s(ids1), s(ids2), dims=[bool(pbc)] * 3)
+    s.close()
+    gp, gd = orc.ordered_pairs(pairs, dist)
+    assert len(gp) == len(pairs)
+    order = np.lexsort((op[:, 1], op[:, 0]))
+    assert_same_pairs(gp, gd, op[order], od[order])
+
+
 CASES = ["within_0.5_resid10", "within_0.3_resid20", "within_0.5_resid555", "within_0.5_pbc_resid555"]
 
 

@@ -161,3 +161,29 @@ def test_single_nonpbc_vs_bruteforce(golden_dir):
     # config 1: rmsd to self is exactly 0
     rc, r = orc.rmsd(xyz, None, xyz, None, prec="f32")
     assert rc == 0 and r == 0.0
+
+
+def test_double_vdw_vs_bruteforce():
+    # distance_search_double_vdw[_pbc] (distance_search.rs:767-879): per-pair cutoff, LOCAL indices
+    M = np.diag([3.0, 3.2, 3.4]).astype(np.float32)
+    xyz = orc.synth_frame(1, 0, 3000, M)
+    ids1 = np.arange(0, 3000, 2, dtype=np.uint64)
+    ids2 = np.arange(1, 3000, 3, dtype=np.uint64)
+    rng = np.random.default_rng(0)
+    v1 = (0.1 + 0.1 * rng.random(len(ids1))).astype(np.float32)
+    v2 = (0.12 + 0.08 * rng.random(len(ids2))).astype(np.float32)
+    a = xyz[ids1.astype(int)].astype(np.float64)
+    b = xyz[ids2.astype(int)].astype(np.float64)
+    for pbc, box in ((0, None), (7, orc.Box(matrix=M))):
+        ij, d, dims = orc.search_double_vdw(xyz, ids1, v1, xyz, ids2, v2, box, pbc, 2)
+        got, gd = orc.ordered_pairs(ij, d)
+        dd = a[:, None, :] - b[None, :, :]
+        if pbc:
+            L = np.diag(M).astype(np.float64)
+            dd -= np.round(dd / L) * L
+        r = np.sqrt((dd ** 2).sum(-1))
+        cut = v1[:, None].astype(np.float64) + v2[None, :] + np.finfo(np.float32).eps
+        bi, bj = np.nonzero(r <= cut)
+        assert len(got) == len(bi)
+        assert np.array_equal(got, np.stack([bi, bj], 1).astype(np.uint64))
+        assert got[:, 0].max() < len(ids1) and got[:, 1].max() < len(ids2)  # local indices
