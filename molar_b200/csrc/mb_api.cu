@@ -213,7 +213,7 @@ void mb_close(MbCtx* h) {
     DevBuf* bufs[] = {&c.xyz_own, &c.xyz2, &c.masses, &c.ids1, &c.ids2, &c.tmp4a, &c.tmp4b, &c.cellid_a,
                       &c.cellid_b, &c.rank_a, &c.refcell_a, &c.refcell_b, &c.sorted4, &c.cell_count,
                       &c.cell_start, &c.scan_tmp, &c.pairs, &c.dists, &c.flags, &c.out_ids, &c.counters,
-                      &c.reduce_tmp, &c.batch, &c.batch_scalars, &c.batch_tmp, &c.batch_ref, &c.pipe_tmp, &c.vdw_a, &c.vdw_b};
+                      &c.reduce_tmp, &c.batch, &c.batch_scalars, &c.batch_tmp, &c.batch_ref, &c.pipe_tmp, &c.vdw_a, &c.vdw_b, &c.rank_b, &c.cell_count_b, &c.cell_start_b, &c.sorted4_b};
     for (DevBuf* b : bufs) b->release();
     for (SearchSlot& sl : c.alt) {
         DevBuf* sb[] = {&sl.tmp4a, &sl.cellid_a, &sl.rank_a, &sl.cell_count, &sl.cell_start, &sl.sorted4, &sl.scan_tmp,
@@ -253,6 +253,7 @@ int mb_set_option(MbCtx* h, const char* key, double value) {
     else if (!strcmp(key, "exact_pbc")) c.opt_exact_pbc = (int)value;
     else if (!strcmp(key, "fused_fit")) c.opt_fused_fit = (int)value;
     else if (!strcmp(key, "batch_streams")) c.opt_batch_streams = (int)value;
+    else if (!strcmp(key, "two_set_cells_min")) c.opt_two_set_cells_min = value;
     else if (!strcmp(key, "profile")) {
         c.opt_profile = (int)value;
         c.prof_search_ms = 0.0;

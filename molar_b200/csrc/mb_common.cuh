@@ -121,6 +121,7 @@ struct Ctx {
     DevBuf refcell_a, refcell_b;  // packed reference cell coords (u64) for the general kernel
     DevBuf sorted4;         // atoms sorted by fine cell
     DevBuf cell_count, cell_start, scan_tmp;
+    DevBuf rank_b, cell_count_b, cell_start_b, sorted4_b;  // second set of a two-set cell search
     DevBuf pairs, dists, flags, out_ids;
     DevBuf counters;        // small block of device counters / results
     DevBuf reduce_tmp;      // per-block partials
@@ -136,6 +137,7 @@ struct Ctx {
     int opt_force_brute = 0;  // force the general all-pairs kernel
     double opt_atoms_per_cell = 8.0;  // minimum mean population of a home tile
     int opt_with_dist = 1;
+    double opt_two_set_cells_min = 5.0e7;  // two-set searches use the cell kernel when n1*n2 exceeds this
     int opt_batch_streams = 0;  // streams (slots) batch_search alternates frames over; 0 = automatic
     int opt_fused_fit = 0;  // 1: batch_fit uses the persistent TMA-staged kernel (slower than the two-kernel path so far)
     int opt_exact_pbc = 0;    // 1: wrapped cell pairs always use the exact PeriodicBox path (no filter)

@@ -55,8 +55,12 @@ struct NbrRow {
 };
 
 struct SearchParams {
-    const float4* sorted;
+    const float4* sorted;        // home atoms (set 1), sorted by fine cell
     const unsigned* cell_start;
+    const float4* sortedB;       // candidate atoms (set 2); same arrays as above for a single-set search
+    const unsigned* cell_startB;
+    int two_sets;                // 1: rows cover the full shell, no self run, pairs are (set-1 id, set-2 id)
+    unsigned char* flags;        // MODE 3 (`within`): flags[global id of a set-1 atom] = 1 if it has a neighbour
     GridSpec g;
     float rc2;
     float rc2_lo, rc2_hi;  // band around cutoff^2 outside which the shifted-image filter is decisive
@@ -461,14 +465,15 @@ struct __align__(16) WarpShared {
 //           per step (two per lane, two coalesced float4 loads), tested against the home atoms that
 //           are broadcast from shared memory (one LDS.128 per home atom), hits are kept as per-lane
 //           bit masks and expanded into the staging buffer afterwards.
-// MODE: 0 pairs, 1 pairs + distances, 2 count only
+// MODE: 0 pairs, 1 pairs + distances, 2 count only, 3 `within` flags (two sets)
 template <int MODE>
 __global__ void __launch_bounds__(SEARCH_WARPS * 32, 4) search_cells_kernel(const __grid_constant__ SearchParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const unsigned lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
     WarpShared& ws = reinterpret_cast<WarpShared*>(smem_raw)[wid];
-    uint2* stage = MODE != 2 ? reinterpret_cast<uint2*>(smem_raw + SEARCH_WARPS * sizeof(WarpShared)) + wid * STAGE_CAP
-                             : nullptr;
+    uint2* stage = (MODE == 0 || MODE == 1)
+                       ? reinterpret_cast<uint2*>(smem_raw + SEARCH_WARPS * sizeof(WarpShared)) + wid * STAGE_CAP
+                       : nullptr;
     float* stage_d = MODE == 1 ? reinterpret_cast<float*>(smem_raw + SEARCH_WARPS * (sizeof(WarpShared) +
                                                                                     STAGE_CAP * sizeof(uint2))) +
                                      wid * STAGE_CAP
@@ -505,7 +510,7 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32, 4) search_cells_kernel(cons
             // ---------------- Phase A: fill the run table ----------------
             unsigned nr = 0, T = 0;
             __syncwarp();
-            if (first) {
+            if (first && !P.two_sets) {
                 if (lane == 0) {
                     ws.rstart[0] = hs;
                     ws.rpos[0] = 0;
@@ -522,7 +527,7 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32, 4) search_cells_kernel(cons
                 unsigned nd = 0, nw = 0, ld = 0, lw = 0;
                 if (ri < P.nrows)
                     gen_row_runs(g, fx, fy, fz, cx, cy, cz, row, [&](int c0, int c1, unsigned f) {
-                        unsigned len = P.cell_start[c1 + 1] - P.cell_start[c0];
+                        unsigned len = P.cell_startB[c1 + 1] - P.cell_startB[c0];
                         if (len) {
                             if (f & 7u) { ++nw; lw += len; } else { ++nd; ld += len; }
                         }
@@ -544,7 +549,7 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32, 4) search_cells_kernel(cons
                 unsigned pd = T + ldi - ld, pw = T + tot_ld + lwi - lw;
                 if (ri < P.nrows)
                     gen_row_runs(g, fx, fy, fz, cx, cy, cz, row, [&](int c0, int c1, unsigned f) {
-                        unsigned s = P.cell_start[c0], len = P.cell_start[c1 + 1] - s;
+                        unsigned s = P.cell_startB[c0], len = P.cell_startB[c1 + 1] - s;
                         if (len) {
                             if (f & 7u) {
                                 ws.rstart[sw] = s; ws.rpos[sw] = pw; ws.rflag[sw] = (unsigned char)f;
@@ -570,6 +575,7 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32, 4) search_cells_kernel(cons
                 ws.home[lane] = (lane < (unsigned)nh) ? __ldg(&P.sorted[hb + lane]) : make_float4(qnan, 0.f, 0.f, 0.f);
                 __syncwarp();
                 unsigned cur0 = 0, cur1 = 0;
+                unsigned hit_any = 0;  // MODE 3: bit j = home atom j has a set-2 atom within the cutoff
 #pragma unroll 1
                 for (unsigned c0 = 0; c0 < T; c0 += 64) {
                     const unsigned p0 = c0 + lane, p1 = p0 + 32;
@@ -579,14 +585,14 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32, 4) search_cells_kernel(cons
                         while (ws.rpos[cur0 + 1] <= p0) ++cur0;
                         a0i = ws.rstart[cur0] + (p0 - ws.rpos[cur0]);
                         f0 = ws.rflag[cur0];
-                        n0 = __ldg(&P.sorted[a0i]);
+                        n0 = __ldg(&P.sortedB[a0i]);
                     }
                     if (p1 < T) {
                         cur1 = max(cur1, cur0);
                         while (ws.rpos[cur1 + 1] <= p1) ++cur1;
                         a1i = ws.rstart[cur1] + (p1 - ws.rpos[cur1]);
                         f1 = ws.rflag[cur1];
-                        n1 = __ldg(&P.sorted[a1i]);
+                        n1 = __ldg(&P.sortedB[a1i]);
                     }
                     unsigned m0 = 0, m1 = 0;
                     if (!__any_sync(0xffffffffu, (f0 | f1) != 0u)) {
@@ -674,6 +680,10 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32, 4) search_cells_kernel(cons
                             m1 &= lim >= 32 ? 0xffffffffu : ((1u << lim) - 1u);
                         }
                     }
+                    if (MODE == 3) {
+                        hit_any |= m0 | m1;
+                        continue;
+                    }
                     const int c0n = __popc(m0), c1n = __popc(m1);
                     if (MODE == 2) {
                         count += c0n + c1n;
@@ -747,6 +757,10 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32, 4) search_cells_kernel(cons
                         stage_n += need;
                     }
                 }
+                if (MODE == 3) {
+                    hit_any = __reduce_or_sync(0xffffffffu, hit_any);
+                    if (lane < (unsigned)nh && ((hit_any >> lane) & 1u)) P.flags[__float_as_uint(home[lane].w)] = 1;
+                }
             }
             first = false;
         } while (row0 < P.nrows);
@@ -755,7 +769,7 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32, 4) search_cells_kernel(cons
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) count += __shfl_xor_sync(0xffffffffu, count, o);
         if (lane == 0 && count) atomicAdd(P.counter, count);
-    } else {
+    } else if (MODE != 3) {
         warp_flush<MODE == 1>(stage, stage_d, stage_n, P, lane);
     }
 }
@@ -958,16 +972,19 @@ __global__ void __launch_bounds__(256) minmax_kernel(const float* __restrict__ x
     }
 }
 
+// by_gid: flags are indexed by GLOBAL atom id (cell kernel) instead of by position in the selection
 __global__ void compact_flags_kernel(const unsigned char* __restrict__ flags, const unsigned* __restrict__ pos,
-                                     const unsigned long long* __restrict__ ids, int n,
+                                     const unsigned long long* __restrict__ ids, int n, int by_gid,
                                      unsigned long long* __restrict__ out) {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
-    if (flags[k]) out[pos[k]] = ids ? ids[k] : (unsigned long long)k;
+    unsigned long long gid = ids ? ids[k] : (unsigned long long)k;
+    if (flags[by_gid ? gid : (unsigned long long)k]) out[pos[k]] = gid;
 }
-__global__ void flags_to_u32_kernel(const unsigned char* __restrict__ flags, int n, unsigned* __restrict__ out) {
+__global__ void flags_to_u32_kernel(const unsigned char* __restrict__ flags, const unsigned long long* __restrict__ ids,
+                                    int n, int by_gid, unsigned* __restrict__ out) {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k < n) out[k] = flags[k];
+    if (k < n) out[k] = flags[by_gid ? (ids ? ids[k] : (unsigned long long)k) : (unsigned long long)k];
 }
 
 __device__ __forceinline__ unsigned long long mix64(unsigned long long x) {
@@ -1081,6 +1098,7 @@ static double min_cell_dist2(const double M[3][3], const int delta[3], int hx = 
 struct Plan {
     GridSpec g;
     bool use_cells;
+    bool full_shell;  // two-set search: rows cover both half-spaces and the home row entirely
     int fast_pbc;
     float rc2_lo, rc2_hi;
     int nrows;
@@ -1198,8 +1216,9 @@ static void plan_cells(const Ctx* c, Plan& pl, float cutoff, size_t n) {
         // in different tiles is then visited from exactly one side, with or without periodic
         // wrapping (offsets are unique modulo the grid because fd >= 2(R+hx)+1).
         int nrows = 0;
-        for (int dz = 0; dz <= R[2]; ++dz)
-            for (int dy = (dz == 0 ? 0 : -R[1]); dy <= R[1]; ++dy) {
+        const bool full = pl.full_shell;
+        for (int dz = (full ? -R[2] : 0); dz <= R[2]; ++dz)
+            for (int dy = ((dz == 0 && !full) ? 0 : -R[1]); dy <= R[1]; ++dy) {
                 int lo = 127, hi = -128;
                 for (int dx = -R[0]; dx <= hx - 1 + R[0]; ++dx) {
                     int delta[3] = {dx, dy, dz};
@@ -1208,7 +1227,7 @@ static void plan_cells(const Ctx* c, Plan& pl, float cutoff, size_t n) {
                         hi = std::max(hi, dx);
                     }
                 }
-                if (dz == 0 && dy == 0) lo = std::max(lo, hx);
+                if (dz == 0 && dy == 0 && !full) lo = std::max(lo, hx);
                 if (lo <= hi) {
                     pl.rows[nrows].dy = (signed char)dy;
                     pl.rows[nrows].dz = (signed char)dz;
@@ -1279,7 +1298,7 @@ struct PlanKey {
     unsigned pbc;
     size_t n;
     float m[9];
-    int subdiv, brute, exact_pbc, sx, sy, sz, slice;
+    int subdiv, brute, exact_pbc, sx, sy, sz, slice, full;
     double apc;
 };
 struct PlanCache {
@@ -1350,7 +1369,7 @@ static int make_grid_pbc(const Ctx* c, float cutoff, uint8_t pbc, GridSpec& g) {
 }
 
 // periodic-variant plan for the context's current box, memoised
-static int get_plan_pbc(Ctx* c, float cutoff, uint8_t pbc, size_t n, Plan& out) {
+static int get_plan_pbc(Ctx* c, float cutoff, uint8_t pbc, size_t n, Plan& out, bool full_shell = false) {
     if (!c->has_box) return fail(MB_ERR_NO_PBC, "periodic search requested but the frame has no box");
     PlanKey k;
     memset(&k, 0, sizeof(k));
@@ -1366,6 +1385,7 @@ static int get_plan_pbc(Ctx* c, float cutoff, uint8_t pbc, size_t n, Plan& out) 
     k.sy = c->opt_subdiv_xyz[1];
     k.sz = c->opt_subdiv_xyz[2];
     k.slice = c->opt_slice_x;
+    k.full = full_shell ? 1 : 0;
     k.apc = c->opt_atoms_per_cell;
     PlanCache* pc = static_cast<PlanCache*>(c->plan_cache);
     if (!pc) {
@@ -1377,6 +1397,7 @@ static int get_plan_pbc(Ctx* c, float cutoff, uint8_t pbc, size_t n, Plan& out) 
         return MB_OK;
     }
     memset(&out, 0, sizeof(out));
+    out.full_shell = full_shell;
     MB_TRY(make_grid_pbc(c, cutoff, pbc, out.g));
     plan_cells(c, out, cutoff, n);
     pc->key = k;
@@ -1434,7 +1455,7 @@ static int bin_set(Ctx* c, const float* xyz, const unsigned long long* d_ids, si
 template <int MODE>
 static int launch_search_cells(Ctx* c, const SearchParams& P) {
     size_t smem = SEARCH_WARPS * sizeof(WarpShared);
-    if (MODE != 2) smem += SEARCH_WARPS * STAGE_CAP * sizeof(uint2);
+    if (MODE == 0 || MODE == 1) smem += SEARCH_WARPS * STAGE_CAP * sizeof(uint2);
     if (MODE == 1) smem += SEARCH_WARPS * STAGE_CAP * sizeof(float);
     MB_CUDA(cudaFuncSetAttribute(search_cells_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 1;
@@ -1477,6 +1498,10 @@ int enqueue_cells_search(Ctx* c, const float* xyz, const unsigned long long* d_i
     SearchParams P;
     P.sorted = c->sorted4.as<float4>();
     P.cell_start = c->cell_start.as<unsigned>();
+    P.sortedB = P.sorted;
+    P.cell_startB = P.cell_start;
+    P.two_sets = 0;
+    P.flags = nullptr;
     P.g = g;
     P.rc2 = cutoff * cutoff;
     P.rc2_lo = pl.rc2_lo;
@@ -1490,6 +1515,56 @@ int enqueue_cells_search(Ctx* c, const float* xyz, const unsigned long long* d_i
     P.counter = d_counter;
     if (mode == 2) return launch_search_cells<2>(c, P);
     if (mode == 1) return launch_search_cells<1>(c, P);
+    return launch_search_cells<0>(c, P);
+}
+
+// Two-set variant (double / within): set 1 supplies the home tiles, set 2 the candidate stream, both
+// binned on the same fine grid; the neighbour table covers the full shell.  kmode 0/1 pairs, 3 flags.
+static int enqueue_cells_search2(Ctx* c, const float* xyz1, const unsigned long long* d_ids1, size_t n1,
+                                 const float* xyz2, const unsigned long long* d_ids2, size_t n2, const Plan& pl,
+                                 float cutoff, int kmode, unsigned long long* d_counter) {
+    const GridSpec& g = pl.g;
+    const size_t cb = (pl.ncells + 2) * sizeof(unsigned);
+    MB_TRY(c->cell_count.reserve(cb));
+    MB_TRY(c->cell_start.reserve(cb));
+    MB_TRY(c->cell_count_b.reserve(cb));
+    MB_TRY(c->cell_start_b.reserve(cb));
+    MB_TRY(c->sorted4.reserve((n1 + 32) * sizeof(float4)));
+    MB_TRY(c->sorted4_b.reserve((n2 + 32) * sizeof(float4)));
+    MB_CUDA(cudaMemsetAsync(c->cell_count.p, 0, (pl.ncells + 1) * sizeof(unsigned), c->stream));
+    MB_CUDA(cudaMemsetAsync(c->cell_count_b.p, 0, (pl.ncells + 1) * sizeof(unsigned), c->stream));
+    MB_CUDA(cudaMemsetAsync(d_counter, 0, 2 * sizeof(unsigned long long), c->stream));
+    MB_TRY(bin_set(c, xyz1, d_ids1, n1, g, c->tmp4a, c->cellid_a, &c->rank_a, c->cell_count.as<unsigned>(), nullptr));
+    MB_TRY(bin_set(c, xyz2, d_ids2, n2, g, c->tmp4b, c->cellid_b, &c->rank_b, c->cell_count_b.as<unsigned>(), nullptr));
+    MB_TRY(exclusive_scan_u32(c, c->cell_count.as<unsigned>(), (int)pl.ncells, c->cell_start.as<unsigned>()));
+    MB_TRY(exclusive_scan_u32(c, c->cell_count_b.as<unsigned>(), (int)pl.ncells, c->cell_start_b.as<unsigned>()));
+    scatter_kernel<<<(int)((n1 + 255) / 256), 256, 0, c->stream>>>(c->tmp4a.as<float4>(), c->cellid_a.as<unsigned>(),
+                                                                  c->rank_a.as<unsigned>(), c->cell_start.as<unsigned>(),
+                                                                  (int)n1, c->sorted4.as<float4>());
+    scatter_kernel<<<(int)((n2 + 255) / 256), 256, 0, c->stream>>>(c->tmp4b.as<float4>(), c->cellid_b.as<unsigned>(),
+                                                                  c->rank_b.as<unsigned>(), c->cell_start_b.as<unsigned>(),
+                                                                  (int)n2, c->sorted4_b.as<float4>());
+    c->launches += 2;
+    SearchParams P;
+    P.sorted = c->sorted4.as<float4>();
+    P.cell_start = c->cell_start.as<unsigned>();
+    P.sortedB = c->sorted4_b.as<float4>();
+    P.cell_startB = c->cell_start_b.as<unsigned>();
+    P.two_sets = 1;
+    P.flags = c->flags.as<unsigned char>();
+    P.g = g;
+    P.rc2 = cutoff * cutoff;
+    P.rc2_lo = pl.rc2_lo;
+    P.rc2_hi = pl.rc2_hi;
+    P.fast_pbc = pl.fast_pbc;
+    P.nrows = pl.nrows;
+    memcpy(P.rows, pl.rows, sizeof(NbrRow) * pl.nrows);
+    P.pairs = c->pairs.as<uint2>();
+    P.dists = c->dists.as<float>();
+    P.pair_cap = c->pair_cap;
+    P.counter = d_counter;
+    if (kmode == 3) return launch_search_cells<3>(c, P);
+    if (kmode == 1) return launch_search_cells<1>(c, P);
     return launch_search_cells<0>(c, P);
 }
 
@@ -1656,11 +1731,25 @@ static int search_two_sets(Ctx* c, float cutoff, const uint64_t* ids1, size_t n1
         }
         make_grid_bounds(cutoff, lo, hi, pl.g);
     }
-    for (int d = 0; d < 3; ++d) {
-        pl.g.k[d] = 1;
-        pl.g.fd[d] = pl.g.dims[d];
-    }
     const bool with_dist = !within && c->opt_with_dist;
+    // Cell path when the all-pairs product is large and the grid is not degenerate; the general
+    // all-pairs kernel otherwise (small sets, 1-2 reference cells in a periodic dim, vdW radii).
+    pl.full_shell = true;
+    bool cells = false;
+    if (!vdw && (double)n1 * (double)n2 > c->opt_two_set_cells_min && n1 <= 0x7fffffffull && n2 <= 0x7fffffffull) {
+        if (pbc) {
+            MB_TRY(get_plan_pbc(c, cutoff, pbc, std::max(n1, (size_t)4096), pl, true));
+        } else {
+            plan_cells(c, pl, cutoff, std::max(n1, (size_t)4096));
+        }
+        cells = pl.use_cells;
+    }
+    if (!cells)
+        for (int d = 0; d < 3; ++d) {
+            pl.g.k[d] = 1;
+            pl.g.fd[d] = pl.g.dims[d];
+            pl.g.hx = 1;
+        }
     const float *d_vdw1 = nullptr, *d_vdw2 = nullptr;
     if (vdw) {
         MB_TRY(c->vdw_a.reserve(n1 * sizeof(float)));
@@ -1670,40 +1759,57 @@ static int search_two_sets(Ctx* c, float cutoff, const uint64_t* ids1, size_t n1
         d_vdw1 = c->vdw_a.as<float>();
         d_vdw2 = c->vdw_b.as<float>();
     }
-    MB_TRY(bin_set(c, c->d_xyz, d_ids1, n1, pl.g, c->tmp4a, c->cellid_a, nullptr, nullptr, &c->refcell_a, vdw ? 1 : 0));
-    MB_TRY(bin_set(c, xyz2, d_ids2, n2, pl.g, c->tmp4b, c->cellid_b, nullptr, nullptr, &c->refcell_b, vdw ? 1 : 0));
+    if (!cells) {
+        MB_TRY(bin_set(c, c->d_xyz, d_ids1, n1, pl.g, c->tmp4a, c->cellid_a, nullptr, nullptr, &c->refcell_a, vdw ? 1 : 0));
+        MB_TRY(bin_set(c, xyz2, d_ids2, n2, pl.g, c->tmp4b, c->cellid_b, nullptr, nullptr, &c->refcell_b, vdw ? 1 : 0));
+    }
     unsigned long long found = 0;
     if (within) {
-        MB_TRY(c->flags.reserve(n1 + 16));
-        MB_CUDA(cudaMemsetAsync(c->flags.p, 0, n1, c->stream));
-        MB_TRY(enqueue_brute(c, pl, cutoff, 2, 0, 0, n1, n2, c->tmp4a.as<float4>(), c->refcell_a.as<unsigned long long>(),
-                             c->tmp4b.as<float4>(), c->refcell_b.as<unsigned long long>(), d_counter));
-        // ordered compaction of the flagged ids (ids are sorted, so the output is sorted and unique)
-        MB_TRY(c->cell_count.reserve((n1 + 1) * sizeof(unsigned)));
-        MB_TRY(c->cell_start.reserve((n1 + 2) * sizeof(unsigned)));
-        flags_to_u32_kernel<<<(int)((n1 + 255) / 256), 256, 0, c->stream>>>(c->flags.as<unsigned char>(), (int)n1,
-                                                                           c->cell_count.as<unsigned>());
+        // flags: by position in set 1 (all-pairs kernel) or by global atom id (cell kernel)
+        const size_t nflags = cells ? c->n_atoms : n1;
+        MB_TRY(c->flags.reserve(nflags + 16));
+        MB_CUDA(cudaMemsetAsync(c->flags.p, 0, nflags, c->stream));
+        if (cells) {
+            MB_TRY(enqueue_cells_search2(c, c->d_xyz, d_ids1, n1, xyz2, d_ids2, n2, pl, cutoff, 3, d_counter));
+        } else {
+            MB_TRY(enqueue_brute(c, pl, cutoff, 2, 0, 0, n1, n2, c->tmp4a.as<float4>(),
+                                 c->refcell_a.as<unsigned long long>(), c->tmp4b.as<float4>(),
+                                 c->refcell_b.as<unsigned long long>(), d_counter));
+        }
+        // ordered compaction of the flagged ids (ids are sorted, so the output is sorted and unique);
+        // the cell arrays of set 2 are free again and serve as scan scratch
+        MB_TRY(c->cell_count_b.reserve((n1 + 1) * sizeof(unsigned)));
+        MB_TRY(c->cell_start_b.reserve((n1 + 2) * sizeof(unsigned)));
+        flags_to_u32_kernel<<<(int)((n1 + 255) / 256), 256, 0, c->stream>>>(c->flags.as<unsigned char>(), d_ids1, (int)n1,
+                                                                           cells ? 1 : 0, c->cell_count_b.as<unsigned>());
         c->launches++;
-        MB_TRY(exclusive_scan_u32(c, c->cell_count.as<unsigned>(), (int)n1, c->cell_start.as<unsigned>()));
+        MB_TRY(exclusive_scan_u32(c, c->cell_count_b.as<unsigned>(), (int)n1, c->cell_start_b.as<unsigned>()));
         MB_TRY(c->out_ids.reserve((n1 + 1) * sizeof(unsigned long long)));
         compact_flags_kernel<<<(int)((n1 + 255) / 256), 256, 0, c->stream>>>(
-            c->flags.as<unsigned char>(), c->cell_start.as<unsigned>(), d_ids1, (int)n1,
+            c->flags.as<unsigned char>(), c->cell_start_b.as<unsigned>(), d_ids1, (int)n1, cells ? 1 : 0,
             c->out_ids.as<unsigned long long>());
         c->launches++;
         unsigned total = 0;
-        MB_CUDA(cudaMemcpyAsync(&total, c->cell_start.as<unsigned>() + n1, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
+        MB_CUDA(cudaMemcpyAsync(&total, c->cell_start_b.as<unsigned>() + n1, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
         MB_CUDA(cudaStreamSynchronize(c->stream));
+        c->harvest_profile();
         found = total;
         c->last.kind = 3;
     } else {
         MB_TRY(ensure_pair_capacity(c, std::max(estimate_pairs(pl, n1, n2, cutoff, false), c->pair_cap), with_dist));
         for (int attempt = 0; attempt < 3; ++attempt) {
-            MB_CUDA(cudaMemsetAsync(d_counter, 0, 2 * sizeof(unsigned long long), c->stream));
-            MB_TRY(enqueue_brute(c, pl, cutoff, 1, with_dist, 0, n1, n2, c->tmp4a.as<float4>(),
-                                 c->refcell_a.as<unsigned long long>(), c->tmp4b.as<float4>(),
-                                 c->refcell_b.as<unsigned long long>(), d_counter, d_vdw1, d_vdw2));
+            if (cells) {
+                MB_TRY(enqueue_cells_search2(c, c->d_xyz, d_ids1, n1, xyz2, d_ids2, n2, pl, cutoff, with_dist ? 1 : 0,
+                                             d_counter));
+            } else {
+                MB_CUDA(cudaMemsetAsync(d_counter, 0, 2 * sizeof(unsigned long long), c->stream));
+                MB_TRY(enqueue_brute(c, pl, cutoff, 1, with_dist, 0, n1, n2, c->tmp4a.as<float4>(),
+                                     c->refcell_a.as<unsigned long long>(), c->tmp4b.as<float4>(),
+                                     c->refcell_b.as<unsigned long long>(), d_counter, d_vdw1, d_vdw2));
+            }
             MB_CUDA(cudaMemcpyAsync(&found, d_counter, sizeof(found), cudaMemcpyDeviceToHost, c->stream));
             MB_CUDA(cudaStreamSynchronize(c->stream));
+            c->harvest_profile();
             if (found <= c->pair_cap) break;
             MB_TRY(ensure_pair_capacity(c, (size_t)found + 1024, with_dist));
         }

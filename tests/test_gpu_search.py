@@ -150,6 +150,50 @@ def test_double_search_vs_oracle(mb):
         assert_same_pairs(gp, gd, op, od)
 
 
+@pytest.mark.parametrize("pbc", [0, 7, 3])
+@pytest.mark.parametrize("tric", [False, True])
+def test_double_and_within_cell_path_vs_oracle(mb, pbc, tric):
+    """Two-set searches large enough for the cell kernel (home tiles from set 1, candidate stream from
+    set 2, full shell): ordered pair set + distances, and the `within` id set, against the oracle."""
+    from molar_b200.api import within
+    M = (TRIC * np.float32(0.33)).astype(np.float32) if tric else np.diag([6.0, 7.0, 8.0]).astype(np.float32)
+    n = 40000
+    xyz = orc.synth_frame(SEED + 31, 0, n, M, stray_permille=10)
+    ids1 = np.arange(0, n, 2, dtype=np.uint64)
+    ids2 = np.arange(1, n, 3, dtype=np.uint64)
+    box = orc.Box(matrix=M)
+    ij, d, dims = orc.search_double(1.0, xyz, ids1, xyz, ids2, box if pbc else None, pbc, 8)
+    op, od = orc.ordered_pairs(ij, d)
+    s = mb.System(xyz, box=M)
+    s.set_option("two_set_cells_min", 0)
+    pairs, dist = mb.distance_search(1.0, s(ids1), s(ids2), dims=[bool(pbc & 1), bool(pbc & 2), bool(pbc & 4)])
+    gp, gd = orc.ordered_pairs(pairs, dist)
+    assert len(gp) == len(pairs)
+    assert_same_pairs(gp, gd, op, od)
+    # within: small inner set, periodic and non-periodic
+    inner = np.arange(100, 400, dtype=np.uint64)
+    if pbc:
+        ref_ids = orc.search_within(0.7, xyz, None, xyz, inner, box=box, pbc=pbc, nthreads=4)
+    else:
+        lo, up = orc.within_bounds(0.7, xyz, None)
+        ref_ids = orc.search_within(0.7, xyz, None, xyz, inner, lower=lo, upper=up, nthreads=4)
+    got = within(0.7, s(), s(inner), dims=pbc)
+    assert np.array_equal(got, np.unique(ref_ids))
+    s.close()
+
+
+@pytest.mark.parametrize("case", ["within_0.5_resid555", "within_0.5_pbc_resid555"])
+def test_within_golden_vectors_through_cell_path(mb, golden_dir, case):
+    from molar_b200.api import within
+    z = np.load(os.path.join(golden_dir, "albumin_within.npz"))
+    cutoff, pbc = z[case + "_params"]
+    s = mb.System(z["xyz"], box=z["box9"].reshape(3, 3).T)
+    s.set_option("two_set_cells_min", 0)
+    got = within(float(np.float32(cutoff)), s(), s(z[case + "_inner"].astype(np.uint64)), dims=int(pbc))
+    s.close()
+    assert np.array_equal(got.astype(np.int64), z[case + "_answer"])
+
+
 @pytest.mark.parametrize("pbc", [0, 7])
 def test_double_vdw_search_vs_oracle(mb, pbc):
     """distance_search_double_vdw[_pbc] (distance_search.rs:767-879) through the pymolar-style
