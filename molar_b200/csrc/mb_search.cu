@@ -292,20 +292,68 @@ static int exclusive_scan_u32(Ctx* c, const unsigned* in, int n, unsigned* out) 
 // pair emission: per-warp staging in shared memory, flushed with ONE global atomic per ~1k pairs
 // and fully coalesced 8-byte stores.
 // ---------------------------------------------------------------------------------------------
+// explicit shared-window accesses (32-bit addresses): generic pointers to shared memory cost the
+// compiler a window-base computation at every use site
+__device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void sts64(unsigned addr, unsigned a, unsigned b) {
+    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
+}
+__device__ __forceinline__ void sts32f(unsigned addr, float a) {
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(a) : "memory");
+}
+__device__ __forceinline__ uint2 lds64(unsigned addr) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned lds32(unsigned addr) {
+    unsigned v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ float lds32f(unsigned addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+    return v;
+}
+
+// stage_sa / staged_sa: shared-window addresses of this warp's pair / distance staging buffers
 template <bool DIST>
-__device__ __forceinline__ void warp_flush(uint2* stage, float* stage_d, int& stage_n, const SearchParams& P,
+__device__ __forceinline__ void warp_flush(unsigned stage_sa, unsigned staged_sa, int& stage_n, const SearchParams& P,
                                            unsigned lane) {
     __syncwarp();
     if (stage_n == 0) return;
+    const int n = stage_n;
     unsigned long long base = 0;
-    if (lane == 0) base = atomicAdd(P.counter, (unsigned long long)stage_n);
+    if (lane == 0) base = atomicAdd(P.counter, (unsigned long long)n);
     base = __shfl_sync(0xffffffffu, base, 0);
-    if (base + (unsigned long long)stage_n <= P.pair_cap) {
-        uint2* __restrict__ dst = P.pairs + base;
-        for (int i = lane; i < stage_n; i += 32) dst[i] = stage[i];
+    if (base + (unsigned long long)n <= P.pair_cap) {
+        // lane-strided copy, 4 elements per lane per trip, immediate offsets
+        uint2* d = P.pairs + base + lane;
+        unsigned sa = stage_sa + lane * 8u;
+        int i = (int)lane;
+        for (; i + 96 < n; i += 128) {
+            const uint2 v0 = lds64(sa), v1 = lds64(sa + 256u), v2 = lds64(sa + 512u), v3 = lds64(sa + 768u);
+            d[0] = v0;
+            d[32] = v1;
+            d[64] = v2;
+            d[96] = v3;
+            d += 128;
+            sa += 1024u;
+        }
+        for (; i < n; i += 32) {
+            *d = lds64(sa);
+            d += 32;
+            sa += 256u;
+        }
         if (DIST) {
-            float* __restrict__ dd = P.dists + base;
-            for (int i = lane; i < stage_n; i += 32) dd[i] = stage_d[i];
+            float* dd = P.dists + base + lane;
+            unsigned sd = staged_sa + lane * 4u;
+            for (int k = (int)lane; k < n; k += 32) {
+                *dd = lds32f(sd);
+                dd += 32;
+                sd += 128u;
+            }
         }
     }
     __syncwarp();
@@ -479,6 +527,8 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32, 4) search_cells_kernel(cons
                                      wid * STAGE_CAP
                                : nullptr;
     const float4* __restrict__ home = ws.home;
+    const unsigned home_sa = smem_addr(ws.home);
+    const unsigned stage_sa = stage ? smem_addr(stage) : 0u, staged_sa = stage_d ? smem_addr(stage_d) : 0u;
     int stage_n = 0;
     unsigned long long count = 0;
     const GridSpec& g = P.g;
@@ -723,35 +773,38 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32, 4) search_cells_kernel(cons
                             base1 = grp ? -q1 : 0;
                             need = hh ? (grp ? t1 - q1 : q1) : (grp ? t0 - q0 : q0);
                         }
-                        if (stage_n + need > STAGE_CAP) warp_flush<MODE == 1>(stage, stage_d, stage_n, P, lane);
+                        if (stage_n + need > STAGE_CAP) warp_flush<MODE == 1>(stage_sa, staged_sa, stage_n, P, lane);
                         unsigned e0 = use0 ? m0 : 0u;
                         unsigned e1 = use1 ? m1 : 0u;
-                        uint2* sp0 = stage + (stage_n + base0 + i0 - c0n);
-                        uint2* sp1 = stage + (stage_n + base1 + i1 - c1n);
-                        float* dp0 = MODE == 1 ? stage_d + (sp0 - stage) : nullptr;
-                        float* dp1 = MODE == 1 ? stage_d + (sp1 - stage) : nullptr;
+                        unsigned sp0 = stage_sa + 8u * (unsigned)(stage_n + base0 + i0 - c0n);
+                        unsigned sp1 = stage_sa + 8u * (unsigned)(stage_n + base1 + i1 - c1n);
+                        unsigned dp0 = staged_sa + 4u * (unsigned)(stage_n + base0 + i0 - c0n);
+                        unsigned dp1 = staged_sa + 4u * (unsigned)(stage_n + base1 + i1 - c1n);
                         const unsigned id0 = __float_as_uint(n0.w), id1 = __float_as_uint(n1.w);
-                        const unsigned* hid = reinterpret_cast<const unsigned*>(home) + 3;  // .w of home[j]
                         while (e0) {
                             const int j = bfind32(e0);
                             e0 ^= 1u << j;
-                            *sp0++ = make_uint2(hid[4 * j], id0);
+                            sts64(sp0, lds32(home_sa + 16u * (unsigned)j + 12u), id0);
+                            sp0 += 8u;
                             if (MODE == 1) {
                                 const float4 h = home[j];
                                 float d2 = (f0 & 7u) ? d2_pbc_call(P.g.box, h.x, h.y, h.z, n0.x, n0.y, n0.z, f0 & 7u)
                                                      : d2_direct(h.x, h.y, h.z, n0.x, n0.y, n0.z);
-                                *dp0++ = __fsqrt_rn(d2);
+                                sts32f(dp0, __fsqrt_rn(d2));
+                                dp0 += 4u;
                             }
                         }
                         while (e1) {
                             const int j = bfind32(e1);
                             e1 ^= 1u << j;
-                            *sp1++ = make_uint2(hid[4 * j], id1);
+                            sts64(sp1, lds32(home_sa + 16u * (unsigned)j + 12u), id1);
+                            sp1 += 8u;
                             if (MODE == 1) {
                                 const float4 h = home[j];
                                 float d2 = (f1 & 7u) ? d2_pbc_call(P.g.box, h.x, h.y, h.z, n1.x, n1.y, n1.z, f1 & 7u)
                                                      : d2_direct(h.x, h.y, h.z, n1.x, n1.y, n1.z);
-                                *dp1++ = __fsqrt_rn(d2);
+                                sts32f(dp1, __fsqrt_rn(d2));
+                                dp1 += 4u;
                             }
                         }
                         stage_n += need;
@@ -770,7 +823,7 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32, 4) search_cells_kernel(cons
         for (int o = 16; o > 0; o >>= 1) count += __shfl_xor_sync(0xffffffffu, count, o);
         if (lane == 0 && count) atomicAdd(P.counter, count);
     } else if (MODE != 3) {
-        warp_flush<MODE == 1>(stage, stage_d, stage_n, P, lane);
+        warp_flush<MODE == 1>(stage_sa, staged_sa, stage_n, P, lane);
     }
 }
 
