@@ -1,0 +1,29 @@
+"""Small-config run of every kernel family for compute-sanitizer (memcheck / racecheck)."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import molar_b200 as mb
+from molar_b200.api import within
+from oracle import oracle_py as orc
+
+TRIC = np.array([[21.5, -2.7, -2.7], [0.0, 21.5, -2.7], [0.0, 0.0, 21.5]], np.float32)
+M = (TRIC * np.float32(0.25)).astype(np.float32)
+n = 9000
+xyz = orc.synth_frame(1, 0, n, M, stray_permille=10)
+m = orc.synth_masses(1, n)
+s = mb.System(xyz, masses=m, box=M, vdw=(0.1 + 0.1 * m / 16).astype(np.float32))
+p, d = mb.distance_search(1.2, s(), dims=[True] * 3)                      # cell kernel, pairs + dist
+ids1 = np.arange(0, n, 2, dtype=np.uint64); ids2 = np.arange(1, n, 3, dtype=np.uint64)
+s.set_option("two_set_cells_min", 0)
+p2, d2 = mb.distance_search(1.0, s(ids1), s(ids2), dims=[True] * 3)       # two-set cell kernel
+w = within(0.7, s(), s(np.arange(50, 90, dtype=np.uint64)), dims=7)       # within flags
+s.set_option("two_set_cells_min", 1e30)
+p3, d3 = mb.distance_search(1.0, s(ids1), s(ids2))                        # all-pairs kernel
+p4, d4 = mb.distance_search("vdw", s(ids1), s(ids2), dims=[True] * 3)     # vdW
+com, rg = s().com(), s().gyration()
+ref = mb.System(orc.synth_frame(1, 1, n, M), masses=m)
+tr = mb.fit_transform(s(), ref()); s().apply_transform(tr); r = mb.rmsd(s(), ref()); rw = mb.rmsd_mw(s(), ref())
+t = mb.Trajectory(); t.synth(1, 0, 4, 8000, M, mass_seed=1)
+c = t.search(1.2); c2 = t.search(1.2, count_only=True); rows = t.pipeline(1.2); rr = t.fit(0)
+t.set_option("fused_fit", 1); rr2 = t.fit(0)
+print("ok", len(p), len(p2), len(w), len(p3), len(p4), c.tolist(), c2.tolist(), float(r))
