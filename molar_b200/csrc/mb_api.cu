@@ -252,6 +252,7 @@ int mb_set_option(MbCtx* h, const char* key, double value) {
     else if (!strcmp(key, "with_dist")) c.opt_with_dist = (int)value;
     else if (!strcmp(key, "exact_pbc")) c.opt_exact_pbc = (int)value;
     else if (!strcmp(key, "fused_fit")) c.opt_fused_fit = (int)value;
+    else if (!strcmp(key, "lane_kernel")) c.opt_lane_kernel = (int)value;
     else if (!strcmp(key, "batch_streams")) c.opt_batch_streams = (int)value;
     else if (!strcmp(key, "two_set_cells_min")) c.opt_two_set_cells_min = value;
     else if (!strcmp(key, "profile")) {

@@ -142,6 +142,7 @@ struct Ctx {
     int opt_fused_fit = 0;  // 1: batch_fit uses the persistent TMA-staged kernel (slower than the two-kernel path so far)
     int opt_exact_pbc = 0;    // 1: wrapped cell pairs always use the exact PeriodicBox path (no filter)
     int opt_profile = 0;      // record CUDA events around every search-kernel launch
+    int opt_lane_kernel = 0;  // 1: search_lanes_kernel (home atom per lane, measured slower); 0: search_cells_kernel (hit masks)
     std::vector<cudaEvent_t> prof_events;  // begin/end pairs not yet harvested
     double prof_search_ms = 0.0;
     uint64_t prof_search_launches = 0;

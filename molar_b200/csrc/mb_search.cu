@@ -71,6 +71,7 @@ struct SearchParams {
     float* dists;
     unsigned long long pair_cap;
     unsigned long long* counter;  // [0] pairs found, [1] work counter (as u64)
+    unsigned long long n_sortedB;  // atoms in the candidate set
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -827,6 +828,8 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32, 4) search_cells_kernel(cons
     }
 }
 
+#include "mb_search_lanes.cuh"
+
 // ---------------------------------------------------------------------------------------------
 // general all-pairs kernel: any grid (degenerate dims, partial PBC), two sets, `within`.
 // Exact for every case the reference handles, O(n1*n2): used for small systems and as the
@@ -1152,6 +1155,7 @@ struct Plan {
     GridSpec g;
     bool use_cells;
     bool full_shell;  // two-set search: rows cover both half-spaces and the home row entirely
+    bool lane_tiles;  // tile size chosen for search_lanes_kernel (one home atom per lane)
     int fast_pbc;
     float rc2_lo, rc2_hi;
     int nrows;
@@ -1165,6 +1169,7 @@ struct Plan {
 static void plan_cells(const Ctx* c, Plan& pl, float cutoff, size_t n) {
     GridSpec& g = pl.g;
     pl.use_cells = false;
+    pl.lane_tiles = c->opt_lane_kernel != 0;
     for (int d = 0; d < 3; ++d) {
         g.k[d] = 1;
         g.kmagic[d] = 0;
@@ -1222,11 +1227,47 @@ static void plan_cells(const Ctx* c, Plan& pl, float cutoff, size_t n) {
             --k[dmax];
         }
     }
+    int hx_auto = 3;  // x slices per home tile (swept on B200)
+    if (pl.lane_tiles && c->opt_subdiv <= 0) {
+        // search_lanes_kernel: one home atom per lane, so a tile should hold close to (but rarely more
+        // than) 32 atoms.  Pick the subdivision that minimises the modelled cost per pair:
+        //   cost(tile) = batches * candidates * c_slot + c_tile,   pairs(tile) ~ mean population m
+        // with candidates = rho/2 * volume of the tile dilated by the cutoff, batches = E[ceil(X/32)],
+        // X ~ Poisson(m) (normal tail), c_slot = 32 lanes * 0.32 instructions, c_tile = 1500 instructions.
+        const double rho = pl.volume > 0 ? (double)n / pl.volume : 0.0;
+        double best = -1.0;
+        int kb[3] = {k[0], k[1], k[2]};
+        for (int k0 = 1; k0 <= 8; ++k0)
+            for (int k1 = 1; k1 <= 8; ++k1)
+                for (int k2 = 1; k2 <= 8; ++k2) {
+                    const double t0 = tref[0] / k0, t1 = tref[1] / k1, t2 = tref[2] / k2;
+                    const double m = (double)n / ((double)pl.ncells * k0 * k1 * k2);
+                    if (m < 2.0 && !(k0 == 1 && k1 == 1 && k2 == 1)) continue;
+                    double batches = 1.0;
+                    for (int j = 1; j < 64; ++j) {
+                        const double pj = 0.5 * std::erfc((32.0 * j + 0.5 - m) / std::sqrt(2.0 * std::max(m, 1e-9)));
+                        if (pj < 1e-9) break;
+                        batches += pj;
+                    }
+                    const double V = t0 * t1 * t2 + 2.0 * rc * (t0 * t1 + t1 * t2 + t0 * t2) +
+                                     3.14159265 * rc * rc * (t0 + t1 + t2) + 4.18879 * rc * rc * rc;
+                    const double cost = batches * (0.5 * rho * V) * 32.0 * 0.32 + 1500.0;
+                    const double score = m / cost;
+                    if (score > best) {
+                        best = score;
+                        kb[0] = k0;
+                        kb[1] = k1;
+                        kb[2] = k2;
+                    }
+                }
+        for (int d = 0; d < 3; ++d) k[d] = kb[d];
+        hx_auto = std::max(1, std::min(8, (int)std::floor(tref[0] / k[0] / (0.16 * rc) + 0.5)));
+    }
     // optional per-dimension overrides and the x slicing of the home tile
     if (c->opt_subdiv_xyz[0] > 0) k[0] = std::min(c->opt_subdiv_xyz[0], 8);
     if (c->opt_subdiv_xyz[1] > 0) k[1] = std::min(c->opt_subdiv_xyz[1], 8);
     if (c->opt_subdiv_xyz[2] > 0) k[2] = std::min(c->opt_subdiv_xyz[2], 8);
-    int hx = c->opt_slice_x > 0 ? std::min(c->opt_slice_x, 8) : 3;  // x slices per home tile (swept on B200)
+    int hx = c->opt_slice_x > 0 ? std::min(c->opt_slice_x, 8) : hx_auto;
     for (int attempt = 0; attempt < 16; ++attempt) {
         // fine-cell lattice: tiles of k[] per reference cell, each tile sliced hx times along x
         const int kf[3] = {k[0] * hx, k[1], k[2]};
@@ -1351,7 +1392,7 @@ struct PlanKey {
     unsigned pbc;
     size_t n;
     float m[9];
-    int subdiv, brute, exact_pbc, sx, sy, sz, slice, full;
+    int subdiv, brute, exact_pbc, sx, sy, sz, slice, full, lane;
     double apc;
 };
 struct PlanCache {
@@ -1439,6 +1480,7 @@ static int get_plan_pbc(Ctx* c, float cutoff, uint8_t pbc, size_t n, Plan& out, 
     k.sz = c->opt_subdiv_xyz[2];
     k.slice = c->opt_slice_x;
     k.full = full_shell ? 1 : 0;
+    k.lane = c->opt_lane_kernel;
     k.apc = c->opt_atoms_per_cell;
     PlanCache* pc = static_cast<PlanCache*>(c->plan_cache);
     if (!pc) {
@@ -1505,14 +1547,29 @@ static int bin_set(Ctx* c, const float* xyz, const unsigned long long* d_ids, si
     return MB_OK;
 }
 
+static bool lanes_enabled(const Ctx* c, int mode, const SearchParams& P) {
+    if (!c->opt_lane_kernel) return false;
+    if (mode == 1 && P.n_sortedB >= (1ull << 28)) return false;
+    return true;
+}
+
 template <int MODE>
 static int launch_search_cells(Ctx* c, const SearchParams& P) {
+    // search_lanes_kernel (one home atom per lane) unless switched off; its distance entries hold a
+    // 28-bit sorted index, so very large selections keep the mask kernel when distances are wanted
+    const bool use_lanes = lanes_enabled(c, MODE, P);
     size_t smem = SEARCH_WARPS * sizeof(WarpShared);
     if (MODE == 0 || MODE == 1) smem += SEARCH_WARPS * STAGE_CAP * sizeof(uint2);
     if (MODE == 1) smem += SEARCH_WARPS * STAGE_CAP * sizeof(float);
-    MB_CUDA(cudaFuncSetAttribute(search_cells_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 1;
-    MB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, search_cells_kernel<MODE>, SEARCH_WARPS * 32, smem));
+    if (use_lanes) {
+        smem = LANE_WARPS * sizeof(LaneShared);
+        MB_CUDA(cudaFuncSetAttribute(search_lanes_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        MB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, search_lanes_kernel<MODE>, LANE_WARPS * 32, smem));
+    } else {
+        MB_CUDA(cudaFuncSetAttribute(search_cells_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        MB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, search_cells_kernel<MODE>, SEARCH_WARPS * 32, smem));
+    }
     if (per_sm < 1) per_sm = 1;
     int blocks = c->sm_count * per_sm;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -1521,7 +1578,11 @@ static int launch_search_cells(Ctx* c, const SearchParams& P) {
         MB_CUDA(cudaEventCreate(&e1));
         MB_CUDA(cudaEventRecord(e0, c->stream));
     }
-    search_cells_kernel<MODE><<<blocks, SEARCH_WARPS * 32, smem, c->stream>>>(P);
+    if (use_lanes) {
+        search_lanes_kernel<MODE><<<blocks, LANE_WARPS * 32, smem, c->stream>>>(P);
+    } else {
+        search_cells_kernel<MODE><<<blocks, SEARCH_WARPS * 32, smem, c->stream>>>(P);
+    }
     c->launches++;
     if (c->opt_profile) {
         MB_CUDA(cudaEventRecord(e1, c->stream));
@@ -1566,6 +1627,7 @@ int enqueue_cells_search(Ctx* c, const float* xyz, const unsigned long long* d_i
     P.dists = c->dists.as<float>();
     P.pair_cap = c->pair_cap;
     P.counter = d_counter;
+    P.n_sortedB = n;
     if (mode == 2) return launch_search_cells<2>(c, P);
     if (mode == 1) return launch_search_cells<1>(c, P);
     return launch_search_cells<0>(c, P);
@@ -1616,6 +1678,7 @@ static int enqueue_cells_search2(Ctx* c, const float* xyz1, const unsigned long 
     P.dists = c->dists.as<float>();
     P.pair_cap = c->pair_cap;
     P.counter = d_counter;
+    P.n_sortedB = n2;
     if (kmode == 3) return launch_search_cells<3>(c, P);
     if (kmode == 1) return launch_search_cells<1>(c, P);
     return launch_search_cells<0>(c, P);
