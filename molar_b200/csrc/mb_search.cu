@@ -318,10 +318,13 @@ __device__ __forceinline__ float lds32f(unsigned addr) {
     return v;
 }
 
-// stage_sa / staged_sa: shared-window addresses of this warp's pair / distance staging buffers
+// stage_sa / staged_sa: shared-window addresses of this warp's pair / distance staging buffers.
+// A staged entry is (j, candidate id) with j the slot of the home atom in ws.home: the home id is looked
+// up here, 32 pairs per instruction, instead of once per pair in the expansion loop — so the buffer must
+// be flushed before the home batch changes.  Fully unrolled, predicated on the entry count.
 template <bool DIST>
-__device__ __forceinline__ void warp_flush(unsigned stage_sa, unsigned staged_sa, int& stage_n, const SearchParams& P,
-                                           unsigned lane) {
+__device__ __forceinline__ void warp_flush(unsigned stage_sa, unsigned staged_sa, unsigned home_sa, int& stage_n,
+                                           const SearchParams& P, unsigned lane) {
     __syncwarp();
     if (stage_n == 0) return;
     const int n = stage_n;
@@ -329,32 +332,24 @@ __device__ __forceinline__ void warp_flush(unsigned stage_sa, unsigned staged_sa
     if (lane == 0) base = atomicAdd(P.counter, (unsigned long long)n);
     base = __shfl_sync(0xffffffffu, base, 0);
     if (base + (unsigned long long)n <= P.pair_cap) {
-        // lane-strided copy, 4 elements per lane per trip, immediate offsets
         uint2* d = P.pairs + base + lane;
         unsigned sa = stage_sa + lane * 8u;
-        int i = (int)lane;
-        for (; i + 96 < n; i += 128) {
-            const uint2 v0 = lds64(sa), v1 = lds64(sa + 256u), v2 = lds64(sa + 512u), v3 = lds64(sa + 768u);
-            d[0] = v0;
-            d[32] = v1;
-            d[64] = v2;
-            d[96] = v3;
-            d += 128;
-            sa += 1024u;
-        }
-        for (; i < n; i += 32) {
-            *d = lds64(sa);
-            d += 32;
-            sa += 256u;
+        int r = n - (int)lane;  // entry q*32 + lane exists iff r > q*32
+        asm volatile("" : "+r"(sa), "+r"(r));  // keep both in registers (ptxas otherwise re-derives them from %tid per chunk)
+#pragma unroll
+        for (int q = 0; q < STAGE_CAP / 32; ++q) {
+            if (r > q * 32) {
+                uint2 v = lds64(sa + (unsigned)q * 256u);
+                v.x = lds32(home_sa + 16u * v.x + 12u);
+                d[q * 32] = v;
+            }
         }
         if (DIST) {
             float* dd = P.dists + base + lane;
-            unsigned sd = staged_sa + lane * 4u;
-            for (int k = (int)lane; k < n; k += 32) {
-                *dd = lds32f(sd);
-                dd += 32;
-                sd += 128u;
-            }
+            const unsigned sd = staged_sa + lane * 4u;
+#pragma unroll
+            for (int q = 0; q < STAGE_CAP / 32; ++q)
+                if (r > q * 32) dd[q * 32] = lds32f(sd + (unsigned)q * 128u);
         }
     }
     __syncwarp();
@@ -774,7 +769,7 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32, 4) search_cells_kernel(cons
                             base1 = grp ? -q1 : 0;
                             need = hh ? (grp ? t1 - q1 : q1) : (grp ? t0 - q0 : q0);
                         }
-                        if (stage_n + need > STAGE_CAP) warp_flush<MODE == 1>(stage_sa, staged_sa, stage_n, P, lane);
+                        if (stage_n + need > STAGE_CAP) warp_flush<MODE == 1>(stage_sa, staged_sa, home_sa, stage_n, P, lane);
                         unsigned e0 = use0 ? m0 : 0u;
                         unsigned e1 = use1 ? m1 : 0u;
                         unsigned sp0 = stage_sa + 8u * (unsigned)(stage_n + base0 + i0 - c0n);
@@ -785,7 +780,7 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32, 4) search_cells_kernel(cons
                         while (e0) {
                             const int j = bfind32(e0);
                             e0 ^= 1u << j;
-                            sts64(sp0, lds32(home_sa + 16u * (unsigned)j + 12u), id0);
+                            sts64(sp0, (unsigned)j, id0);
                             sp0 += 8u;
                             if (MODE == 1) {
                                 const float4 h = home[j];
@@ -798,7 +793,7 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32, 4) search_cells_kernel(cons
                         while (e1) {
                             const int j = bfind32(e1);
                             e1 ^= 1u << j;
-                            sts64(sp1, lds32(home_sa + 16u * (unsigned)j + 12u), id1);
+                            sts64(sp1, (unsigned)j, id1);
                             sp1 += 8u;
                             if (MODE == 1) {
                                 const float4 h = home[j];
@@ -815,6 +810,8 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32, 4) search_cells_kernel(cons
                     hit_any = __reduce_or_sync(0xffffffffu, hit_any);
                     if (lane < (unsigned)nh && ((hit_any >> lane) & 1u)) P.flags[__float_as_uint(home[lane].w)] = 1;
                 }
+                // staged entries name home atoms by their slot in ws.home: write them out before it changes
+                if (MODE == 0 || MODE == 1) warp_flush<MODE == 1>(stage_sa, staged_sa, home_sa, stage_n, P, lane);
             }
             first = false;
         } while (row0 < P.nrows);
@@ -823,8 +820,6 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32, 4) search_cells_kernel(cons
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) count += __shfl_xor_sync(0xffffffffu, count, o);
         if (lane == 0 && count) atomicAdd(P.counter, count);
-    } else if (MODE != 3) {
-        warp_flush<MODE == 1>(stage_sa, staged_sa, stage_n, P, lane);
     }
 }
 
