@@ -18,6 +18,11 @@
  *   mb_rmsd               rmsd / rmsd_mw                                  measure.rs:485-504,538-558
  *   mb_fit_transform      fit_transform / fit_transform_at_origin         measure.rs:507-535,613-643
  *   mb_apply_transform    Modify::apply_transform                         modify.rs:32-36
+ *   mb_center_of_geometry Measure::center_of_geometry                     measure.rs:37-45
+ *   mb_center_pbc         center_of_{mass,geometry}_pbc[_dims]            measure.rs:142-214
+ *   mb_gyration_pbc       Measure::gyration_pbc                           measure.rs:216-226
+ *   mb_inertia            Measure::inertia[_pbc] + do_inertia             measure.rs:88-98,228-238,573-610
+ *   mb_principal_transform  Measure::principal_transform[_pbc]            measure.rs:100-108,240-252,645-649
  *   mb_batch_*            the per-frame loop AnalysisTask::run drives     analysis_task.rs:113-280
  *
  * Data conventions (identical to the Rust side, so a binding passes its buffers as they are):
@@ -131,6 +136,21 @@ int mb_fit_transform(MbCtx* ctx, const uint64_t* ids1, size_t n1, const uint64_t
 /* in place on the current frame (device copy; fetch with mb_get_frame) */
 int mb_apply_transform(MbCtx* ctx, const uint64_t* ids, size_t n, const double R9_colmajor[9],
                        const double t3[3]);
+
+/* ---- periodic variants, inertia tensor, principal axes ----------------------------------- */
+int mb_center_of_geometry(MbCtx* ctx, const uint64_t* ids, size_t n, double out3[3]);
+/* center_of_mass_pbc[_dims] (mass_weighted != 0) / center_of_geometry_pbc[_dims]: every atom is replaced by
+   its closest image next to the FIRST atom of the selection (pbc_dims: which dimensions wrap; 7 = the
+   plain _pbc variants).  As in the reference, the first atom enters the mass-weighted numerator with
+   weight one.  MB_ERR_NO_PBC without a box. */
+int mb_center_pbc(MbCtx* ctx, const uint64_t* ids, size_t n, int mass_weighted, uint8_t pbc_dims, double out3[3]);
+int mb_gyration_pbc(MbCtx* ctx, const uint64_t* ids, size_t n, double* out);
+/* moments ascending; axes column-major, columns = principal axes (col2 = col0 x col1).  An axis is defined
+   up to its sign: col0 and col1 are returned with their largest component positive.  pbc != 0: distances to
+   the periodic centre of mass are minimum-image vectors (inertia_pbc). */
+int mb_inertia(MbCtx* ctx, const uint64_t* ids, size_t n, int pbc, double moments3[3], double axes9_colmajor[9]);
+/* p' = R p + t rotates the selection about its centre of mass onto its principal axes */
+int mb_principal_transform(MbCtx* ctx, const uint64_t* ids, size_t n, int pbc, double R9_colmajor[9], double t3[3]);
 
 /* ---- batched, device-resident trajectory (what the benchmark drives) -------------------- */
 /* Allocate n_frames x n_atoms x 3 f32 on the device and fill it with the synthetic generator

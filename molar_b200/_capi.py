@@ -44,6 +44,11 @@ SIGNATURES = {
     "mb_rmsd": (C.c_int, [C.c_void_p, u64p, C.c_size_t, u64p, C.c_size_t, C.c_int, C.c_int, f64p]),
     "mb_fit_transform": (C.c_int, [C.c_void_p, u64p, C.c_size_t, u64p, C.c_size_t, C.c_int, C.c_int, f64p, f64p]),
     "mb_apply_transform": (C.c_int, [C.c_void_p, u64p, C.c_size_t, f64p, f64p]),
+    "mb_center_of_geometry": (C.c_int, [C.c_void_p, u64p, C.c_size_t, f64p]),
+    "mb_center_pbc": (C.c_int, [C.c_void_p, u64p, C.c_size_t, C.c_int, C.c_uint8, f64p]),
+    "mb_gyration_pbc": (C.c_int, [C.c_void_p, u64p, C.c_size_t, f64p]),
+    "mb_inertia": (C.c_int, [C.c_void_p, u64p, C.c_size_t, C.c_int, f64p, f64p]),
+    "mb_principal_transform": (C.c_int, [C.c_void_p, u64p, C.c_size_t, C.c_int, f64p, f64p]),
     "mb_batch_synth": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_size_t, C.c_size_t, f32p, C.c_int]),
     "mb_batch_upload": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, f32p]),
     "mb_batch_synth_masses": (C.c_int, [C.c_void_p, C.c_uint64, C.c_size_t]),

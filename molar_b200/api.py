@@ -139,18 +139,64 @@ class Sel:
         return np.arange(self._n, dtype=np.uint64) if self.index is None else self.index.copy()
 
     def com(self, dims=None):
-        if _pbc_bits(dims):
-            raise NotImplementedError("periodic centre of mass is outside the accelerated path")
+        """Centre of mass; with periodic `dims` every atom is taken at its closest image next to the first
+        atom (center_of_mass_pbc_dims, molar_python/src/selection.rs:816-829)."""
         out = np.zeros(3, np.float64)
         p, n = self._ids()
-        check(self.sys._lib.mb_center_of_mass(self.sys._h, p, n, out.ctypes.data_as(f64p)))
+        bits = _pbc_bits(dims)
+        if bits:
+            check(self.sys._lib.mb_center_pbc(self.sys._h, p, n, 1, bits, out.ctypes.data_as(f64p)))
+        else:
+            check(self.sys._lib.mb_center_of_mass(self.sys._h, p, n, out.ctypes.data_as(f64p)))
         return out
 
-    def gyration(self):
+    def cog(self, dims=None):
+        """Centre of geometry, optionally periodic (selection.rs:845-858)."""
+        out = np.zeros(3, np.float64)
+        p, n = self._ids()
+        bits = _pbc_bits(dims)
+        if bits:
+            check(self.sys._lib.mb_center_pbc(self.sys._h, p, n, 0, bits, out.ctypes.data_as(f64p)))
+        else:
+            check(self.sys._lib.mb_center_of_geometry(self.sys._h, p, n, out.ctypes.data_as(f64p)))
+        return out
+
+    def gyration(self, pbc=False):
+        """Radius of gyration (selection.rs:935-941)."""
         out = C.c_double(0.0)
         p, n = self._ids()
-        check(self.sys._lib.mb_gyration(self.sys._h, p, n, C.byref(out)))
+        if pbc:
+            check(self.sys._lib.mb_gyration_pbc(self.sys._h, p, n, C.byref(out)))
+        else:
+            check(self.sys._lib.mb_gyration(self.sys._h, p, n, C.byref(out)))
         return out.value
+
+    def gyration_pbc(self):
+        return self.gyration(pbc=True)
+
+    def inertia(self, pbc=False):
+        """(moments[3] ascending, axes[3,3] with the principal axes as columns) (selection.rs:1068-1084)."""
+        mom = np.zeros(3, np.float64)
+        ax = np.zeros(9, np.float64)
+        p, n = self._ids()
+        check(self.sys._lib.mb_inertia(self.sys._h, p, n, 1 if pbc else 0, mom.ctypes.data_as(f64p),
+                                       ax.ctypes.data_as(f64p)))
+        return mom, ax.reshape(3, 3).T.copy()
+
+    def inertia_pbc(self):
+        return self.inertia(pbc=True)
+
+    def principal_transform(self, pbc=False):
+        """Rigid transform onto the principal axes (selection.rs:866-873)."""
+        R9 = np.zeros(9, np.float64)
+        t3 = np.zeros(3, np.float64)
+        p, n = self._ids()
+        check(self.sys._lib.mb_principal_transform(self.sys._h, p, n, 1 if pbc else 0, R9.ctypes.data_as(f64p),
+                                                   t3.ctypes.data_as(f64p)))
+        return IsometryTransform(R9.reshape(3, 3).T.copy(), t3)
+
+    def principal_transform_pbc(self):
+        return self.principal_transform(pbc=True)
 
     def apply_transform(self, tr):
         R9 = np.ascontiguousarray(tr.R.T.reshape(9), dtype=np.float64)

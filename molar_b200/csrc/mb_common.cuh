@@ -125,6 +125,7 @@ struct Ctx {
     DevBuf pairs, dists, flags, out_ids;
     DevBuf counters;        // small block of device counters / results
     DevBuf reduce_tmp;      // per-block partials
+    DevBuf pbc_tmp;         // ticket + results + partials of the periodic reductions (mb_measure_pbc.cu)
     SearchResult last;
     size_t pair_cap = 0;
     SearchSlot alt[2];        // alternate slots for batch_search (streams created lazily)

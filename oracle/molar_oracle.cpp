@@ -859,6 +859,162 @@ int gyration(const float* xyz, const float* masses, const uint64_t* ids, size_t 
     return 0;
 }
 
+// ---- periodic variants, inertia, principal axes ------------------------------------------------
+// TI: precision in which the per-atom image is chosen (the reference's Float), TA: accumulator.
+// (float,float) and (double,double) restate the two builds of the reference; (float,double) is the
+// f32 build's per-atom arithmetic with noise-free sums — the statement the CUDA path is checked against.
+template <class TI>
+inline BoxT<TI> box_as(const Boxf& b) {
+    M3<TI> m;
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) m.m[i][j] = (TI)b.matrix.m[i][j];
+    BoxT<TI> out;
+    box_from_matrix(m, out);
+    return out;
+}
+
+// center_of_mass_pbc[_dims] (measure.rs:172-214) / center_of_geometry_pbc[_dims] (:142-168); masses == NULL: geometry.
+// Keeps the reference's quirk: `let mut cm = p0.coords` — the first atom is not multiplied by its mass.
+template <class TI, class TA>
+int center_pbc(const float* xyz, const float* masses, const uint64_t* ids, size_t n, const Boxf& box, uint8_t dims,
+               V3<TA>& out) {
+    const BoxT<TI> b = box_as<TI>(box);
+    const V3<TI> p0 = load_pos<TI>(xyz, ids, 0);
+    V3<TA> cm = {{(TA)p0[0], (TA)p0[1], (TA)p0[2]}};
+    TA mass = masses ? load_mass<TA>(masses, ids, 0) : TA(1);
+    for (size_t k = 1; k < n; ++k) {
+        const V3<TI> c = load_pos<TI>(xyz, ids, k);
+        const V3<TI> im = add(p0, shortest_vector_dims(b, sub(c, p0), dims));  // closest_image_dims (periodic_box.rs:327-330)
+        const TA m = masses ? load_mass<TA>(masses, ids, k) : TA(1);
+        for (int d = 0; d < 3; ++d) cm[d] += (TA)im[d] * m;
+        mass += m;
+    }
+    if (masses && mass == TA(0)) return 1;
+    if (!masses) mass = (TA)n;
+    for (int d = 0; d < 3; ++d) out[d] = cm[d] / mass;
+    return 0;
+}
+
+// center_of_geometry (measure.rs:37-45)
+template <class T>
+void center_of_geometry(const float* xyz, const uint64_t* ids, size_t n, V3<T>& out) {
+    V3<T> cog = {{0, 0, 0}};
+    for (size_t k = 0; k < n; ++k) {
+        V3<T> c = load_pos<T>(xyz, ids, k);
+        for (int d = 0; d < 3; ++d) cog[d] += c[d];
+    }
+    for (int d = 0; d < 3; ++d) out[d] = cog[d] / (T)n;
+}
+
+// distances fed to do_gyration / do_inertia: pos - c, or shortest_vector(pos - c) for the _pbc variants;
+// c is a Pos, i.e. it is rounded to the reference's Float (TI) before use
+template <class TI, class TA, class F>
+void for_each_dist(const float* xyz, const float* masses, const uint64_t* ids, size_t n, const Boxf* box,
+                   const V3<TA>& centre, F&& f) {
+    const V3<TI> c = {{(TI)centre[0], (TI)centre[1], (TI)centre[2]}};
+    BoxT<TI> b;
+    if (box) b = box_as<TI>(*box);
+    for (size_t k = 0; k < n; ++k) {
+        V3<TI> d = sub(load_pos<TI>(xyz, ids, k), c);
+        if (box) d = shortest_vector_dims(b, d, PBC_FULL);
+        f(V3<TA>{{(TA)d[0], (TA)d[1], (TA)d[2]}}, load_mass<TA>(masses, ids, k));
+    }
+}
+
+// gyration_pbc (measure.rs:216-226)
+template <class TI, class TA>
+int gyration_pbc(const float* xyz, const float* masses, const uint64_t* ids, size_t n, const Boxf& box, TA& out) {
+    V3<TA> c;
+    int rc = center_pbc<TI, TA>(xyz, masses, ids, n, box, PBC_FULL, c);
+    if (rc) return rc;
+    TA sd = 0, sm = 0;
+    for_each_dist<TI, TA>(xyz, masses, ids, n, &box, c, [&](const V3<TA>& d, TA m) {
+        sd += norm_squared(d) * m;
+        sm += m;
+    });
+    out = std::sqrt(sd / sm);
+    return 0;
+}
+
+// cyclic Jacobi for a symmetric 3x3 (stands in for nalgebra::SymmetricEigen, measure.rs:590): eigenvalues
+// on the diagonal of A, eigenvectors in the columns of V
+template <class T>
+void sym_eigen3(T A[3][3], T V[3][3]) {
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) V[i][j] = i == j ? T(1) : T(0);
+    for (int sweep = 0; sweep < 64; ++sweep) {
+        T off = std::fabs(A[0][1]) + std::fabs(A[0][2]) + std::fabs(A[1][2]);
+        T diag = std::fabs(A[0][0]) + std::fabs(A[1][1]) + std::fabs(A[2][2]);
+        if (off == T(0) || off <= std::numeric_limits<T>::epsilon() * T(0.01) * diag) break;
+        for (int p = 0; p < 2; ++p)
+            for (int q = p + 1; q < 3; ++q) {
+                if (A[p][q] == T(0)) continue;
+                T theta = (A[q][q] - A[p][p]) / (T(2) * A[p][q]);
+                T t = (theta >= 0 ? T(1) : T(-1)) / (std::fabs(theta) + std::sqrt(theta * theta + T(1)));
+                T cs = T(1) / std::sqrt(t * t + T(1)), sn = t * cs;
+                for (int k = 0; k < 3; ++k) {
+                    T akp = A[k][p], akq = A[k][q];
+                    A[k][p] = cs * akp - sn * akq;
+                    A[k][q] = sn * akp + cs * akq;
+                }
+                for (int k = 0; k < 3; ++k) {
+                    T apk = A[p][k], aqk = A[q][k];
+                    A[p][k] = cs * apk - sn * aqk;
+                    A[q][k] = sn * apk + cs * aqk;
+                }
+                for (int k = 0; k < 3; ++k) {
+                    T vkp = V[k][p], vkq = V[k][q];
+                    V[k][p] = cs * vkp - sn * vkq;
+                    V[k][q] = sn * vkp + cs * vkq;
+                }
+            }
+    }
+}
+
+// inertia / inertia_pbc (measure.rs:88-98,228-238) + do_inertia (:573-610).  tensor9 row-major, moments ascending,
+// axes9 column-major with col2 = col0 x col1; the sign of col0/col1 is whatever the eigen-solver returns.
+template <class TI, class TA>
+int inertia(const float* xyz, const float* masses, const uint64_t* ids, size_t n, const Boxf* box, TA* tensor9,
+            TA* moments3, TA* axes9, TA* centre3) {
+    V3<TA> c;
+    int rc = box ? center_pbc<TI, TA>(xyz, masses, ids, n, *box, PBC_FULL, c) : center_of_mass<TA>(xyz, masses, ids, n, c);
+    if (rc) return rc;
+    TA tens[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+    for_each_dist<TI, TA>(xyz, masses, ids, n, box, c, [&](const V3<TA>& d, TA m) {
+        tens[0][0] += m * (d[1] * d[1] + d[2] * d[2]);
+        tens[1][1] += m * (d[0] * d[0] + d[2] * d[2]);
+        tens[2][2] += m * (d[0] * d[0] + d[1] * d[1]);
+        tens[0][1] -= m * d[0] * d[1];
+        tens[0][2] -= m * d[0] * d[2];
+        tens[1][2] -= m * d[1] * d[2];
+    });
+    tens[1][0] = tens[0][1];
+    tens[2][0] = tens[0][2];
+    tens[2][1] = tens[1][2];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) tensor9[3 * i + j] = tens[i][j];
+    TA V[3][3];
+    sym_eigen3(tens, V);
+    int ord[3] = {0, 1, 2};
+    std::sort(ord, ord + 3, [&](int a, int b) { return tens[a][a] < tens[b][b]; });
+    for (int j = 0; j < 3; ++j) moments3[j] = tens[ord[j]][ord[j]];
+    V3<TA> col0 = {{V[0][ord[0]], V[1][ord[0]], V[2][ord[0]]}}, col1 = {{V[0][ord[1]], V[1][ord[1]], V[2][ord[1]]}};
+    TA n0 = norm(col0), n1 = norm(col1);
+    for (int d = 0; d < 3; ++d) {
+        col0[d] /= n0;
+        col1[d] /= n1;
+    }
+    V3<TA> col2 = {{col0[1] * col1[2] - col0[2] * col1[1], col0[2] * col1[0] - col0[0] * col1[2],
+                    col0[0] * col1[1] - col0[1] * col1[0]}};
+    for (int d = 0; d < 3; ++d) {
+        axes9[d] = col0[d];
+        axes9[3 + d] = col1[d];
+        axes9[6 + d] = col2[d];
+        centre3[d] = c[d];
+    }
+    return 0;
+}
+
 // measure.rs:485-504
 template <class T>
 int rmsd(const float* xyz1, const uint64_t* ids1, size_t n1, const float* xyz2, const uint64_t* ids2,
@@ -1054,6 +1210,65 @@ int orc_center_of_mass_f64(const float* xyz, const float* masses, const uint64_t
     int rc = center_of_mass<double>(xyz, masses, ids, n, c);
     if (!rc) for (int d = 0; d < 3; ++d) out3[d] = c[d];
     return rc;
+}
+// prec: 0 = (f32 images, f32 sums), 1 = (f64, f64), 2 = (f32 images, f64 sums).  Outputs are doubles.
+int orc_center_pbc(const float* xyz, const float* masses, const uint64_t* ids, size_t n, const OrcBox* box,
+                   uint8_t dims, int prec, double* out3) {
+    int rc;
+    if (prec == 0) {
+        V3<float> c;
+        rc = center_pbc<float, float>(xyz, masses, ids, n, box->b, dims, c);
+        if (!rc) for (int d = 0; d < 3; ++d) out3[d] = c[d];
+    } else if (prec == 1) {
+        V3<double> c;
+        rc = center_pbc<double, double>(xyz, masses, ids, n, box->b, dims, c);
+        if (!rc) for (int d = 0; d < 3; ++d) out3[d] = c[d];
+    } else {
+        V3<double> c;
+        rc = center_pbc<float, double>(xyz, masses, ids, n, box->b, dims, c);
+        if (!rc) for (int d = 0; d < 3; ++d) out3[d] = c[d];
+    }
+    return rc;
+}
+void orc_center_of_geometry(const float* xyz, const uint64_t* ids, size_t n, int prec, double* out3) {
+    if (prec == 0) {
+        V3<float> c;
+        center_of_geometry<float>(xyz, ids, n, c);
+        for (int d = 0; d < 3; ++d) out3[d] = c[d];
+    } else {
+        V3<double> c;
+        center_of_geometry<double>(xyz, ids, n, c);
+        for (int d = 0; d < 3; ++d) out3[d] = c[d];
+    }
+}
+int orc_gyration_pbc(const float* xyz, const float* masses, const uint64_t* ids, size_t n, const OrcBox* box, int prec,
+                     double* out) {
+    int rc;
+    if (prec == 0) {
+        float r = 0;
+        rc = gyration_pbc<float, float>(xyz, masses, ids, n, box->b, r);
+        *out = r;
+    } else if (prec == 1) {
+        rc = gyration_pbc<double, double>(xyz, masses, ids, n, box->b, *out);
+    } else {
+        rc = gyration_pbc<float, double>(xyz, masses, ids, n, box->b, *out);
+    }
+    return rc;
+}
+// box == NULL: inertia; else inertia_pbc.  tensor9 row-major, axes9 column-major, centre3 = the centre used.
+int orc_inertia(const float* xyz, const float* masses, const uint64_t* ids, size_t n, const OrcBox* box, int prec,
+                double* tensor9, double* moments3, double* axes9, double* centre3) {
+    const Boxf* b = box ? &box->b : nullptr;
+    if (prec == 0) {
+        float t[9], m[3], a[9], c[3];
+        int rc = inertia<float, float>(xyz, masses, ids, n, b, t, m, a, c);
+        if (rc) return rc;
+        for (int i = 0; i < 9; ++i) { tensor9[i] = t[i]; axes9[i] = a[i]; }
+        for (int i = 0; i < 3; ++i) { moments3[i] = m[i]; centre3[i] = c[i]; }
+        return 0;
+    }
+    if (prec == 1) return inertia<double, double>(xyz, masses, ids, n, b, tensor9, moments3, axes9, centre3);
+    return inertia<float, double>(xyz, masses, ids, n, b, tensor9, moments3, axes9, centre3);
 }
 int orc_gyration_f32(const float* xyz, const float* masses, const uint64_t* ids, size_t n, float* out) {
     return gyration<float>(xyz, masses, ids, n, *out);

@@ -109,6 +109,21 @@ void orc_apply_transform_f32(float* xyz, const uint64_t* ids, size_t n, const fl
 void orc_apply_transform_f64(const float* xyz, const uint64_t* ids, size_t n, const double* R9,
                              const double* t3, double* out);
 
+/* ---- periodic variants, inertia (measure.rs:37-45,88-108,142-252,573-610) ----------------
+   prec: 0 = the default f32 build, 1 = the f64 build, 2 = f32 per-atom image arithmetic with f64 sums
+   (what the CUDA path is checked against bit-for-bit in its choice of images).  masses == NULL in
+   orc_center_pbc selects center_of_geometry_pbc[_dims].  PARITY UNPINNED by the reference (no test
+   exercises these); pinned against numpy in tests/test_oracle_measure_pbc.py. */
+int orc_center_pbc(const float* xyz, const float* masses, const uint64_t* ids, size_t n, const OrcBox* box,
+                   uint8_t dims, int prec, double* out3);
+void orc_center_of_geometry(const float* xyz, const uint64_t* ids, size_t n, int prec, double* out3);
+int orc_gyration_pbc(const float* xyz, const float* masses, const uint64_t* ids, size_t n, const OrcBox* box,
+                     int prec, double* out);
+/* box == NULL: inertia, else inertia_pbc.  tensor9 row-major; moments ascending; axes9 column-major
+   (col2 = col0 x col1; eigenvector signs are the solver's); centre3 = the centre of mass used. */
+int orc_inertia(const float* xyz, const float* masses, const uint64_t* ids, size_t n, const OrcBox* box, int prec,
+                double* tensor9, double* moments3, double* axes9, double* centre3);
+
 /* ---- synthetic frames — shared definition of the bench input ---- */
 /* pos = M * s, s_axis = float(splitmix64(seed ^ (frame<<32) ^ (atom*3+axis)) >> 40) * 2^-24,
    unfused, a4 order.  masses = 1 + 15*s'. stray_permille: that many per 1000 atoms are

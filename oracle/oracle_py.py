@@ -80,6 +80,11 @@ def lib():
                                                                C.c_size_t, C.c_int, fp, fp]
         L.orc_apply_transform_f32.argtypes = [_f32p, _u64p, C.c_size_t, _f32p, _f32p]
         L.orc_apply_transform_f64.argtypes = [_f32p, _u64p, C.c_size_t, _f64p, _f64p, _f64p]
+        L.orc_center_pbc.argtypes = [_f32p, _f32p, _u64p, C.c_size_t, C.c_void_p, C.c_uint8, C.c_int, _f64p]
+        L.orc_center_of_geometry.argtypes = [_f32p, _u64p, C.c_size_t, C.c_int, _f64p]
+        L.orc_center_of_geometry.restype = None
+        L.orc_gyration_pbc.argtypes = [_f32p, _f32p, _u64p, C.c_size_t, C.c_void_p, C.c_int, _f64p]
+        L.orc_inertia.argtypes = [_f32p, _f32p, _u64p, C.c_size_t, C.c_void_p, C.c_int, _f64p, _f64p, _f64p, _f64p]
         L.orc_synth_frame.argtypes = [C.c_uint64, C.c_uint64, C.c_size_t, _f32p, C.c_int, _f32p]
         L.orc_synth_masses.argtypes = [C.c_uint64, C.c_size_t, _f32p]
         _lib = L
@@ -308,6 +313,56 @@ def gyration(xyz, masses, ids=None, prec="f64"):
     out = np.zeros(1, np.float64 if prec == "f64" else np.float32)
     rc = _measure("gyration", prec)(xp, mp, ip, n, out.ctypes.data_as(_f64p if prec == "f64" else _f32p))
     return rc, float(out[0])
+
+
+_PREC = {"f32": 0, "f64": 1, "mixed": 2}
+
+
+def center_pbc(xyz, masses, box, dims=7, ids=None, prec="mixed"):
+    """center_of_mass_pbc[_dims] (masses given) / center_of_geometry_pbc[_dims] (masses None)."""
+    x, xp = _f32(xyz)
+    mp = None
+    if masses is not None:
+        m, mp = _f32(masses)
+    i, ip = _ids(ids)
+    n = len(i) if i is not None else x.size // 3
+    out = np.zeros(3, np.float64)
+    rc = lib().orc_center_pbc(xp, mp, ip, n, box.h, dims, _PREC[prec], out.ctypes.data_as(_f64p))
+    return rc, out
+
+
+def center_of_geometry(xyz, ids=None, prec="f64"):
+    x, xp = _f32(xyz)
+    i, ip = _ids(ids)
+    n = len(i) if i is not None else x.size // 3
+    out = np.zeros(3, np.float64)
+    lib().orc_center_of_geometry(xp, ip, n, _PREC[prec], out.ctypes.data_as(_f64p))
+    return out
+
+
+def gyration_pbc(xyz, masses, box, ids=None, prec="mixed"):
+    x, xp = _f32(xyz)
+    m, mp = _f32(masses)
+    i, ip = _ids(ids)
+    n = len(i) if i is not None else x.size // 3
+    out = np.zeros(1, np.float64)
+    rc = lib().orc_gyration_pbc(xp, mp, ip, n, box.h, _PREC[prec], out.ctypes.data_as(_f64p))
+    return rc, float(out[0])
+
+
+def inertia(xyz, masses, box=None, ids=None, prec="mixed"):
+    """returns rc, tensor[3,3], moments[3], axes[3,3] (columns = axes), centre[3]"""
+    x, xp = _f32(xyz)
+    m, mp = _f32(masses)
+    i, ip = _ids(ids)
+    n = len(i) if i is not None else x.size // 3
+    t = np.zeros(9, np.float64)
+    mom = np.zeros(3, np.float64)
+    ax = np.zeros(9, np.float64)
+    c = np.zeros(3, np.float64)
+    rc = lib().orc_inertia(xp, mp, ip, n, box.h if box is not None else None, _PREC[prec], t.ctypes.data_as(_f64p),
+                           mom.ctypes.data_as(_f64p), ax.ctypes.data_as(_f64p), c.ctypes.data_as(_f64p))
+    return rc, t.reshape(3, 3), mom, ax.reshape(3, 3).T.copy(), c
 
 
 def rmsd(xyz1, ids1, xyz2, ids2, prec="f64", masses1=None):
