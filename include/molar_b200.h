@@ -24,6 +24,8 @@
  *   mb_inertia            Measure::inertia[_pbc] + do_inertia             measure.rs:88-98,228-238,573-610
  *   mb_principal_transform  Measure::principal_transform[_pbc]            measure.rs:100-108,240-252,645-649
  *   mb_batch_*            the per-frame loop AnalysisTask::run drives     analysis_task.rs:113-280
+ *   mb_batch_load_traj    DcdFileHandler::read_state / XtcFileHandler::read_state (+ molly's XTC codec)
+ *                                                                         io/dcd_handler.rs:204-300,389-464; io/xtc_handler.rs:64-110
  *
  * Data conventions (identical to the Rust side, so a binding passes its buffers as they are):
  *   coordinates  Vec<Pos> = N x 3 f32, AoS, 12-byte stride                aliases.rs:23
@@ -162,6 +164,17 @@ int mb_batch_synth(MbCtx* ctx, uint64_t seed, uint64_t first_frame, size_t n_fra
 int mb_batch_upload(MbCtx* ctx, const float* xyz, size_t n_frames, size_t n_atoms,
                     const float* box9_colmajor);
 int mb_batch_synth_masses(MbCtx* ctx, uint64_t seed, size_t n_atoms);
+/* Trajectory ingest: decode frames [first_frame, first_frame + n_frames) of a DCD or XTC byte stream (the file
+   contents, or any prefix holding whole frames) ON THE DEVICE into the resident batch.  The box of the first
+   loaded frame becomes the batch box; per-frame boxes (9 floats, column-major, zeros = no box) and times are
+   written to the optional host arrays.  DCD: both endiannesses, CHARMM extra/4D blocks, fixed atoms;
+   coordinates are `x * 0.1` in f32 as the reference forms them.  XTC: magic 1995, precision as stored. */
+enum { MB_TRAJ_DCD = 0, MB_TRAJ_XTC = 1 };
+int mb_traj_probe(const void* bytes, size_t n_bytes, int format, size_t* n_frames, size_t* n_atoms);
+int mb_batch_load_traj(MbCtx* ctx, const void* bytes, size_t n_bytes, int format, size_t first_frame, size_t n_frames,
+                       float* boxes9_out, float* times_out);
+/* Copy frames [f0, f1) of the resident batch to the host (n_atoms x 3 f32 each). */
+int mb_batch_download(MbCtx* ctx, size_t f0, size_t f1, float* xyz_out);
 /* Make batch frame f the current frame (no copy). */
 int mb_batch_select(MbCtx* ctx, size_t frame);
 /* Neighbour search on every frame [f0, f1): per-frame pair count and checksum written to

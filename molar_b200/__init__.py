@@ -6,6 +6,6 @@ C ABI in include/molar_b200.h.  Importing the package does not need a GPU; calli
 """
 from . import _capi  # noqa: F401
 from .api import (System, Sel, PeriodicBox, IsometryTransform, Trajectory, distance_search, fit_transform,  # noqa: F401
-                  rmsd, rmsd_py, rmsd_mw, MolarB200Error)
+                  rmsd, rmsd_py, rmsd_mw, MolarB200Error, probe_trajectory, load_trajectory)
 
 __version__ = "0.1.0"

@@ -318,6 +318,21 @@ def fit_transform(sel1, sel2, at_origin=False):
     return IsometryTransform(R9.reshape(3, 3).T.copy(), t3)
 
 
+_TRAJ_FORMATS = {"dcd": 0, "xtc": 1}
+
+
+def probe_trajectory(data, fmt):
+    """(frames, atoms) of a DCD / XTC byte stream (headers only, on the host)."""
+    buf = np.frombuffer(data, dtype=np.uint8)
+    nf, na = C.c_size_t(0), C.c_size_t(0)
+    check(_capi.load().mb_traj_probe(buf.ctypes.data, buf.size, _TRAJ_FORMATS[fmt], C.byref(nf), C.byref(na)))
+    return nf.value, na.value
+
+
+def load_trajectory(data, fmt, first_frame=0, n_frames=None, device=0):
+    return Trajectory(device).load(data, fmt, first_frame, n_frames)
+
+
 class Trajectory:
     """Device-resident block of frames: the GPU analogue of the per-frame loop that
     AnalysisTask::run drives (analysis_task.rs:113-280)."""
@@ -364,6 +379,29 @@ class Trajectory:
             m = np.ascontiguousarray(masses, dtype=np.float32)
             check(self._lib.mb_set_masses(self._h, m.ctypes.data, m.shape[0]))
         self.n_frames, self.n_atoms = nf, na
+
+    def load(self, data, fmt, first_frame=0, n_frames=None):
+        """Decode frames of a DCD / XTC byte stream on the device into the resident batch
+        (FileHandler::read_state for every frame, io/dcd_handler.rs:389-464, io/xtc_handler.rs:64-110)."""
+        buf = np.frombuffer(data, dtype=np.uint8)
+        code = _TRAJ_FORMATS[fmt]
+        if n_frames is None:
+            n_frames = probe_trajectory(data, fmt)[0] - first_frame
+        boxes = np.zeros((n_frames, 9), np.float32)
+        times = np.zeros(n_frames, np.float32)
+        check(self._lib.mb_batch_load_traj(self._h, buf.ctypes.data, buf.size, code, first_frame, n_frames,
+                                           boxes.ctypes.data_as(f32p), times.ctypes.data_as(f32p)))
+        self.n_frames = n_frames
+        self.n_atoms = probe_trajectory(data, fmt)[1]
+        self.boxes = boxes.reshape(n_frames, 3, 3).transpose(0, 2, 1).copy()  # [f] = 3x3, columns = box vectors
+        self.times = times
+        return self
+
+    def frames(self, f0=0, f1=None):
+        f1 = self.n_frames if f1 is None else f1
+        out = np.empty((f1 - f0, self.n_atoms, 3), np.float32)
+        check(self._lib.mb_batch_download(self._h, f0, f1, out.ctypes.data))
+        return out
 
     def frame(self, f):
         check(self._lib.mb_batch_select(self._h, f))

@@ -156,6 +156,7 @@ struct Ctx {
     DevBuf batch_scalars;  // rows of doubles
     size_t batch_rows = 0, batch_row_doubles = 0;
     DevBuf batch_tmp, batch_ref, pipe_tmp;
+    DevBuf traj_raw, traj_aux;  // trajectory ingest: raw file bytes / decode tables (mb_traj.cu)
 
     // memoised search plan (owned by mb_search.cu)
     void* plan_cache = nullptr;
