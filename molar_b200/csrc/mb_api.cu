@@ -339,6 +339,10 @@ int mb_get_stat(MbCtx* h, const char* key, double* out) {
     else if (!strcmp(key, "search_kernel_launches")) *out = (double)c.prof_search_launches;
     else if (!strcmp(key, "pair_capacity")) *out = (double)c.pair_cap;
     else if (!strcmp(key, "sm_count")) *out = (double)c.sm_count;
+    else if (!strcmp(key, "traj_h2d_ms")) *out = c.traj_h2d_ms;        // last mb_batch_load_traj: raw bytes to the device
+    else if (!strcmp(key, "traj_decode_ms")) *out = c.traj_decode_ms;  // ... all decode kernels (CUDA events)
+    else if (!strcmp(key, "traj_scan_ms")) *out = c.traj_scan_ms;      // ... of which xtc_scan_kernel
+    else if (!strcmp(key, "traj_raw_bytes")) *out = c.traj_raw_bytes;
     else return fail(MB_ERR_ARG, "unknown stat '%s'", key);
     return MB_OK;
 }

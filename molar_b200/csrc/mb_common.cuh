@@ -157,6 +157,7 @@ struct Ctx {
     size_t batch_rows = 0, batch_row_doubles = 0;
     DevBuf batch_tmp, batch_ref, pipe_tmp;
     DevBuf traj_raw, traj_aux;  // trajectory ingest: raw file bytes / decode tables (mb_traj.cu)
+    double traj_h2d_ms = 0.0, traj_decode_ms = 0.0, traj_scan_ms = 0.0, traj_raw_bytes = 0.0;  // last load, CUDA events
 
     // memoised search plan (owned by mb_search.cu)
     void* plan_cache = nullptr;

@@ -563,6 +563,26 @@ static int xtc_parse(const uint8_t* b, size_t nb, std::vector<XtcHostFrame>& fra
 // (xtc_handler.rs:99), so the stored floats ARE the column-major matrix with columns = box vectors.
 static void xtc_box_colmajor(const float stored[9], float m9[9]) { memcpy(m9, stored, 9 * sizeof(float)); }
 
+// CUDA-event stopwatch on the context stream (mb_get_stat "traj_*")
+struct EvTimer {
+    cudaEvent_t a = nullptr, b = nullptr;
+    cudaStream_t st;
+    explicit EvTimer(cudaStream_t s) : st(s) {
+        cudaEventCreate(&a);
+        cudaEventCreate(&b);
+    }
+    ~EvTimer() {
+        if (a) cudaEventDestroy(a);
+        if (b) cudaEventDestroy(b);
+    }
+    void start() { cudaEventRecord(a, st); }
+    void stop() { cudaEventRecord(b, st); }
+    double ms() {  // after the stream has been synchronised
+        float t = 0.f;
+        return cudaEventElapsedTime(&t, a, b) == cudaSuccess ? (double)t : 0.0;
+    }
+};
+
 static int finish_batch(Ctx& c, size_t n_frames, size_t n_atoms, const float* box9_first) {
     if (box9_first) {
         if (host_box_from_colmajor(box9_first, &c.box) == MB_OK) c.has_box = true;
@@ -640,8 +660,12 @@ int mb_batch_load_traj(MbCtx* h, const void* bytes, size_t n_bytes, int format, 
         }
         const size_t start = dcd_frame_off(I, first_frame), end = dcd_frame_off(I, first_frame + n_frames);
         MB_TRY(c.traj_raw.reserve(end - start + 16));
-        MB_CUDA(cudaMemcpyAsync(c.traj_raw.p, b + start, end - start, cudaMemcpyHostToDevice, c.stream));
         MB_TRY(c.batch.reserve(n_frames * I.n_atoms * 3 * sizeof(float)));
+        EvTimer t_h2d(c.stream), t_dec(c.stream);
+        t_h2d.start();
+        MB_CUDA(cudaMemcpyAsync(c.traj_raw.p, b + start, end - start, cudaMemcpyHostToDevice, c.stream));
+        t_h2d.stop();
+        c.traj_raw_bytes = (double)(end - start);
         DcdDev D;
         memset(&D, 0, sizeof(D));
         D.raw = c.traj_raw.as<uint32_t>();
@@ -687,6 +711,7 @@ int mb_batch_load_traj(MbCtx* h, const void* bytes, size_t n_bytes, int format, 
                 D.fixed = d_fixed;
             }
         }
+        t_dec.start();
         if (n_frames > 65535) {
             // grid.y limit: launch in slabs
             for (size_t f0 = 0; f0 < n_frames; f0 += 65535) {
@@ -705,8 +730,12 @@ int mb_batch_load_traj(MbCtx* h, const void* bytes, size_t n_bytes, int format, 
             dcd_unpack_kernel<<<dim3(bx, (unsigned)n_frames), 256, 0, c.stream>>>(D);
             c.launches++;
         }
+        t_dec.stop();
         MB_CUDA(cudaGetLastError());
         MB_CUDA(cudaStreamSynchronize(c.stream));
+        c.traj_h2d_ms = t_h2d.ms();
+        c.traj_decode_ms = t_dec.ms();
+        c.traj_scan_ms = 0.0;
         return finish_batch(c, n_frames, I.n_atoms, have_first_box ? first_box : nullptr);
     }
 
@@ -719,7 +748,12 @@ int mb_batch_load_traj(MbCtx* h, const void* bytes, size_t n_bytes, int format, 
         const size_t start = fr[first_frame].off;
         const size_t end = fr[first_frame + n_frames - 1].off + fr[first_frame + n_frames - 1].size;
         MB_TRY(c.traj_raw.reserve(end - start + 64));
+        EvTimer t_h2d(c.stream);
+        t_h2d.start();
         MB_CUDA(cudaMemcpyAsync(c.traj_raw.p, b + start, end - start, cudaMemcpyHostToDevice, c.stream));
+        t_h2d.stop();
+        c.traj_raw_bytes = (double)(end - start);
+        c.traj_decode_ms = c.traj_scan_ms = 0.0;
         MB_CUDA(cudaMemsetAsync(static_cast<char*>(c.traj_raw.p) + (end - start), 0, 64, c.stream));
         MB_TRY(c.batch.reserve(n_frames * na * 3 * sizeof(float)));
         // frames are decoded in passes that bound the group tables (<= one group per atom)
@@ -746,15 +780,24 @@ int mb_batch_load_traj(MbCtx* h, const void* bytes, size_t n_bytes, int format, 
             }
             MB_CUDA(cudaMemcpyAsync(d_frames, desc.data(), nf * sizeof(XtcFrame), cudaMemcpyHostToDevice, c.stream));
             MB_CUDA(cudaStreamSynchronize(c.stream));  // `desc` is reused by the next pass
+            EvTimer t_scan(c.stream), t_all(c.stream);
+            t_all.start();
+            t_scan.start();
             xtc_scan_kernel<<<(unsigned)((nf + 63) / 64), 64, 0, c.stream>>>(c.traj_raw.as<uint8_t>(), d_frames, (int)nf,
                                                                              d_bit, d_atom, d_meta, d_count, d_status);
+            t_scan.stop();
             const unsigned gx = (unsigned)std::max<size_t>(1, std::min<size_t>((na + 127) / 128, 1024));
             xtc_decode_kernel<<<dim3(gx, (unsigned)nf), 128, 0, c.stream>>>(c.traj_raw.as<uint8_t>(), d_frames, d_bit, d_atom,
                                                                             d_meta, d_count,
                                                                             c.batch.as<float>() + f0 * na * 3, (int)na);
+            t_all.stop();
             c.launches += 2;
             MB_CUDA(cudaGetLastError());
+            MB_CUDA(cudaStreamSynchronize(c.stream));
+            c.traj_decode_ms += t_all.ms();
+            c.traj_scan_ms += t_scan.ms();
         }
+        c.traj_h2d_ms = t_h2d.ms();
         int status = 0;
         MB_CUDA(cudaMemcpyAsync(&status, d_status, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
         MB_CUDA(cudaStreamSynchronize(c.stream));

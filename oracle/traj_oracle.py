@@ -314,3 +314,102 @@ def read_dcd(buf):
         frames.append(dict(xyz=xyz, cell=cell, time=float(time)))
         cur += 1
     return frames
+
+
+# ---------------------------------------------------------------------------------------------- XTC writer
+class _BitWriter:
+    def __init__(self):
+        self.out = bytearray()
+        self.acc = 0
+        self.n = 0
+
+    def put(self, nbits, value):
+        if nbits == 0:
+            return
+        self.acc = (self.acc << nbits) | (value & ((1 << nbits) - 1))
+        self.n += nbits
+        while self.n >= 8:
+            self.n -= 8
+            self.out.append((self.acc >> self.n) & 0xFF)
+        self.acc &= (1 << self.n) - 1
+
+    def finish(self):
+        if self.n:
+            self.out.append((self.acc << (8 - self.n)) & 0xFF)
+            self.acc = self.n = 0
+        return bytes(self.out)
+
+
+def _sendints(bw, nbits, sizes, nums):
+    """inverse of _receiveints: mixed-radix number, bytes least significant first"""
+    v = (nums[0] * sizes[1] + nums[1]) * sizes[2] + nums[2]
+    full, rem = divmod(nbits, 8)
+    for j in range(full):
+        bw.put(8, (v >> (8 * j)) & 0xFF)
+    if rem:
+        bw.put(rem, (v >> (8 * full)) & ((1 << rem) - 1))
+
+
+def write_xtc_frame(xyz_nm, box, step=0, time=0.0, precision=1000.0, smallidx=24, max_small=8):
+    """A VALID xtc frame for synthetic data (test / bench input).  Not the xdrfile compressor: the small-integer
+    width stays fixed (`smallidx`), runs are formed greedily wherever consecutive atoms are close enough, and
+    the flag bit is left clear when the run length repeats — every branch of the decoder is exercised except
+    the adaptive change of the small-integer width."""
+    xyz = np.asarray(xyz_nm, np.float32)
+    n = len(xyz)
+    box = np.asarray(box, np.float32).reshape(3, 3)
+    head = struct.pack(">iiif", 1995, n, step, time) + box.T.astype(">f4").tobytes() + struct.pack(">i", n)
+    if n <= 9:
+        return head + xyz.astype(">f4").tobytes()
+    ints = np.rint(xyz.astype(np.float64) * precision).astype(np.int64)
+    minint, maxint = ints.min(0), ints.max(0)
+    sizeint = [int(maxint[k] - minint[k] + 1) for k in range(3)]
+    if any(s > 0xFFFFFF for s in sizeint):
+        bitsizeint, bitsize = [_sizeofint(s) for s in sizeint], 0
+    else:
+        bitsize = _sizeofints(sizeint)
+    ss = MAGICINTS[smallidx]
+    smallnum = ss // 2
+    rel = (ints - minint).tolist()
+    a = ints.tolist()
+
+    def close(p, q):
+        return all(0 <= a[p][k] - a[q][k] + smallnum < ss for k in range(3))
+
+    bw = _BitWriter()
+    i, prev_run = 0, 0
+    while i < n:
+        # atoms i.. : [S1, F, S2, S3, ...] on output; F is stored first
+        nsmall = 0
+        if i + 1 < n and close(i, i + 1):
+            nsmall = 1
+            last = i
+            j = i + 2
+            while j < n and nsmall < max_small and close(j, last):
+                last = j
+                nsmall += 1
+                j += 1
+        f = i + 1 if nsmall else i
+        if bitsize == 0:
+            for k in range(3):
+                bw.put(bitsizeint[k], rel[f][k])
+        else:
+            _sendints(bw, bitsize, sizeint, rel[f])
+        run = 3 * nsmall
+        if run == prev_run:
+            bw.put(1, 0)
+        else:
+            bw.put(1, 1)
+            bw.put(5, run + 1)  # run % 3 == 1: the width of the small integers stays as it is
+        prev_run = run
+        if nsmall:
+            _sendints(bw, smallidx, [ss] * 3, [a[i][k] - a[f][k] + smallnum for k in range(3)])
+            last = i
+            for j in range(i + 2, i + 1 + nsmall):
+                _sendints(bw, smallidx, [ss] * 3, [a[j][k] - a[last][k] + smallnum for k in range(3)])
+                last = j
+        i += 1 + nsmall
+    data = bw.finish()
+    pad = (-len(data)) % 4
+    return (head + struct.pack(">f", precision) + struct.pack(">3i", *[int(v) for v in minint]) +
+            struct.pack(">3i", *[int(v) for v in maxint]) + struct.pack(">ii", smallidx, len(data)) + data + b"\0" * pad)

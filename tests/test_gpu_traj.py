@@ -58,6 +58,25 @@ def test_xtc_small_fixtures_vs_oracle(mb, golden_dir):
         traj.close()
 
 
+def test_xtc_synthetic_runs_and_wide_fields(mb):
+    """Synthetic frames from the oracle's writer: long runs, repeated run lengths (flag bit clear), isolated
+    atoms, and a coordinate range above 2^24 (separate bit fields), 300k atoms."""
+    from tests.test_oracle_traj import _waterlike
+    xyz = _waterlike(80_000, 9.0, 6)
+    box = np.diag([9.0, 9.0, 9.0]).astype(np.float32)
+    far = xyz.copy()
+    far[17] = [17000.0, 2.0, -3.0]
+    buf = T.write_xtc_frame(xyz, box, step=1, time=1.0) + T.write_xtc_frame(far, box, step=2, time=2.0) + \
+        T.write_xtc_frame(xyz[::-1].copy(), box, step=3, time=3.0, smallidx=30, max_small=3)
+    want = T.read_xtc(buf)
+    traj = _load(mb, buf, "xtc")
+    got = traj.frames()
+    for f in range(3):
+        assert np.array_equal(got[f], want[f]["xyz"]), f
+    assert list(traj.times) == [1.0, 2.0, 3.0]
+    traj.close()
+
+
 def test_xtc_tiny_system_is_stored_raw(mb):
     # natoms <= 9: uncompressed big-endian floats (xdr3dfcoord)
     import struct

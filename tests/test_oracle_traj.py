@@ -64,3 +64,31 @@ def test_dcd_fixed_atoms():
         assert np.array_equal(got[f]["xyz"][fixed], got[0]["xyz"][fixed])
         ang = (frames[f] * np.float32(10.0)).astype(np.float32)
         assert np.array_equal(got[f]["xyz"][free], (ang * np.float32(0.1))[free])
+
+
+def _waterlike(n_mol, box_len, seed):
+    rng = np.random.default_rng(seed)
+    o = rng.random((n_mol, 3)) * box_len
+    w = np.repeat(o, 3, axis=0) + rng.normal(0.0, 0.03, (3 * n_mol, 3))
+    iso = rng.random((n_mol // 4, 3)) * box_len
+    return np.concatenate([w[: n_mol], iso, w[n_mol:]]).astype(np.float32)
+
+
+def _quantised(xyz, precision=1000.0):
+    q = np.rint(xyz.astype(np.float64) * precision).astype(np.int64)
+    return (q.astype(np.float32) * (np.float32(1.0) / np.float32(precision))).astype(np.float32)
+
+
+def test_synthetic_xtc_writer_roundtrip():
+    xyz = _waterlike(1500, 6.0, 5)
+    box = np.diag([6.0, 6.0, 6.0]).astype(np.float32)
+    buf = T.write_xtc_frame(xyz, box, step=7, time=3.5) + T.write_xtc_frame(xyz[::-1].copy(), box, step=8, time=4.0)
+    fr = T.read_xtc(buf)
+    assert [f["step"] for f in fr] == [7, 8] and fr[1]["time"] == 4.0
+    assert np.array_equal(fr[0]["xyz"], _quantised(xyz)) and np.array_equal(fr[1]["xyz"], _quantised(xyz[::-1]))
+    assert len(buf) < 0.5 * xyz.nbytes * 2  # runs of small integers do compress
+    # one coordinate range wider than 2^24 integers: the three fields are stored separately
+    far = xyz.copy()
+    far[3] = [20000.0, -5.0, 1.0]
+    fr = T.read_xtc(T.write_xtc_frame(far, box))
+    assert np.array_equal(fr[0]["xyz"], _quantised(far))

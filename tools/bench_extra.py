@@ -1,0 +1,154 @@
+#!/usr/bin/env python3
+"""Measurement of the SURVEY §8(f) rows built after the headline path (not the driver's bench contract):
+periodic reductions / inertia, DCD decode, XTC decode.  One JSON line per workload on stdout:
+value in the row's own unit, the kernel's algorithmic-byte roofline (CUDA events inside the library,
+mb_get_stat "traj_*", or wall clock around the synchronous C-ABI call for the reductions) and the oracle
+timed beside it on the host (a reported baseline, bounded sample).
+
+    python tools/bench_extra.py [--atoms 1000000] [--frames 16] [--reps 20]
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+sys.path.insert(0, ROOT)
+
+TRIC = np.array([[21.5, -2.7, -2.7], [0.0, 21.5, -2.7], [0.0, 0.0, 21.5]], np.float32)
+
+
+def peak():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        return 6650.0
+
+
+def roof(alg_bytes, ms, kernel):
+    a = alg_bytes / (ms * 1e-3) / 1e9
+    return {"bound": "hbm", "kernel": kernel, "achieved": a, "peak": peak(), "unit": "GB/s", "frac": a / peak(),
+            "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": ms, "traffic": None}
+
+
+def bench_pbc(mb, orc, n, reps):
+    xyz = orc.synth_frame(20260, 0, n, TRIC, stray_permille=10)
+    m = orc.synth_masses(20260, n)
+    s = mb.System(xyz, masses=m, box=TRIC)
+    sel = s()
+    out = []
+    for name, fn, passes, cpu in (
+            ("center_of_mass_pbc", lambda: sel.com(dims=[True, True, True]), 1,
+             lambda: orc.center_pbc(xyz, m, orc.Box(matrix=TRIC), 7, prec="f32")),
+            ("gyration_pbc", lambda: sel.gyration(pbc=True), 2,
+             lambda: orc.gyration_pbc(xyz, m, orc.Box(matrix=TRIC), prec="f32")),
+            ("inertia_pbc", lambda: sel.inertia(pbc=True), 2,
+             lambda: orc.inertia(xyz, m, orc.Box(matrix=TRIC), prec="f32"))):
+        for _ in range(3):
+            fn()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        ms = (time.perf_counter() - t0) * 1e3 / reps
+        t0 = time.perf_counter()
+        cpu()
+        cms = (time.perf_counter() - t0) * 1e3
+        out.append({"workload": f"{name}, {n} atoms, triclinic box, 1% stray atoms", "metric": "calls/sec",
+                    "value": 1e3 / ms, "unit": "calls/s", "ms_per_call": ms,
+                    "roofline": roof(passes * 16.0 * n, ms, "center_pbc_kernel" + ("+tensor_kernel" if passes == 2 else "")
+                                     + " (wall clock of the synchronous call: launch + sync latency included)"),
+                    "cpu_baseline": {"value": 1e3 / cms, "unit": "calls/s", "cores": 1, "kind": "port",
+                                     "sample": "1 call of the oracle's f32 restatement (serial, as the reference)"}})
+    s.close()
+    return out
+
+
+def bench_dcd(mb, T, n, frames):
+    rng = np.random.default_rng(0)
+    one = (rng.random((1, n, 3)) * 20.0).astype(np.float32)
+    cell = np.array([215.0, 0.0, 215.0, 0.0, 0.0, 215.0])
+    buf = T.write_dcd(np.repeat(one, frames, axis=0), boxes=[cell] * frames)
+    traj = mb.Trajectory()
+    traj.load(buf, "dcd")
+    t0 = time.perf_counter()
+    traj.load(buf, "dcd")
+    wall = time.perf_counter() - t0
+    dec, h2d = traj.stat("traj_decode_ms"), traj.stat("traj_h2d_ms")
+    t0 = time.perf_counter()
+    T.read_dcd(buf[: len(buf) // frames * min(frames, 4) + 400])
+    cpu_s = (time.perf_counter() - t0) / min(frames, 4)
+    traj.close()
+    return [{"workload": f"DCD decode, {n} atoms x {frames} frames (x[],y[],z[] f32 -> [atom][3] nm)",
+             "metric": "frames/sec (decode kernel)", "value": frames / (dec * 1e-3), "unit": "frames/s",
+             "roofline": roof(24.0 * n * frames, dec, "dcd_unpack_kernel (one launch, all frames)"),
+             "e2e": {"value": frames / wall, "unit": "frames/s", "h2d_bytes_per_step": len(buf), "d2h_bytes_per_step": 0,
+                     "h2d_ms": h2d, "note": "host byte buffer (pageable) -> device frames, whole call"},
+             "cpu_baseline": {"value": 1.0 / cpu_s, "unit": "frames/s", "cores": 1, "kind": "port",
+                              "sample": "numpy restatement of DcdFileHandler::read_state on 4 frames"}}]
+
+
+def bench_xtc(mb, T, n, frames):
+    rng = np.random.default_rng(1)
+    L = (n / 100.0) ** (1.0 / 3.0)
+    nmol = n // 3
+    o = rng.random((nmol, 3)) * L
+    xyz = (np.repeat(o, 3, axis=0) + rng.normal(0.0, 0.03, (3 * nmol, 3))).astype(np.float32)
+    box = np.diag([L, L, L]).astype(np.float32)
+    t0 = time.perf_counter()
+    fr = T.write_xtc_frame(xyz, box)
+    enc_s = time.perf_counter() - t0
+    buf = fr * frames
+    traj = mb.Trajectory()
+    traj.load(buf, "xtc")
+    t0 = time.perf_counter()
+    traj.load(buf, "xtc")
+    wall = time.perf_counter() - t0
+    dec, scan, h2d = traj.stat("traj_decode_ms"), traj.stat("traj_scan_ms"), traj.stat("traj_h2d_ms")
+    ok = bool(np.array_equal(traj.frames(0, 1)[0][:3000], T.read_xtc_frame(fr)[0]["xyz"][:3000])) if n <= 200_000 else None
+    cpu = None
+    if n <= 200_000:
+        t0 = time.perf_counter()
+        T.read_xtc_frame(fr)
+        cpu = time.perf_counter() - t0
+    traj.close()
+    na = len(xyz)
+    return [{"workload": f"XTC decode, {na} atoms x {frames} frames, water-like synthetic frames "
+                         f"({len(fr) / na:.2f} B/atom compressed)",
+             "metric": "frames/sec (scan + decode kernels)", "value": frames / (dec * 1e-3), "unit": "frames/s",
+             "scan_ms": scan, "decode_ms": dec - scan, "checked_against_oracle": ok,
+             "roofline": roof((len(fr) + 12.0 * na) * frames, dec, "xtc_scan_kernel + xtc_decode_kernel"),
+             "e2e": {"value": frames / wall, "unit": "frames/s", "h2d_bytes_per_step": len(buf), "d2h_bytes_per_step": 0,
+                     "h2d_ms": h2d, "note": "host byte buffer (pageable) -> device frames, whole call"},
+             "cpu_baseline": ({"value": 1.0 / cpu, "unit": "frames/s", "cores": 1, "kind": "port",
+                               "sample": "pure-Python oracle decoder, 1 frame (a checker, not a fast CPU decoder)"}
+                              if cpu else None),
+             "input_synthesis_s": enc_s}]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--atoms", type=int, default=1_000_000)
+    ap.add_argument("--frames", type=int, default=16)
+    ap.add_argument("--reps", type=int, default=20)
+    ap.add_argument("--only", default="")
+    a = ap.parse_args()
+    import molar_b200 as mb
+    from oracle import oracle_py as orc
+    from oracle import traj_oracle as T
+    lines = []
+    if a.only in ("", "pbc"):
+        lines += bench_pbc(mb, orc, a.atoms, a.reps)
+    if a.only in ("", "dcd"):
+        lines += bench_dcd(mb, T, a.atoms, a.frames)
+    if a.only in ("", "xtc"):
+        lines += bench_xtc(mb, T, min(a.atoms, 150_000), max(a.frames, 256))
+        lines += bench_xtc(mb, T, a.atoms, a.frames)
+    for ln in lines:
+        print(json.dumps(ln))
+
+
+if __name__ == "__main__":
+    main()
