@@ -182,6 +182,11 @@ int mb_batch_select(MbCtx* ctx, size_t frame);
    mode 0 = enumerate pairs, 1 = count only. */
 int mb_batch_search(MbCtx* ctx, float cutoff, uint8_t pbc_dims, size_t f0, size_t f1, int mode,
                     int64_t* counts, uint64_t* checksums2);
+/* The same search over n_frames HOST frames ([n_frames][n_atoms][3] f32, ideally pinned): frames are uploaded on a
+   copy stream in chunks while the previous chunk is searched — the role of the reference's IO thread + bounded
+   channel (io.rs:209-233).  The pair list of the last frame stays on the device (mb_fill_pairs). */
+int mb_stream_search(MbCtx* ctx, float cutoff, uint8_t pbc_dims, const float* frames, size_t n_frames, size_t n_atoms,
+                     const float* box9_colmajor, int mode, int64_t* counts);
 /* Kabsch fit of every frame [f0,f1) onto frame `ref_frame`, superposition in place and
    unweighted RMSD after the fit (config 4).  rmsd_out: f1-f0 doubles (host, may be NULL). */
 int mb_batch_fit(MbCtx* ctx, size_t ref_frame, size_t f0, size_t f1, int superpose, double* rmsd_out);

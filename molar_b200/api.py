@@ -418,6 +418,19 @@ class Trajectory:
                                         chk.ctypes.data_as(u64p) if checksums else None))
         return (counts, chk) if checksums else counts
 
+    def stream_search(self, frames, cutoff, box, dims=(True, True, True), count_only=False):
+        """Neighbour search over HOST frames [F][N][3] (upload overlapped with the search of the previous chunk)."""
+        x = frames if isinstance(frames, np.ndarray) and frames.dtype == np.float32 and frames.flags.c_contiguous \
+            else np.ascontiguousarray(frames, dtype=np.float32)
+        nf, na = x.shape[0], x.shape[1]
+        b = box if isinstance(box, PeriodicBox) else PeriodicBox(box)
+        counts = np.zeros(nf, np.int64)
+        check(self._lib.mb_stream_search(self._h, cutoff, _pbc_bits(dims), x.ctypes.data, nf, na,
+                                         b.colmajor9.ctypes.data_as(f32p), 1 if count_only else 0,
+                                         counts.ctypes.data_as(i64p)))
+        self.n_frames, self.n_atoms = min(nf, 8), na
+        return counts
+
     def last_pairs(self):
         """Pair list of the last frame searched (host copy)."""
         n = C.c_int64(0)

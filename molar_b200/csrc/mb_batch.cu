@@ -145,6 +145,52 @@ int mb_batch_search(MbCtx* h, float cutoff, uint8_t pbc_dims, size_t f0, size_t 
     return batch_search_impl(&h->c, cutoff, pbc_dims & 7, f0, f1, mode, counts, checksums2);
 }
 
+// Streaming search over HOST frames: what the reference's trajectory loop does with an IO thread feeding a
+// bounded channel while the consumer analyses (io.rs:209-233, analysis_task.rs:113-280), done with a copy stream:
+// frames are uploaded in chunks into one half of a two-chunk ring while the previous chunk is being searched.
+int mb_stream_search(MbCtx* h, float cutoff, uint8_t pbc_dims, const float* frames, size_t n_frames, size_t n_atoms,
+                     const float* box9, int mode, int64_t* counts) {
+    if (!h || !frames || n_frames == 0 || n_atoms == 0) return fail(MB_ERR_ARG, "mb_stream_search: bad argument");
+    Ctx& c = h->c;
+    MB_CUDA(cudaSetDevice(c.device));
+    if (box9) {
+        MB_TRY(host_box_from_colmajor(box9, &c.box));
+        c.has_box = true;
+    }
+    const size_t chunk = std::min<size_t>(n_frames, n_atoms >= 500000 ? 4 : 32);
+    const size_t fbytes = n_atoms * 3 * sizeof(float);
+    MB_TRY(c.batch.reserve(2 * chunk * fbytes));
+    c.batch_frames = 2 * chunk;
+    c.batch_atoms = n_atoms;
+    c.d_xyz = c.batch.as<float>();
+    c.n_atoms = n_atoms;
+    if (!c.aux_stream[0]) MB_CUDA(cudaStreamCreateWithFlags(&c.aux_stream[0], cudaStreamNonBlocking));
+    cudaStream_t copy = c.aux_stream[0];
+    cudaEvent_t up[2] = {nullptr, nullptr};
+    for (int k = 0; k < 2; ++k) MB_CUDA(cudaEventCreateWithFlags(&up[k], cudaEventDisableTiming));
+    const size_t nchunks = (n_frames + chunk - 1) / chunk;
+    auto upload = [&](size_t k) -> int {
+        const size_t f0 = k * chunk, nf = std::min(chunk, n_frames - f0);
+        MB_CUDA(cudaMemcpyAsync(c.batch.as<char>() + (k & 1) * chunk * fbytes, frames + f0 * n_atoms * 3, nf * fbytes,
+                                cudaMemcpyHostToDevice, copy));
+        MB_CUDA(cudaEventRecord(up[k & 1], copy));
+        return MB_OK;
+    };
+    int rc = upload(0);
+    for (size_t k = 0; k < nchunks && rc == MB_OK; ++k) {
+        // the other half was searched by the previous (synchronous) batch_search_impl call: free to overwrite
+        if (k + 1 < nchunks) rc = upload(k + 1);
+        if (rc != MB_OK) break;
+        cudaStreamWaitEvent(c.stream, up[k & 1], 0);
+        const size_t f0 = k * chunk, nf = std::min(chunk, n_frames - f0);
+        const size_t b0 = (k & 1) * chunk;
+        rc = batch_search_impl(&c, cutoff, pbc_dims & 7, b0, b0 + nf, mode, counts ? counts + f0 : nullptr, nullptr);
+    }
+    cudaStreamSynchronize(copy);
+    for (int k = 0; k < 2; ++k) cudaEventDestroy(up[k]);
+    return rc;
+}
+
 int mb_batch_fit(MbCtx* h, size_t ref_frame, size_t f0, size_t f1, int superpose, double* rmsd_out) {
     if (!h) return fail(MB_ERR_ARG, "null context");
     return batch_fit_impl(&h->c, ref_frame, f0, f1, superpose, rmsd_out);

@@ -13,8 +13,9 @@
 // XTC on a GPU.  The bit stream of a frame is a chain of GROUPS (one full-width atom, a flag bit, an
 // optional 5-bit run code, run/3 small atoms); where a group starts depends on every flag before it,
 // what it contains does not.  So the decode is split:
-//   xtc_scan_kernel    one thread per frame walks ONLY the flag / run bits and records, per group, the
-//                      bit offset, the first atom index, the small-integer width and the run length;
+//   xtc_scan_kernel    one warp per frame walks ONLY the flag / run bits (32 groups per step while the flag
+//                      stays clear) and records, per group, the bit offset, the first atom index, the
+//                      small-integer width and the run length;
 //   xtc_decode_kernel  one thread per group unpacks the mixed-radix integers (64/128-bit arithmetic
 //                      instead of the byte-wise long division of the serial code), applies the delta
 //                      chain inside the group and writes nm coordinates.
@@ -320,52 +321,97 @@ __device__ __forceinline__ void xtc_unpack3(const uint8_t* __restrict__ d, unsig
     }
 }
 
-// one thread per frame: group table
-__global__ void __launch_bounds__(64) xtc_scan_kernel(const uint8_t* __restrict__ raw, const XtcFrame* __restrict__ frames,
-                                                      int nf, unsigned* __restrict__ g_bit, unsigned* __restrict__ g_atom,
-                                                      unsigned short* __restrict__ g_meta, unsigned* __restrict__ g_count,
-                                                      int* __restrict__ status) {
-    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+// One WARP per frame: group table.  The walk is serial in principle (a group's length depends on its own flag
+// bit), but as long as the flag stays clear every group has the same length — the steady state of solvent,
+// where the run length repeats — so the 32 lanes test the flag bits of the next 32 groups under that assumption
+// and the warp advances over the longest confirmed prefix at once; a set flag (new run code, possibly a new
+// small-integer width) is then handled as one serial step.
+constexpr int XTC_SCAN_THREADS = 128;
+__global__ void __launch_bounds__(XTC_SCAN_THREADS) xtc_scan_kernel(const uint8_t* __restrict__ raw,
+                                                                    const XtcFrame* __restrict__ frames, int nf,
+                                                                    unsigned* __restrict__ g_bit,
+                                                                    unsigned* __restrict__ g_atom,
+                                                                    unsigned short* __restrict__ g_meta,
+                                                                    unsigned* __restrict__ g_count,
+                                                                    int* __restrict__ status) {
+    const int f = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+    const unsigned lane = threadIdx.x & 31u;
     if (f >= nf) return;
     const XtcFrame F = frames[f];
     if (F.raw) {
-        g_count[f] = 0;
+        if (lane == 0) g_count[f] = 0;
         return;
     }
     const uint8_t* d = raw + F.data_off;
     const unsigned long long total_bits = (unsigned long long)F.nbytes * 8ull;
-    const int fullbits = F.bitsize ? F.bitsize : F.bitsizeint[0] + F.bitsizeint[1] + F.bitsizeint[2];
+    const unsigned fullbits = (unsigned)(F.bitsize ? F.bitsize : F.bitsizeint[0] + F.bitsizeint[1] + F.bitsizeint[2]);
     unsigned long long bp = 0;
     int i = 0, run = 0, smallidx = F.smallidx;
     unsigned ng = 0;
+    bool bad = false;
+    // The walk is one dependent chain per frame, so nothing hides memory latency but prefetching: keep the next
+    // 8 KB of the stream on their way into L2 and the next 1 KB into L1.
+    unsigned long long pf = 0;
     while (i < F.natoms) {
-        unsigned long long p = bp + fullbits;
-        if (p + 1 > total_bits || smallidx < XTC_FIRSTIDX || smallidx >= XTC_LASTIDX) {
-            atomicExch(status, f + 1);  // corrupt stream
+        if (smallidx < XTC_FIRSTIDX || smallidx >= XTC_LASTIDX) {
+            bad = true;
             break;
         }
-        const unsigned flag = xtc_bits(d, p, 1);
-        p += 1;
-        int is_smaller = 0;
-        if (flag) {
-            run = (int)xtc_bits(d, p, 5);
-            p += 5;
-            is_smaller = run % 3;
+        {
+            const unsigned long long cur = bp >> 3;
+            while (pf < cur + 8192ull && pf < F.nbytes) {
+                const unsigned long long a = pf + (unsigned long long)lane * 128ull;
+                if (a < F.nbytes) asm volatile("prefetch.global.L2 [%0];" ::"l"(d + a));
+                pf += 4096ull;
+            }
+            const unsigned long long a1 = cur + 256ull + (unsigned long long)lane * 128ull;
+            if (lane < 8u && a1 < F.nbytes) asm volatile("prefetch.global.L1 [%0];" ::"l"(d + a1));
+        }
+        const int nsmall = run / 3, per = 1 + nsmall;
+        const unsigned len0 = fullbits + 1u + (unsigned)(nsmall * smallidx);  // length of a group whose flag is clear
+        const int left = (F.natoms - i + per - 1) / per;
+        const unsigned long long p = bp + (unsigned long long)lane * len0, fp = p + fullbits;
+        const bool ok = (int)lane < left && fp < total_bits;
+        const unsigned flag = ok ? xtc_bits(d, fp, 1) : 1u;
+        const unsigned clear = __ballot_sync(0xffffffffu, flag == 0u);
+        const int nz = clear == 0xffffffffu ? 32 : __ffs((int)~clear) - 1;
+        if ((int)lane < nz) {
+            const size_t e = F.group_off + ng + lane;
+            g_bit[e] = (unsigned)p;
+            g_atom[e] = (unsigned)(i + (int)lane * per);
+            g_meta[e] = (unsigned short)(smallidx | (run << 8));
+        }
+        bp += (unsigned long long)nz * len0;
+        i += nz * per;
+        ng += (unsigned)nz;
+        if (nz < 32 && i < F.natoms) {
+            // the next group has its flag set: new run code (and possibly a new small-integer width)
+            const unsigned long long q = bp + fullbits;
+            if (q + 6 > total_bits || xtc_bits(d, q, 1) == 0u) {
+                bad = true;
+                break;
+            }
+            run = (int)xtc_bits(d, q + 1, 5);
+            int is_smaller = run % 3;
             run -= is_smaller;
             is_smaller--;
+            if (lane == 0) {
+                const size_t e = F.group_off + ng;
+                g_bit[e] = (unsigned)bp;
+                g_atom[e] = (unsigned)i;
+                g_meta[e] = (unsigned short)(smallidx | (run << 8));
+            }
+            ++ng;
+            const int ns = run / 3;
+            i += 1 + ns;
+            bp = q + 6 + (unsigned long long)ns * (unsigned)smallidx;
+            smallidx += is_smaller;
         }
-        const size_t e = F.group_off + ng;
-        g_bit[e] = (unsigned)bp;
-        g_atom[e] = (unsigned)i;
-        g_meta[e] = (unsigned short)(smallidx | (run << 8));
-        ++ng;
-        const int nsmall = run / 3;
-        i += 1 + nsmall;
-        bp = p + (unsigned long long)nsmall * (unsigned)smallidx;
-        smallidx += is_smaller;
     }
-    if (i > F.natoms) atomicExch(status, f + 1);
-    g_count[f] = ng;
+    if (lane == 0) {
+        if (bad || i > F.natoms) atomicExch(status, f + 1);  // corrupt stream
+        g_count[f] = ng;
+    }
 }
 
 // one thread per group (blockIdx.y = frame)
@@ -783,7 +829,7 @@ int mb_batch_load_traj(MbCtx* h, const void* bytes, size_t n_bytes, int format, 
             EvTimer t_scan(c.stream), t_all(c.stream);
             t_all.start();
             t_scan.start();
-            xtc_scan_kernel<<<(unsigned)((nf + 63) / 64), 64, 0, c.stream>>>(c.traj_raw.as<uint8_t>(), d_frames, (int)nf,
+            xtc_scan_kernel<<<(unsigned)((nf * 32 + XTC_SCAN_THREADS - 1) / XTC_SCAN_THREADS), XTC_SCAN_THREADS, 0, c.stream>>>(c.traj_raw.as<uint8_t>(), d_frames, (int)nf,
                                                                              d_bit, d_atom, d_meta, d_count, d_status);
             t_scan.stop();
             const unsigned gx = (unsigned)std::max<size_t>(1, std::min<size_t>((na + 127) / 128, 1024));

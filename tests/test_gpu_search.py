@@ -351,3 +351,26 @@ def test_single_pbc_big_box_filter_vs_exact_path(mb, exact):
     op, od, dims = oracle_single(1.2, xyz, box=Mo, pbc=7, nthreads=8)
     gp, gd = run_single(mb, xyz, 1.2, box=Mo, dims=[True] * 3, exact_pbc=exact)
     assert_same_pairs(gp, gd, op, od)
+
+
+def test_stream_search_host_frames(mb):
+    """mb_stream_search: host frames uploaded chunk by chunk while the previous chunk is searched; counts and the
+    last frame's pair list equal the per-call path."""
+    n, nf = 60_000, 11
+    box = np.diag([8.0, 9.0, 8.5]).astype(np.float32)
+    frames = np.stack([orc.synth_frame(SEED + 3, f, n, box, stray_permille=5) for f in range(nf)])
+    traj = mb.Trajectory()
+    counts = traj.stream_search(frames, 1.2, box)
+    s = mb.System(frames[0], box=box)
+    for f in (0, 4, nf - 1):
+        s.set_state(frames[f], box)
+        pairs, dist = mb.distance_search(1.2, s(), dims=[True, True, True])
+        assert counts[f] == len(pairs)
+    lp = traj.last_pairs()
+    got = np.unique(np.sort(lp, axis=1), axis=0)
+    want = np.unique(np.sort(np.asarray(pairs, dtype=np.uint64), axis=1), axis=0)
+    assert np.array_equal(got, want)
+    counts2 = traj.stream_search(frames, 1.2, box, count_only=True)
+    assert np.array_equal(counts, counts2)
+    traj.close()
+    s.close()

@@ -60,10 +60,10 @@ def test_xtc_small_fixtures_vs_oracle(mb, golden_dir):
 
 def test_xtc_synthetic_runs_and_wide_fields(mb):
     """Synthetic frames from the oracle's writer: long runs, repeated run lengths (flag bit clear), isolated
-    atoms, and a coordinate range above 2^24 (separate bit fields), 300k atoms."""
+    atoms, and a coordinate range above 2^24 (separate bit fields)."""
     from tests.test_oracle_traj import _waterlike
-    xyz = _waterlike(80_000, 9.0, 6)
-    box = np.diag([9.0, 9.0, 9.0]).astype(np.float32)
+    xyz = _waterlike(12_000, 5.0, 6)
+    box = np.diag([5.0, 5.0, 5.0]).astype(np.float32)
     far = xyz.copy()
     far[17] = [17000.0, 2.0, -3.0]
     buf = T.write_xtc_frame(xyz, box, step=1, time=1.0) + T.write_xtc_frame(far, box, step=2, time=2.0) + \
