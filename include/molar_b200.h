@@ -187,6 +187,11 @@ int mb_batch_search(MbCtx* ctx, float cutoff, uint8_t pbc_dims, size_t f0, size_
    channel (io.rs:209-233).  The pair list of the last frame stays on the device (mb_fill_pairs). */
 int mb_stream_search(MbCtx* ctx, float cutoff, uint8_t pbc_dims, const float* frames, size_t n_frames, size_t n_atoms,
                      const float* box9_colmajor, int mode, int64_t* counts);
+/* Same streaming for the other two per-frame loops: Kabsch fit of every host frame onto the first one (RMSD after
+   the fit out; masses via mb_set_masses), and COM + gyration + contact count (n_frames x 5 doubles out). */
+int mb_stream_fit(MbCtx* ctx, const float* frames, size_t n_frames, size_t n_atoms, double* rmsd_out);
+int mb_stream_pipeline(MbCtx* ctx, float cutoff, uint8_t pbc_dims, const float* frames, size_t n_frames, size_t n_atoms,
+                       const float* box9_colmajor, double* out);
 /* Kabsch fit of every frame [f0,f1) onto frame `ref_frame`, superposition in place and
    unweighted RMSD after the fit (config 4).  rmsd_out: f1-f0 doubles (host, may be NULL). */
 int mb_batch_fit(MbCtx* ctx, size_t ref_frame, size_t f0, size_t f1, int superpose, double* rmsd_out);

@@ -58,6 +58,8 @@ SIGNATURES = {
     "mb_batch_download": (C.c_int, [C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p]),
     "mb_batch_search": (C.c_int, [C.c_void_p, C.c_float, C.c_uint8, C.c_size_t, C.c_size_t, C.c_int, i64p, u64p]),
     "mb_stream_search": (C.c_int, [C.c_void_p, C.c_float, C.c_uint8, C.c_void_p, C.c_size_t, C.c_size_t, f32p, C.c_int, i64p]),
+    "mb_stream_fit": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, f64p]),
+    "mb_stream_pipeline": (C.c_int, [C.c_void_p, C.c_float, C.c_uint8, C.c_void_p, C.c_size_t, C.c_size_t, f32p, f64p]),
     "mb_batch_fit": (C.c_int, [C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, f64p]),
     "mb_batch_pipeline": (C.c_int, [C.c_void_p, C.c_float, C.c_uint8, C.c_size_t, C.c_size_t, f64p]),
     "mb_batch_scalars_device": (C.c_void_p, [C.c_void_p, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),

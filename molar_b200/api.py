@@ -431,6 +431,32 @@ class Trajectory:
         self.n_frames, self.n_atoms = min(nf, 8), na
         return counts
 
+    def stream_fit(self, frames, masses):
+        """Kabsch fit of every HOST frame onto the first one; returns the RMSD after the fit per frame."""
+        x = frames if isinstance(frames, np.ndarray) and frames.dtype == np.float32 and frames.flags.c_contiguous \
+            else np.ascontiguousarray(frames, dtype=np.float32)
+        nf, na = x.shape[0], x.shape[1]
+        if masses is not None:
+            m = np.ascontiguousarray(masses, dtype=np.float32)
+            check(self._lib.mb_set_masses(self._h, m.ctypes.data, m.shape[0]))
+        out = np.zeros(nf, np.float64)
+        check(self._lib.mb_stream_fit(self._h, x.ctypes.data, nf, na, out.ctypes.data_as(f64p)))
+        return out
+
+    def stream_pipeline(self, frames, cutoff, box, masses=None, dims=(True, True, True)):
+        """COM + gyration + contact count per HOST frame -> [F,5] {com_x, com_y, com_z, rg, count}."""
+        x = frames if isinstance(frames, np.ndarray) and frames.dtype == np.float32 and frames.flags.c_contiguous \
+            else np.ascontiguousarray(frames, dtype=np.float32)
+        nf, na = x.shape[0], x.shape[1]
+        if masses is not None:
+            m = np.ascontiguousarray(masses, dtype=np.float32)
+            check(self._lib.mb_set_masses(self._h, m.ctypes.data, m.shape[0]))
+        b = box if isinstance(box, PeriodicBox) else PeriodicBox(box)
+        out = np.zeros((nf, 5), np.float64)
+        check(self._lib.mb_stream_pipeline(self._h, cutoff, _pbc_bits(dims), x.ctypes.data, nf, na,
+                                           b.colmajor9.ctypes.data_as(f32p), out.ctypes.data_as(f64p)))
+        return out
+
     def last_pairs(self):
         """Pair list of the last frame searched (host copy)."""
         n = C.c_int64(0)

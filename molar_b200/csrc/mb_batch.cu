@@ -67,6 +67,54 @@ __global__ void assemble_rows_kernel(const double* __restrict__ rows8, const uns
     rows5[5 * f + 4] = (double)counters[2 * f];
 }
 
+// Streaming over HOST frames: what the reference's trajectory loop does with an IO thread feeding a bounded
+// channel while the consumer analyses (io.rs:209-233, analysis_task.rs:113-280), done with a copy stream: frames are
+// uploaded in chunks into one half of a two-chunk ring while the previous chunk is being processed.
+// work(b0, nf, f0): process ring frames [b0, b0+nf) = stream frames [f0, f0+nf); synchronous.
+template <class Work>
+static int stream_chunks(Ctx& c, const float* frames, size_t n_frames, size_t n_atoms, size_t chunk, Work&& work) {
+    MB_CUDA(cudaSetDevice(c.device));
+    chunk = std::max<size_t>(1, std::min(chunk, n_frames));
+    const size_t fbytes = n_atoms * 3 * sizeof(float);
+    MB_TRY(c.batch.reserve(2 * chunk * fbytes));
+    c.batch_frames = 2 * chunk;
+    c.batch_atoms = n_atoms;
+    c.d_xyz = c.batch.as<float>();
+    c.n_atoms = n_atoms;
+    if (!c.aux_stream[0]) MB_CUDA(cudaStreamCreateWithFlags(&c.aux_stream[0], cudaStreamNonBlocking));
+    cudaStream_t copy = c.aux_stream[0];
+    cudaEvent_t up[2] = {nullptr, nullptr};
+    for (int k = 0; k < 2; ++k) MB_CUDA(cudaEventCreateWithFlags(&up[k], cudaEventDisableTiming));
+    const size_t nchunks = (n_frames + chunk - 1) / chunk;
+    auto upload = [&](size_t k) -> int {
+        const size_t f0 = k * chunk, nf = std::min(chunk, n_frames - f0);
+        MB_CUDA(cudaMemcpyAsync(c.batch.as<char>() + (k & 1) * chunk * fbytes, frames + f0 * n_atoms * 3, nf * fbytes,
+                                cudaMemcpyHostToDevice, copy));
+        MB_CUDA(cudaEventRecord(up[k & 1], copy));
+        return MB_OK;
+    };
+    int rc = upload(0);
+    for (size_t k = 0; k < nchunks && rc == MB_OK; ++k) {
+        // the other half was processed by the previous (synchronous) work() call: free to overwrite
+        if (k + 1 < nchunks) rc = upload(k + 1);
+        if (rc != MB_OK) break;
+        cudaStreamWaitEvent(c.stream, up[k & 1], 0);
+        const size_t f0 = k * chunk, nf = std::min(chunk, n_frames - f0);
+        rc = work((k & 1) * chunk, nf, f0);
+    }
+    cudaStreamSynchronize(copy);
+    for (int k = 0; k < 2; ++k) cudaEventDestroy(up[k]);
+    return rc;
+}
+
+static int stream_box(Ctx& c, const float* box9) {
+    if (box9) {
+        MB_TRY(host_box_from_colmajor(box9, &c.box));
+        c.has_box = true;
+    }
+    return MB_OK;
+}
+
 }  // namespace mb
 
 using namespace mb;
@@ -145,50 +193,37 @@ int mb_batch_search(MbCtx* h, float cutoff, uint8_t pbc_dims, size_t f0, size_t 
     return batch_search_impl(&h->c, cutoff, pbc_dims & 7, f0, f1, mode, counts, checksums2);
 }
 
-// Streaming search over HOST frames: what the reference's trajectory loop does with an IO thread feeding a
-// bounded channel while the consumer analyses (io.rs:209-233, analysis_task.rs:113-280), done with a copy stream:
-// frames are uploaded in chunks into one half of a two-chunk ring while the previous chunk is being searched.
 int mb_stream_search(MbCtx* h, float cutoff, uint8_t pbc_dims, const float* frames, size_t n_frames, size_t n_atoms,
                      const float* box9, int mode, int64_t* counts) {
     if (!h || !frames || n_frames == 0 || n_atoms == 0) return fail(MB_ERR_ARG, "mb_stream_search: bad argument");
     Ctx& c = h->c;
-    MB_CUDA(cudaSetDevice(c.device));
-    if (box9) {
-        MB_TRY(host_box_from_colmajor(box9, &c.box));
-        c.has_box = true;
-    }
-    const size_t chunk = std::min<size_t>(n_frames, n_atoms >= 500000 ? 4 : 32);
-    const size_t fbytes = n_atoms * 3 * sizeof(float);
-    MB_TRY(c.batch.reserve(2 * chunk * fbytes));
-    c.batch_frames = 2 * chunk;
-    c.batch_atoms = n_atoms;
-    c.d_xyz = c.batch.as<float>();
-    c.n_atoms = n_atoms;
-    if (!c.aux_stream[0]) MB_CUDA(cudaStreamCreateWithFlags(&c.aux_stream[0], cudaStreamNonBlocking));
-    cudaStream_t copy = c.aux_stream[0];
-    cudaEvent_t up[2] = {nullptr, nullptr};
-    for (int k = 0; k < 2; ++k) MB_CUDA(cudaEventCreateWithFlags(&up[k], cudaEventDisableTiming));
-    const size_t nchunks = (n_frames + chunk - 1) / chunk;
-    auto upload = [&](size_t k) -> int {
-        const size_t f0 = k * chunk, nf = std::min(chunk, n_frames - f0);
-        MB_CUDA(cudaMemcpyAsync(c.batch.as<char>() + (k & 1) * chunk * fbytes, frames + f0 * n_atoms * 3, nf * fbytes,
-                                cudaMemcpyHostToDevice, copy));
-        MB_CUDA(cudaEventRecord(up[k & 1], copy));
-        return MB_OK;
-    };
-    int rc = upload(0);
-    for (size_t k = 0; k < nchunks && rc == MB_OK; ++k) {
-        // the other half was searched by the previous (synchronous) batch_search_impl call: free to overwrite
-        if (k + 1 < nchunks) rc = upload(k + 1);
-        if (rc != MB_OK) break;
-        cudaStreamWaitEvent(c.stream, up[k & 1], 0);
-        const size_t f0 = k * chunk, nf = std::min(chunk, n_frames - f0);
-        const size_t b0 = (k & 1) * chunk;
-        rc = batch_search_impl(&c, cutoff, pbc_dims & 7, b0, b0 + nf, mode, counts ? counts + f0 : nullptr, nullptr);
-    }
-    cudaStreamSynchronize(copy);
-    for (int k = 0; k < 2; ++k) cudaEventDestroy(up[k]);
-    return rc;
+    MB_TRY(stream_box(c, box9));
+    return stream_chunks(c, frames, n_frames, n_atoms, n_atoms >= 500000 ? 4 : 32, [&](size_t b0, size_t nf, size_t f0) {
+        return batch_search_impl(&c, cutoff, pbc_dims & 7, b0, b0 + nf, mode, counts ? counts + f0 : nullptr, nullptr);
+    });
+}
+
+// Kabsch fit of every host frame onto the FIRST one + unweighted RMSD after the fit (config 4); the superposed
+// coordinates stay on the device (last chunk) — only the RMSD values travel back.
+int mb_stream_fit(MbCtx* h, const float* frames, size_t n_frames, size_t n_atoms, double* rmsd_out) {
+    if (!h || !frames || n_frames == 0 || n_atoms == 0) return fail(MB_ERR_ARG, "mb_stream_fit: bad argument");
+    Ctx& c = h->c;
+    const size_t chunk = std::max<size_t>(8, std::min<size_t>(128, ((size_t)48 << 20) / (n_atoms * 12)));
+    return stream_chunks(c, frames, n_frames, n_atoms, chunk, [&](size_t b0, size_t nf, size_t f0) {
+        // the first chunk stages frame 0 as the reference; later chunks keep it
+        return batch_fit_impl(&c, f0 == 0 ? b0 : (size_t)-1, b0, b0 + nf, 1, rmsd_out ? rmsd_out + f0 : nullptr);
+    });
+}
+
+// Per-frame COM + gyration + contact count over host frames (config 5): out is n_frames x 5 doubles.
+int mb_stream_pipeline(MbCtx* h, float cutoff, uint8_t pbc_dims, const float* frames, size_t n_frames, size_t n_atoms,
+                       const float* box9, double* out) {
+    if (!h || !frames || !out || n_frames == 0 || n_atoms == 0) return fail(MB_ERR_ARG, "mb_stream_pipeline: bad argument");
+    Ctx& c = h->c;
+    MB_TRY(stream_box(c, box9));
+    return stream_chunks(c, frames, n_frames, n_atoms, n_atoms >= 500000 ? 4 : 32, [&](size_t b0, size_t nf, size_t f0) {
+        return mb_batch_pipeline(h, cutoff, pbc_dims, b0, b0 + nf, out + 5 * f0);
+    });
 }
 
 int mb_batch_fit(MbCtx* h, size_t ref_frame, size_t f0, size_t f1, int superpose, double* rmsd_out) {

@@ -636,16 +636,22 @@ static int com_gyr(Ctx* c, const uint64_t* ids, size_t n, double out8[8]) {
 }
 
 // ---- batch (device-resident trajectory) ------------------------------------------------------
+// ref_frame == SIZE_MAX: keep the reference frame already staged in batch_ref (streaming: the ring no longer holds it)
 int batch_fit_impl(Ctx* c, size_t ref_frame, size_t f0, size_t f1, int superpose, double* rmsd_out) {
-    if (!c->batch.p || f1 > c->batch_frames || f0 >= f1 || ref_frame >= c->batch_frames)
+    const bool keep_ref = ref_frame == (size_t)-1;
+    if (!c->batch.p || f1 > c->batch_frames || f0 >= f1 || (!keep_ref && ref_frame >= c->batch_frames))
         return fail(MB_ERR_ARG, "batch_fit: bad frame range");
+    if (keep_ref && c->batch_ref.cap < c->batch_atoms * 3 * sizeof(float))
+        return fail(MB_ERR_STATE, "batch_fit: no reference frame staged");
     MB_CUDA(cudaSetDevice(c->device));
     if (!c->masses.p || c->n_masses < c->batch_atoms) return fail(MB_ERR_STATE, "masses not set for the batch");
     const size_t n = c->batch_atoms, nf = f1 - f0;
     // private copy of the reference frame: it may itself be superposed in place below
-    MB_TRY(c->batch_ref.reserve(n * 3 * sizeof(float)));
-    MB_CUDA(cudaMemcpyAsync(c->batch_ref.p, c->batch.as<float>() + ref_frame * n * 3, n * 3 * sizeof(float),
-                            cudaMemcpyDeviceToDevice, c->stream));
+    if (!keep_ref) {
+        MB_TRY(c->batch_ref.reserve(n * 3 * sizeof(float)));
+        MB_CUDA(cudaMemcpyAsync(c->batch_ref.p, c->batch.as<float>() + ref_frame * n * 3, n * 3 * sizeof(float),
+                                cudaMemcpyDeviceToDevice, c->stream));
+    }
     const float* ref = c->batch_ref.as<float>();
     // ---- fused persistent path (TMA-staged slices; 12 B/atom read + 12 B/atom written per frame) ----
     {

@@ -191,3 +191,25 @@ def test_batch_pipeline_config5_shape(mb):
             ij, d, dims = orc.search_single(1.2, xyz, None, b, 7, 8)
             assert int(rows[f, 4]) == len(orc.canonical_pairs(ij))
     t.close()
+
+
+def test_stream_fit_and_pipeline_host_frames(mb):
+    """mb_stream_fit / mb_stream_pipeline: host frames uploaded chunk by chunk; results equal the resident-batch path."""
+    n, nf = 40_000, 21
+    frames = np.stack([orc.synth_frame(SEED + 9, f, n, M) for f in range(nf)])
+    m = orc.synth_masses(SEED + 9, n)
+    a = mb.Trajectory()
+    a.upload(frames, box=M, masses=m)
+    want_rmsd = a.fit(ref_frame=0, superpose=True)
+    b = mb.Trajectory()
+    got_rmsd = b.stream_fit(frames, m)
+    assert np.allclose(got_rmsd, want_rmsd, rtol=1e-12, atol=1e-12)
+    rc, R, t = orc.fit_transform(frames[5], m, None, frames[0], m, None)
+    rc, r5 = orc.rmsd(orc.apply_transform_f64(frames[5], None, R, t).astype(np.float32), None, frames[0], None)
+    assert abs(got_rmsd[5] - r5) / r5 < 1e-5
+    a.upload(frames, box=M, masses=m)
+    want = a.pipeline(1.2)
+    got = b.stream_pipeline(frames, 1.2, M, masses=m)
+    assert np.allclose(got, want, rtol=1e-12, atol=0)
+    a.close()
+    b.close()
