@@ -111,6 +111,15 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def dist_env():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -174,7 +183,7 @@ def run_reference(args, wl):
                                    f"CPU algorithm (MolAR is Rust; no cargo in this image)"},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -256,8 +265,8 @@ def run_ours(args, wl):
 
     if args.no_e2e:
         if rank == 0:
-            print(json.dumps({"tuning": True, "opts": args.opts, "value": fps, "ms_per_frame": ms / (F * args.steps),
-                              "search_kernel_ms": k_ms / max(k_n, 1), "workload": args.workload}))
+            emit({"tuning": True, "opts": args.opts, "value": fps, "ms_per_frame": ms / (F * args.steps),
+                              "search_kernel_ms": k_ms / max(k_n, 1), "workload": args.workload})
         traj.close()
         if world > 1:
             dist.destroy_process_group()
@@ -389,7 +398,7 @@ def run_ours(args, wl):
             line["cpu_baseline"] = {"value": cfps, "unit": "frames/s", "cores": nthreads, "kind": "port",
                                     "sample": f"{nfr} frames of the same workload ({cdt:.1f} s); C++ restatement "
                                               f"of MolAR's CPU algorithm, not MolAR itself"}
-        print(json.dumps(line))
+        emit(line)
     traj.close()
     sysm.close()
     if refsys:
@@ -412,6 +421,12 @@ def main():
     ap.add_argument("--opts", default="", help="library tuning options, e.g. subdiv_x=3,slice_x=2 (tuning runs only)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
+    # stdout must carry exactly ONE JSON line: native libraries (NCCL prints its version banner there) write to
+    # fd 1 directly, so fd 1 is pointed at stderr and the JSON line goes to a private copy of the real stdout
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     import __graft_entry__
     __graft_entry__.build()
     if args.impl == "reference":
