@@ -24,6 +24,8 @@
  *   mb_inertia            Measure::inertia[_pbc] + do_inertia             measure.rs:88-98,228-238,573-610
  *   mb_principal_transform  Measure::principal_transform[_pbc]            measure.rs:100-108,240-252,645-649
  *   mb_batch_*            the per-frame loop AnalysisTask::run drives     analysis_task.rs:113-280
+ *   mb_connectivity       SearchConnectivity::from_iter                   connectivity.rs:8-38
+ *   mb_unwrap_connectivity  Modify::unwrap_connectivity[_dim]             modify.rs:64-131
  *   mb_batch_load_traj    DcdFileHandler::read_state / XtcFileHandler::read_state (+ molly's XTC codec)
  *                                                                         io/dcd_handler.rs:204-300,389-464; io/xtc_handler.rs:64-110
  *
@@ -153,6 +155,20 @@ int mb_gyration_pbc(MbCtx* ctx, const uint64_t* ids, size_t n, double* out);
 int mb_inertia(MbCtx* ctx, const uint64_t* ids, size_t n, int pbc, double moments3[3], double axes9_colmajor[9]);
 /* p' = R p + t rotates the selection about its centre of mass onto its principal axes */
 int mb_principal_transform(MbCtx* ctx, const uint64_t* ids, size_t n, int pbc, double R9_colmajor[9], double t3[3]);
+
+/* ---- pair-list consumers that stay on the device --------------------------------------------
+ * Adjacency (atom -> neighbours, both directions) of the LAST pair list of this context as CSR over the index
+ * space [0, n_index): returns the number of entries (2 x pairs); row_ptr_out (n_index + 1 entries) may be NULL;
+ * the neighbour lists follow with mb_fill_connectivity.  Order inside a row is unspecified (as in the reference). */
+int64_t mb_connectivity(MbCtx* ctx, size_t n_index, uint64_t* row_ptr_out);
+int mb_fill_connectivity(MbCtx* ctx, uint64_t* cols_out);
+/* unwrap_connectivity_dim: contact graph of the selection at `cutoff` (periodic in all dims), every atom moved to
+ * its closest image (image_dims) next to the atom it is reached from, walking from the lowest-index atom of each
+ * component; coordinates change in place on the device (mb_get_frame).  roots_out[k] (may be NULL) = position within
+ * the selection of the start atom of k's component.  Returns the number of components (start atoms).  Components and
+ * start atoms are the reference's; positions agree with any traversal order up to f32 rounding. */
+int64_t mb_unwrap_connectivity(MbCtx* ctx, float cutoff, const uint64_t* ids, size_t n, uint8_t image_dims,
+                               int64_t* roots_out);
 
 /* ---- batched, device-resident trajectory (what the benchmark drives) -------------------- */
 /* Allocate n_frames x n_atoms x 3 f32 on the device and fill it with the synthetic generator

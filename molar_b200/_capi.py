@@ -44,6 +44,9 @@ SIGNATURES = {
     "mb_rmsd": (C.c_int, [C.c_void_p, u64p, C.c_size_t, u64p, C.c_size_t, C.c_int, C.c_int, f64p]),
     "mb_fit_transform": (C.c_int, [C.c_void_p, u64p, C.c_size_t, u64p, C.c_size_t, C.c_int, C.c_int, f64p, f64p]),
     "mb_apply_transform": (C.c_int, [C.c_void_p, u64p, C.c_size_t, f64p, f64p]),
+    "mb_connectivity": (C.c_int64, [C.c_void_p, C.c_size_t, u64p]),
+    "mb_fill_connectivity": (C.c_int, [C.c_void_p, u64p]),
+    "mb_unwrap_connectivity": (C.c_int64, [C.c_void_p, C.c_float, u64p, C.c_size_t, C.c_uint8, i64p]),
     "mb_center_of_geometry": (C.c_int, [C.c_void_p, u64p, C.c_size_t, f64p]),
     "mb_center_pbc": (C.c_int, [C.c_void_p, u64p, C.c_size_t, C.c_int, C.c_uint8, f64p]),
     "mb_gyration_pbc": (C.c_int, [C.c_void_p, u64p, C.c_size_t, f64p]),

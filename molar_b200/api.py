@@ -122,6 +122,15 @@ class System:
     def launch_count(self):
         return int(self._lib.mb_launch_count(self._h))
 
+    def connectivity(self):
+        """Adjacency of the last pair list as CSR (row_ptr[n+1], cols): SearchConnectivity (connectivity.rs:8-38)."""
+        row_ptr = np.zeros(self._n + 1, np.uint64)
+        nnz = check(self._lib.mb_connectivity(self._h, self._n, row_ptr.ctypes.data_as(u64p)))
+        cols = np.zeros(nnz, np.uint64)
+        if nnz:
+            check(self._lib.mb_fill_connectivity(self._h, cols.ctypes.data_as(u64p)))
+        return row_ptr, cols
+
 
 class Sel:
     def __init__(self, system, index, n):
@@ -197,6 +206,26 @@ class Sel:
 
     def principal_transform_pbc(self):
         return self.principal_transform(pbc=True)
+
+    def unwrap_connectivity(self, cutoff, dims=None):
+        """Make every connected group of the selection whole (Modify::unwrap_connectivity_dim, modify.rs:72-131).
+        Returns, like the reference, one selection per start atom holding the atoms reached from it (the start
+        atom itself is not included and isolated atoms yield nothing)."""
+        bits = 7 if dims is None else _pbc_bits(dims)
+        p, n = self._ids()
+        roots = np.zeros(n, np.int64)
+        check(self.sys._lib.mb_unwrap_connectivity(self.sys._h, cutoff, p, n, bits, roots.ctypes.data_as(i64p)))
+        self.sys._version += 1
+        idx = self.get_index()
+        out = []
+        order = np.argsort(roots, kind="stable")
+        bounds = np.flatnonzero(np.diff(roots[order])) + 1
+        for grp in np.split(order, bounds):
+            members = grp[grp != roots[grp[0]]]
+            if members.size:
+                out.append(Sel(self.sys, idx[members].astype(np.uint64), members.size))
+        self.roots = roots
+        return out
 
     def apply_transform(self, tr):
         R9 = np.ascontiguousarray(tr.R.T.reshape(9), dtype=np.float64)

@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libmolar_b200.so")
-SOURCES = ["mb_api.cu", "mb_search.cu", "mb_measure.cu", "mb_measure_pbc.cu", "mb_batch.cu", "mb_traj.cu"]
+SOURCES = ["mb_api.cu", "mb_search.cu", "mb_measure.cu", "mb_measure_pbc.cu", "mb_batch.cu", "mb_traj.cu", "mb_connect.cu"]
 HEADERS = ["mb_common.cuh", "mb_reduce.cuh", "mb_search_lanes.cuh", os.path.join("..", "..", "include", "molar_b200.h")]
 
 NVCC_FLAGS = [

@@ -213,7 +213,7 @@ void mb_close(MbCtx* h) {
     DevBuf* bufs[] = {&c.xyz_own, &c.xyz2, &c.masses, &c.ids1, &c.ids2, &c.tmp4a, &c.tmp4b, &c.cellid_a,
                       &c.cellid_b, &c.rank_a, &c.refcell_a, &c.refcell_b, &c.sorted4, &c.cell_count,
                       &c.cell_start, &c.scan_tmp, &c.pairs, &c.dists, &c.flags, &c.out_ids, &c.counters,
-                      &c.reduce_tmp, &c.batch, &c.batch_scalars, &c.batch_tmp, &c.batch_ref, &c.pipe_tmp, &c.vdw_a, &c.vdw_b, &c.rank_b, &c.cell_count_b, &c.cell_start_b, &c.sorted4_b, &c.pbc_tmp, &c.traj_raw, &c.traj_aux};
+                      &c.reduce_tmp, &c.batch, &c.batch_scalars, &c.batch_tmp, &c.batch_ref, &c.pipe_tmp, &c.vdw_a, &c.vdw_b, &c.rank_b, &c.cell_count_b, &c.cell_start_b, &c.sorted4_b, &c.pbc_tmp, &c.traj_raw, &c.traj_aux, &c.conn_tmp, &c.conn_cols};
     for (DevBuf* b : bufs) b->release();
     for (SearchSlot& sl : c.alt) {
         DevBuf* sb[] = {&sl.tmp4a, &sl.cellid_a, &sl.rank_a, &sl.cell_count, &sl.cell_start, &sl.sorted4, &sl.scan_tmp,

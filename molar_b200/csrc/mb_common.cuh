@@ -156,6 +156,8 @@ struct Ctx {
     DevBuf batch_scalars;  // rows of doubles
     size_t batch_rows = 0, batch_row_doubles = 0;
     DevBuf batch_tmp, batch_ref, pipe_tmp;
+    DevBuf conn_tmp, conn_cols;  // pair-list consumers: CSR adjacency / union-find / BFS scratch (mb_connect.cu)
+    size_t conn_n = 0, conn_nnz = 0;
     DevBuf traj_raw, traj_aux;  // trajectory ingest: raw file bytes / decode tables (mb_traj.cu)
     double traj_h2d_ms = 0.0, traj_decode_ms = 0.0, traj_scan_ms = 0.0, traj_raw_bytes = 0.0;  // last load, CUDA events
 
@@ -207,6 +209,32 @@ __device__ __forceinline__ float d2_pbc(const DevBox& bx, float ax, float ay, fl
     }
     return best2;
 }
+// PeriodicBox::shortest_vector_dims (periodic_box.rs:286-318), f32, unfused, nalgebra gemv order
+__device__ __forceinline__ void shortest_vector_dev(const DevBox& bx, float v0, float v1, float v2, unsigned w,
+                                                    float& o0, float& o1, float& o2) {
+    float f0, f1, f2;
+    xmatvec(bx.inv, v0, v1, v2, f0, f1, f2);
+    if (w & 1u) f0 = xsub(f0, roundf(f0));
+    if (w & 2u) f1 = xsub(f1, roundf(f1));
+    if (w & 4u) f2 = xsub(f2, roundf(f2));
+    float s0, s1, s2;
+    xmatvec(bx.m, f0, f1, f2, s0, s1, s2);
+    o0 = s0;
+    o1 = s1;
+    o2 = s2;
+    if (bx.ncorr == 0 || w != 7u) return;
+    float best2 = xnorm2(s0, s1, s2);
+    for (int c = 0; c < bx.ncorr; ++c) {
+        const float c0 = xadd(s0, bx.corr[3 * c]), c1 = xadd(s1, bx.corr[3 * c + 1]), c2 = xadd(s2, bx.corr[3 * c + 2]);
+        const float n2 = xnorm2(c0, c1, c2);
+        if (n2 < best2) {
+            best2 = n2;
+            o0 = c0;
+            o1 = c1;
+            o2 = c2;
+        }
+    }
+}
 #endif  // __CUDACC__
 
 // implemented in the respective translation units
@@ -217,6 +245,8 @@ int batch_search_impl(Ctx* c, float cutoff, uint8_t pbc, size_t f0, size_t f1, i
 int enqueue_count_frame(Ctx* c, const float* xyz, size_t n, float cutoff, uint8_t pbc,
                         unsigned long long* d_counter2);
 void free_plan_cache(Ctx* c);
+// exclusive scan of n u32 on the context stream, out[n] = total (mb_search.cu)
+int exclusive_scan_u32(Ctx* c, const unsigned* in, int n, unsigned* out);
 int batch_fit_impl(Ctx* c, size_t ref_frame, size_t f0, size_t f1, int superpose, double* rmsd_out);
 int enqueue_batch_moments(Ctx* c, size_t f0, size_t f1, double* d_rows8, double* partials, unsigned* tickets,
                           int nb);

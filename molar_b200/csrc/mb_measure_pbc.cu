@@ -28,33 +28,6 @@ namespace mb {
 
 constexpr int PRED_THREADS = 256;
 
-// PeriodicBox::shortest_vector_dims (periodic_box.rs:286-318), f32, unfused, nalgebra gemv order
-__device__ __forceinline__ void shortest_vector_dev(const DevBox& bx, float v0, float v1, float v2, unsigned w,
-                                                    float& o0, float& o1, float& o2) {
-    float f0, f1, f2;
-    xmatvec(bx.inv, v0, v1, v2, f0, f1, f2);
-    if (w & 1u) f0 = xsub(f0, roundf(f0));
-    if (w & 2u) f1 = xsub(f1, roundf(f1));
-    if (w & 4u) f2 = xsub(f2, roundf(f2));
-    float s0, s1, s2;
-    xmatvec(bx.m, f0, f1, f2, s0, s1, s2);
-    o0 = s0;
-    o1 = s1;
-    o2 = s2;
-    if (bx.ncorr == 0 || w != 7u) return;
-    float best2 = xnorm2(s0, s1, s2);
-    for (int c = 0; c < bx.ncorr; ++c) {
-        const float c0 = xadd(s0, bx.corr[3 * c]), c1 = xadd(s1, bx.corr[3 * c + 1]), c2 = xadd(s2, bx.corr[3 * c + 2]);
-        const float n2 = xnorm2(c0, c1, c2);
-        if (n2 < best2) {
-            best2 = n2;
-            o0 = c0;
-            o1 = c1;
-            o2 = c2;
-        }
-    }
-}
-
 struct PbcRedParams {
     const float* xyz;
     const unsigned long long* ids;

@@ -277,7 +277,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(const unsigned
     if (blockIdx.x == gridDim.x - 1 && threadIdx.x == SCAN_THREADS - 1) out[n] = ex;
 }
 
-static int exclusive_scan_u32(Ctx* c, const unsigned* in, int n, unsigned* out) {
+int exclusive_scan_u32(Ctx* c, const unsigned* in, int n, unsigned* out) {
     int ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
     MB_TRY(c->scan_tmp.reserve((size_t)ntiles * sizeof(unsigned)));
     unsigned* ts = c->scan_tmp.as<unsigned>();

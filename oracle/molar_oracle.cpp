@@ -644,6 +644,62 @@ OrcResult* orc_search_single_pbc(float cutoff, const float* xyz, const uint64_t*
     return res;
 }
 
+// Modify::unwrap_connectivity_dim (modify.rs:72-131) with SearchConnectivity::from_iter (connectivity.rs:18-37).
+// xyz: whole frame, modified in place for the selected atoms.  roots_out[k] (k = position in the selection) = the
+// position of the atom the walk that reached k started from (its own position for a start atom).  The reference
+// returns one selection per start atom holding every atom reached from it — NOT the start atom itself
+// (`sel_vec` only receives discovered atoms) and nothing for isolated atoms.  Returns the number of start atoms.
+// The neighbour order inside an atom's list is the pair order of the search (serial plan order here; whatever
+// rayon produced in the reference), so the spanning tree — and with it the last bits of the unwrapped coordinates —
+// is not a defined quantity of the reference; the components are.
+int64_t orc_unwrap_connectivity(float cutoff, float* xyz, const uint64_t* ids, size_t n, const OrcBox* box,
+                                uint8_t dims, int nthreads, int64_t* roots_out) {
+    std::vector<float> pos(3 * n);
+    for (size_t k = 0; k < n; ++k) {
+        size_t id = ids ? (size_t)ids[k] : k;
+        for (int d = 0; d < 3; ++d) pos[3 * k + d] = xyz[3 * id + d];
+    }
+    OrcResult* r = orc_search_single_pbc(cutoff, pos.data(), nullptr, n, box, PBC_FULL, nthreads);
+    std::vector<std::vector<size_t>> conn(n);
+    for (const Triple& t : r->triples) {
+        conn[t.i].push_back(t.j);
+        conn[t.j].push_back(t.i);
+    }
+    orc_result_free(r);
+    std::vector<char> used(n, 0);
+    std::vector<size_t> todo;
+    int64_t nstart = 0;
+    size_t next_unused = 0;
+    while (true) {
+        while (next_unused < n && used[next_unused]) ++next_unused;  // find_position(|el| !el): lowest unused index
+        if (next_unused >= n) break;
+        const size_t root = next_unused;
+        todo.push_back(root);
+        used[root] = 1;
+        roots_out[root] = (int64_t)root;
+        ++nstart;
+        while (!todo.empty()) {
+            const size_t c = todo.back();
+            todo.pop_back();
+            const Vf p0 = {{pos[3 * c], pos[3 * c + 1], pos[3 * c + 2]}};
+            for (size_t ind : conn[c]) {
+                if (used[ind]) continue;
+                const Vf p = {{pos[3 * ind], pos[3 * ind + 1], pos[3 * ind + 2]}};
+                const Vf im = add(p0, shortest_vector_dims(box->b, sub(p, p0), dims));  // closest_image_dims
+                for (int d = 0; d < 3; ++d) pos[3 * ind + d] = im[d];
+                todo.push_back(ind);
+                used[ind] = 1;
+                roots_out[ind] = (int64_t)root;
+            }
+        }
+    }
+    for (size_t k = 0; k < n; ++k) {
+        size_t id = ids ? (size_t)ids[k] : k;
+        for (int d = 0; d < 3; ++d) xyz[3 * id + d] = pos[3 * k + d];
+    }
+    return nstart;
+}
+
 // distance_search.rs:659-698
 OrcResult* orc_search_double(float cutoff, const float* xyz1, const uint64_t* ids1, size_t n1,
                              const float* xyz2, const uint64_t* ids2, size_t n2, int nthreads) {

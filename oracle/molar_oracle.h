@@ -75,6 +75,12 @@ OrcResult* orc_search_within_pbc(float cutoff, const float* xyz1, const uint64_t
 OrcResult* orc_search_double_vdw(const float* xyz1, const uint64_t* ids1, size_t n1, const float* vdw1,
                                  const float* xyz2, const uint64_t* ids2, size_t n2, const float* vdw2,
                                  const OrcBox* box, uint8_t pbc_dims, int nthreads);
+/* Modify::unwrap_connectivity_dim (modify.rs:72-131): contact graph at `cutoff` (periodic search, all dims), walk
+   from the lowest unused atom, every reached atom moved to its closest image (`dims`) next to the atom it was
+   reached from.  xyz is modified in place; roots_out[k] = position (within the selection) of the start atom of
+   k's walk.  Returns the number of start atoms.  See the .cpp for what is and is not defined by the reference. */
+int64_t orc_unwrap_connectivity(float cutoff, float* xyz, const uint64_t* ids, size_t n, const OrcBox* box,
+                                uint8_t dims, int nthreads, int64_t* roots_out);
 /* Measure::min_max (measure.rs:22-36) followed by the +-cutoff+EPS padding the `within`
    AST node applies (selection/ast.rs:598-600). */
 void orc_within_bounds(float cutoff, const float* xyz, const uint64_t* ids, size_t n,

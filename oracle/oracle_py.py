@@ -69,6 +69,9 @@ def lib():
         L.orc_search_double_vdw.restype = C.c_void_p
         L.orc_search_double_vdw.argtypes = [_f32p, _u64p, C.c_size_t, _f32p, _f32p, _u64p, C.c_size_t, _f32p,
                                             C.c_void_p, C.c_uint8, C.c_int]
+        L.orc_unwrap_connectivity.argtypes = [C.c_float, _f32p, _u64p, C.c_size_t, C.c_void_p, C.c_uint8, C.c_int,
+                                              C.POINTER(C.c_int64)]
+        L.orc_unwrap_connectivity.restype = C.c_int64
         L.orc_within_bounds.argtypes = [C.c_float, _f32p, _u64p, C.c_size_t, _f32p, _f32p]
         for suf, fp in (("f32", _f32p), ("f64", _f64p)):
             getattr(L, "orc_center_of_mass_" + suf).argtypes = [_f32p, _f32p, _u64p, C.c_size_t, fp]
@@ -313,6 +316,17 @@ def gyration(xyz, masses, ids=None, prec="f64"):
     out = np.zeros(1, np.float64 if prec == "f64" else np.float32)
     rc = _measure("gyration", prec)(xp, mp, ip, n, out.ctypes.data_as(_f64p if prec == "f64" else _f32p))
     return rc, float(out[0])
+
+
+def unwrap_connectivity(cutoff, xyz, box, ids=None, dims=7, nthreads=4):
+    """-> (unwrapped copy of xyz, roots[n]: start atom of each selected atom's walk, number of start atoms)"""
+    x = np.ascontiguousarray(xyz, dtype=np.float32).copy()
+    i, ip = _ids(ids)
+    n = len(i) if i is not None else x.size // 3
+    roots = np.zeros(n, np.int64)
+    ns = lib().orc_unwrap_connectivity(cutoff, x.ctypes.data_as(_f32p), ip, n, box.h, dims, nthreads,
+                                       roots.ctypes.data_as(C.POINTER(C.c_int64)))
+    return x, roots, int(ns)
 
 
 _PREC = {"f32": 0, "f64": 1, "mixed": 2}
