@@ -49,9 +49,11 @@ def test_connectivity_csr_vs_pair_list(mb):
     s.close()
 
 
-@pytest.mark.parametrize("n_mol,n_per", [(40, 60), (3, 2000), (500, 3)])
-def test_unwrap_connectivity_vs_oracle(mb, n_mol, n_per):
-    L = 5.0
+@pytest.mark.parametrize("n_mol,n_per,L", [(40, 60, 5.0), (3, 2000, 24.0), (500, 3, 5.0)])
+def test_unwrap_connectivity_vs_oracle(mb, n_mol, n_per, L):
+    # (3, 2000): long chains, deep walk (hundreds of levels); the box is large enough that a chain never touches
+    # its own periodic image — otherwise the contact graph has loops around the box and "the" unwrapped position
+    # is ambiguous by a lattice vector in the reference as well
     box = np.diag([L, L, L]).astype(np.float32)
     whole, wrapped = _chains(n_mol, n_per, L, seed=n_mol)
     want_xyz, want_roots, want_n = orc.unwrap_connectivity(0.2, wrapped, orc.Box(matrix=box))

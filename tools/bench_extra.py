@@ -128,6 +128,53 @@ def bench_xtc(mb, T, n, frames):
              "input_synthesis_s": enc_s}]
 
 
+def bench_connect(mb, orc, n):
+    """CSR adjacency of the 1.2 nm pair list, and unwrap of a water-like system (3-atom molecules, 0.12 nm bonds)."""
+    out = []
+    box = TRIC
+    xyz = orc.synth_frame(20260, 0, n, box)
+    s = mb.System(xyz, box=box)
+    s.set_option("with_dist", 0)
+    lib, h = s._lib, s._h
+    npairs = mb._capi.check(lib.mb_search_single(h, 1.2, None, n, 7))
+    t0 = time.perf_counter()
+    nnz = mb._capi.check(lib.mb_connectivity(h, n, None))
+    ms = (time.perf_counter() - t0) * 1e3
+    out.append({"workload": f"SearchConnectivity (CSR) of the 1.2 nm pair list, {n} atoms, {npairs} pairs",
+                "metric": "calls/sec", "value": 1e3 / ms, "unit": "calls/s", "ms_per_call": ms,
+                "roofline": roof(8.0 * npairs * 2 + 8.0 * npairs, ms, "csr_count_kernel + scan + csr_fill_kernel "
+                                 "(pairs read twice, 2P neighbour ids written; wall clock of the synchronous call)"),
+                "cpu_baseline": None})
+    s.close()
+    rng = np.random.default_rng(2)
+    L = (n / 100.0) ** (1.0 / 3.0)
+    nmol = n // 3
+    o = rng.random((nmol, 3)) * L
+    w = np.repeat(o, 3, axis=0) + rng.normal(0.0, 0.03, (3 * nmol, 3))
+    wrapped = np.mod(w, L).astype(np.float32)
+    bx = np.diag([L, L, L]).astype(np.float32)
+    s = mb.System(wrapped, box=bx)
+    sel = s()
+    t0 = time.perf_counter()
+    roots = np.zeros(len(wrapped), np.int64)
+    ncomp = mb._capi.check(s._lib.mb_unwrap_connectivity(s._h, 0.12, None, len(wrapped), 7,
+                                                         roots.ctypes.data_as(mb._capi.i64p)))
+    ms = (time.perf_counter() - t0) * 1e3
+    t0 = time.perf_counter()
+    sub = wrapped[: min(len(wrapped), 150_000)]
+    orc.unwrap_connectivity(0.12, sub, orc.Box(matrix=bx))
+    cpu_ms = (time.perf_counter() - t0) * 1e3 * len(wrapped) / len(sub)
+    out.append({"workload": f"unwrap_connectivity, {len(wrapped)} atoms in 3-atom molecules, cutoff 0.12 nm "
+                            f"({ncomp} components)", "metric": "calls/sec", "value": 1e3 / ms, "unit": "calls/s",
+                "ms_per_call": ms,
+                "roofline": roof(24.0 * len(wrapped), ms, "search + CSR + union-find + unwrap_bfs_kernel (whole call, "
+                                 "wall clock; algorithmic bytes = frame read + written)"),
+                "cpu_baseline": {"value": 1e3 / cpu_ms, "unit": "calls/s", "cores": 4, "kind": "port",
+                                 "sample": f"oracle on the first {len(sub)} atoms, scaled linearly"}})
+    s.close()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--atoms", type=int, default=1_000_000)
@@ -141,6 +188,8 @@ def main():
     lines = []
     if a.only in ("", "pbc"):
         lines += bench_pbc(mb, orc, a.atoms, a.reps)
+    if a.only in ("", "connect"):
+        lines += bench_connect(mb, orc, a.atoms)
     if a.only in ("", "dcd"):
         lines += bench_dcd(mb, T, a.atoms, a.frames)
     if a.only in ("", "xtc"):
