@@ -27,3 +27,23 @@ t = mb.Trajectory(); t.synth(1, 0, 4, 8000, M, mass_seed=1)
 c = t.search(1.2); c2 = t.search(1.2, count_only=True); rows = t.pipeline(1.2); rr = t.fit(0)
 t.set_option("fused_fit", 1); rr2 = t.fit(0)
 print("ok", len(p), len(p2), len(w), len(p3), len(p4), c.tolist(), c2.tolist(), float(r))
+# ---- round 2 additions: lane kernel, periodic reductions, inertia, trajectory ingest, pair-list consumers ----
+from oracle import traj_oracle as T
+s2 = mb.System(xyz, masses=m, box=M)
+s2.set_option("lane_kernel", 1)
+pl, dl = mb.distance_search(1.2, s2(), dims=[True] * 3)                   # lane kernel, pairs + dist
+s2.set_option("with_dist", 0)
+npl2 = mb._capi.check(s2._lib.mb_search_single(s2._h, 1.2, None, n, 7))    # lane kernel, pairs only
+pl2 = np.empty((npl2, 2), np.uint64); mb._capi.check(s2._lib.mb_fill_pairs(s2._h, pl2.ctypes.data, None))
+rp, cols = s2.connectivity()                                               # CSR adjacency
+cp = s2().com(dims=[True] * 3); cg = s2().cog(dims=[True, False, True]); gp = s2().gyration(pbc=True)
+mom, ax = s2().inertia(pbc=True); mom2, ax2 = s2().inertia(); ptr = s2().principal_transform()
+sels = s2(np.arange(0, n, 2, dtype=np.uint64)).unwrap_connectivity(0.25)   # union-find + persistent BFS kernel
+fr = np.stack([xyz, xyz[::-1].copy(), xyz])
+tt = mb.Trajectory(); cs = tt.stream_search(fr, 1.2, M); rf = tt.stream_fit(fr, m); pp = tt.stream_pipeline(fr, 1.2, M, masses=m)
+ang = T.write_dcd(fr, boxes=[np.array([50.0, 0, 50.0, 0, 0, 50.0])] * 3, fixed=[1, 5, 77])
+td = mb.load_trajectory(ang, "dcd"); fd = td.frames()
+xb = T.write_xtc_frame(np.abs(xyz), M) + T.write_xtc_frame(np.abs(xyz[:7]), M)[:0]
+tx = mb.load_trajectory(xb, "xtc"); fx = tx.frames()
+print("ok2", len(pl), len(pl2), len(cols), cp.tolist(), float(gp), mom.tolist(), len(sels), cs.tolist(), fd.shape, fx.shape)
+assert len(pl) == len(p) and len(pl2) == len(p)
