@@ -72,6 +72,7 @@ struct SearchParams {
     unsigned long long pair_cap;
     unsigned long long* counter;  // [0] pairs found, [1] work counter (as u64)
     unsigned long long n_sortedB;  // atoms in the candidate set
+    float one;                     // 1.0f, opaque to ptxas: multiplier of the exact packed sums (see d2_pair_fma)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -160,6 +161,10 @@ __global__ void __launch_bounds__(256) bin_atoms_kernel(const float* __restrict_
                 sub[d] = subcell(u, loc[d], g.k[d]);
             }
         }
+        // Atoms with a non-finite coordinate: the reference bins them (NaN casts to cell 0) but no comparison
+        // with them is ever true, so they are in no pair.  They are left out here, which keeps NaNs away from the
+        // distance loop (it reads a sign bit instead of comparing).
+        if (!(isfinite(p[0]) && isfinite(p[1]) && isfinite(p[2]))) skip = true;
         if (!skip) {
             int fx = loc[0] * g.k[0] + sub[0], fy = loc[1] * g.k[1] + sub[1], fz = loc[2] * g.k[2] + sub[2];
             cell = (unsigned)(fx + g.fd[0] * (fy + g.fd[1] * fz));
@@ -408,6 +413,25 @@ __device__ __forceinline__ void d2_pair(unsigned long long nx, unsigned long lon
     d1 = xadd(xadd(x1, y1), z1);
 }
 
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+// rc2 - ((dx*dx + dy*dy) + dz*dz) for two neighbours, every operation rounded on its own, all packed.
+// The sums are fma(s, 1.0, t) = round(s + t): the same number as an add, but a PACKED add fed by a packed
+// multiply is contracted by ptxas into FFMA2 (one rounding instead of two), while a fused multiply-add whose
+// multiplier is a run-time 1.0 is left alone.  The sign bit of each half answers d2 <= rc2 (no NaNs reach
+// this: non-finite atoms are dropped at binning and the padding is finite): clear = within the cutoff.
+__device__ __forceinline__ unsigned long long rc2_minus_d2(unsigned long long nx, unsigned long long ny,
+                                                           unsigned long long nz, const float4& h,
+                                                           unsigned long long one2, unsigned long long rc22) {
+    const unsigned long long dx = sub2(nx, pk2(h.x, h.x)), dy = sub2(ny, pk2(h.y, h.y)), dz = sub2(nz, pk2(h.z, h.z));
+    const unsigned long long xx = mul2(dx, dx), yy = mul2(dy, dy), zz = mul2(dz, dz);
+    const unsigned long long s = fma2(fma2(xx, one2, yy), one2, zz);
+    return sub2(rc22, s);
+}
+
 // Out-of-line copy of the exact periodic distance for the rare paths of the cell kernel (band
 // resolution, distance output of wrapped pairs): keeps the hot loop inside the instruction cache.
 __device__ __noinline__ float d2_pbc_call(const DevBox& bx, float ax, float ay, float az, float bxx, float byy,
@@ -532,7 +556,9 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32, 4) search_cells_kernel(cons
     const int hx = g.hx, tdx = fdx / hx;  // tiles per x-row
     const unsigned ntiles = (unsigned)(tdx * fdy * fdz);
     const float rc2 = P.rc2;
-    const float qnan = __int_as_float(0x7fc00000);
+    // padding of unused home slots / candidate lanes: finite and 2e18 apart, so a padded test is never a hit and
+    // never produces a NaN (the direct path reads the SIGN of rc2 - d2)
+    const float pad_home = 1.0e18f, pad_cand = -1.0e18f;
     const float finf = __int_as_float(0x7f800000);
 
     for (;;) {
@@ -618,14 +644,14 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32, 4) search_cells_kernel(cons
             for (unsigned hb = hs; hb < he; hb += 32) {
                 const int nh = min(32u, he - hb);
                 __syncwarp();
-                ws.home[lane] = (lane < (unsigned)nh) ? __ldg(&P.sorted[hb + lane]) : make_float4(qnan, 0.f, 0.f, 0.f);
+                ws.home[lane] = (lane < (unsigned)nh) ? __ldg(&P.sorted[hb + lane]) : make_float4(pad_home, pad_home, pad_home, 0.f);
                 __syncwarp();
                 unsigned cur0 = 0, cur1 = 0;
                 unsigned hit_any = 0;  // MODE 3: bit j = home atom j has a set-2 atom within the cutoff
 #pragma unroll 1
                 for (unsigned c0 = 0; c0 < T; c0 += 64) {
                     const unsigned p0 = c0 + lane, p1 = p0 + 32;
-                    float4 n0 = make_float4(qnan, 0.f, 0.f, 0.f), n1 = n0;  // NaN: never within cutoff
+                    float4 n0 = make_float4(pad_cand, pad_cand, pad_cand, 0.f), n1 = n0;  // never within the cutoff
                     unsigned f0 = 0, f1 = 0, a0i = 0, a1i = 0;
                     if (p0 < T) {
                         while (ws.rpos[cur0 + 1] <= p0) ++cur0;
@@ -641,6 +667,7 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32, 4) search_cells_kernel(cons
                         n1 = __ldg(&P.sortedB[a1i]);
                     }
                     unsigned m0 = 0, m1 = 0;
+                    const unsigned valid_slots = nh >= 32 ? 0xffffffffu : ((1u << nh) - 1u);
                     if (!__any_sync(0xffffffffu, (f0 | f1) != 0u)) {
                         // ---- all 64 candidates come from un-wrapped cell pairs: direct difference ----
                         // x + 0 is exact: the FADD2 only serves to give each packed coordinate its own aligned
@@ -648,19 +675,25 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32, 4) search_cells_kernel(cons
                         const unsigned long long zz2 = pk2(0.f, 0.f);
                         const unsigned long long nx = add2(pk2(n0.x, n1.x), zz2), ny = add2(pk2(n0.y, n1.y), zz2),
                                                  nz = add2(pk2(n0.z, n1.z), zz2);
+                        // Home slots are visited from the top down and each test pushes its "not within" bit
+                        // (the sign of rc2 - d2) into the accumulators with one funnel shift, so that slot j ends
+                        // up at bit j.
+                        const unsigned long long one2 = pk2_once(P.one, P.one), rc22 = pk2_once(rc2, rc2);
+                        const int nh4 = (nh + 3) & ~3;
+                        unsigned a0 = 0, a1 = 0;
 #pragma unroll 1
-                        for (int gj = 0; gj < nh; gj += 4) {
-                            unsigned l0 = 0, l1 = 0;
+                        for (int gj = nh4 - 4; gj >= 0; gj -= 4) {
 #pragma unroll
-                            for (int jj = 0; jj < 4; ++jj) {
-                                float d0, d1;
-                                d2_pair(nx, ny, nz, home[gj + jj], d0, d1);
-                                if (d0 <= rc2) l0 |= 1u << jj;
-                                if (d1 <= rc2) l1 |= 1u << jj;
+                            for (int jj = 3; jj >= 0; --jj) {
+                                const unsigned long long t = rc2_minus_d2(nx, ny, nz, home[gj + jj], one2, rc22);
+                                float t0, t1;
+                                upk2(t, t0, t1);
+                                a0 = __funnelshift_l(__float_as_uint(t0), a0, 1);
+                                a1 = __funnelshift_l(__float_as_uint(t1), a1, 1);
                             }
-                            m0 |= l0 << gj;
-                            m1 |= l1 << gj;
                         }
+                        m0 = ~a0 & valid_slots;
+                        m1 = ~a1 & valid_slots;
                     } else {
                         // ---- mixed step: self cell (index-order filter) and/or wrapped cell pairs.
                         // Wrapped candidates are tested on the lattice-shifted image; outside the band
@@ -702,8 +735,12 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32, 4) search_cells_kernel(cons
                             m0 |= l0 << gj; m1 |= l1 << gj;
                             b0 |= u0 << gj; b1 |= u1 << gj;
                         }
-                        b0 ^= m0;
-                        b1 ^= m1;
+                        // unused home slots hold finite padding: with the unbounded band of the exact mode (hi = inf)
+                        // they would qualify for a re-evaluation, so they are masked out here
+                        m0 &= valid_slots;
+                        m1 &= valid_slots;
+                        b0 = (b0 & valid_slots) ^ m0;
+                        b1 = (b1 & valid_slots) ^ m1;
                         while (b0) {
                             const int j = bfind32(b0);
                             b0 ^= 1u << j;
@@ -1613,6 +1650,7 @@ int enqueue_cells_search(Ctx* c, const float* xyz, const unsigned long long* d_i
     P.flags = nullptr;
     P.g = g;
     P.rc2 = cutoff * cutoff;
+    P.one = 1.0f;
     P.rc2_lo = pl.rc2_lo;
     P.rc2_hi = pl.rc2_hi;
     P.fast_pbc = pl.fast_pbc;
@@ -1664,6 +1702,7 @@ static int enqueue_cells_search2(Ctx* c, const float* xyz1, const unsigned long 
     P.flags = c->flags.as<unsigned char>();
     P.g = g;
     P.rc2 = cutoff * cutoff;
+    P.one = 1.0f;
     P.rc2_lo = pl.rc2_lo;
     P.rc2_hi = pl.rc2_hi;
     P.fast_pbc = pl.fast_pbc;
