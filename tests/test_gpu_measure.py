@@ -213,3 +213,24 @@ def test_stream_fit_and_pipeline_host_frames(mb):
     assert np.allclose(got, want, rtol=1e-12, atol=0)
     a.close()
     b.close()
+
+
+def test_stream_entry_points_multi_chunk_500k(mb):
+    """500k-atom frames: the streaming calls work in several chunks (ring of two chunks, upload of chunk k+1
+    overlapped with the work on chunk k); every result must equal the resident-batch path."""
+    n, nf = 500_000, 10
+    box = np.diag([17.0, 17.0, 17.3]).astype(np.float32)
+    frames = np.stack([orc.synth_frame(SEED + 21, f, n, box) for f in range(nf)])
+    m = orc.synth_masses(SEED + 21, n)
+    a = mb.Trajectory()
+    a.upload(frames, box=box, masses=m)
+    want_counts = a.search(1.2, count_only=True)
+    want_rows = a.pipeline(1.2)
+    want_rmsd = a.fit(ref_frame=0, superpose=True)
+    a.close()
+    b = mb.Trajectory()
+    assert np.array_equal(b.stream_search(frames, 1.2, box), want_counts)
+    assert np.array_equal(b.stream_search(frames, 1.2, box, count_only=True), want_counts)
+    assert np.allclose(b.stream_pipeline(frames, 1.2, box, masses=m), want_rows, rtol=1e-12, atol=0)
+    assert np.allclose(b.stream_fit(frames, m), want_rmsd, rtol=1e-12, atol=1e-12)
+    b.close()

@@ -313,10 +313,10 @@ def test_config3_1m_triclinic_properties(mb):
 
 
 def test_single_pbc_dense_system_multipass_emission(mb):
-    """600 atoms/nm^3: one 64-candidate step finds more pairs than the per-warp staging buffer holds,
+    """450 atoms/nm^3: one 64-candidate step finds more pairs than the per-warp staging buffer holds,
     so the masks are expanded in several passes."""
     M = np.diag([3.7, 3.8, 3.9]).astype(np.float32)
-    xyz = orc.synth_frame(SEED + 13, 0, 32000, M, stray_permille=10)
+    xyz = orc.synth_frame(SEED + 13, 0, 24000, M, stray_permille=10)
     op, od, dims = oracle_single(1.2, xyz, box=M, pbc=7, nthreads=8)
     assert list(dims) == [3, 3, 3]
     for opts in ({}, {"subdiv": 1}, {"with_dist": 0}):
