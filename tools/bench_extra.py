@@ -194,7 +194,7 @@ def main():
         lines += bench_dcd(mb, T, a.atoms, a.frames)
     if a.only in ("", "xtc"):
         lines += bench_xtc(mb, T, min(a.atoms, 150_000), max(a.frames, 256))
-        lines += bench_xtc(mb, T, a.atoms, a.frames)
+        lines += bench_xtc(mb, T, a.atoms, max(a.frames, 96))
     for ln in lines:
         print(json.dumps(ln))
 
