@@ -234,8 +234,8 @@ int64_t mb_connectivity(MbCtx* h, size_t n_index, uint64_t* row_ptr_out) {
     if (!h) return fail(MB_ERR_ARG, "null context");
     Ctx* c = &h->c;
     MB_CUDA(cudaSetDevice(c->device));
-    unsigned *rp, *cols;
-    size_t nnz;
+    unsigned *rp = nullptr, *cols = nullptr;
+    size_t nnz = 0;
     MB_TRY(build_csr(c, n_index, &rp, &cols, &nnz));
     if (row_ptr_out) {
         MB_TRY(c->out_ids.reserve((n_index + 1) * sizeof(unsigned long long)));
@@ -281,8 +281,8 @@ int64_t mb_unwrap_connectivity(MbCtx* h, float cutoff, const uint64_t* ids, size
     // scratch after the CSR words: label[N] cand[N] frontier0[N] frontier1[N] count[8] visited[N] member[N]
     const size_t csr_words = 2 * (N + 2);
     MB_TRY(c->conn_tmp.reserve((csr_words + 4 * N + 8) * sizeof(unsigned) + 2 * N + 64));
-    unsigned *rp, *cols;
-    size_t nnz;
+    unsigned *rp = nullptr, *cols = nullptr;
+    size_t nnz = 0;
     MB_TRY(build_csr(c, N, &rp, &cols, &nnz));
     unsigned* base = c->conn_tmp.as<unsigned>() + csr_words;
     unsigned* label = base;

@@ -526,6 +526,77 @@ struct __align__(16) WarpShared {
     unsigned char rflag[MAX_RUNS];   // w | sgn << 3 | RUN_SELF
 };
 
+// Phase A of both pair kernels: lanes work on different neighbour rows of the home tile and append their runs
+// (contiguous ranges of the sorted candidate array) to the warp's run table, direct runs of a batch of 32 rows
+// first, wrapped runs after them; `first` adds the self run in front.  Fills rows from row0 on until all rows are
+// in or the table (MAXR entries) is full; returns the number of runs (nr) and of candidates (T) and advances row0.
+template <int MAXR>
+__device__ __forceinline__ void fill_run_table(const SearchParams& P, unsigned* __restrict__ rstart,
+                                               unsigned* __restrict__ rpos, unsigned char* __restrict__ rflag, int fx,
+                                               int fy, int fz, int cx, int cy, int cz, unsigned hs, unsigned he,
+                                               bool first, unsigned lane, int& row0, unsigned& nr, unsigned& T) {
+    const GridSpec& g = P.g;
+    nr = 0;
+    T = 0;
+    __syncwarp();
+    if (first && !P.two_sets) {
+        if (lane == 0) {
+            rstart[0] = hs;
+            rpos[0] = 0;
+            rflag[0] = RUN_SELF;
+        }
+        nr = 1;
+        T = he - hs;
+    }
+#pragma unroll 1
+    while (row0 < P.nrows) {
+        const int ri = row0 + (int)lane;
+        NbrRow row = P.rows[min(ri, P.nrows - 1)];
+        // pass 1: count runs and atoms per class (direct / wrapped)
+        unsigned nd = 0, nw = 0, ld = 0, lw = 0;
+        if (ri < P.nrows)
+            gen_row_runs(g, fx, fy, fz, cx, cy, cz, row, [&](int c0, int c1, unsigned f) {
+                unsigned len = P.cell_startB[c1 + 1] - P.cell_startB[c0];
+                if (len) {
+                    if (f & 7u) { ++nw; lw += len; } else { ++nd; ld += len; }
+                }
+            });
+        // warp scans: counts packed (direct low 16, wrapped high 16), lengths separately
+        unsigned cn = nd | (nw << 16), cni = cn, ldi = ld, lwi = lw;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned t0 = __shfl_up_sync(0xffffffffu, cni, o), t1 = __shfl_up_sync(0xffffffffu, ldi, o),
+                     t2 = __shfl_up_sync(0xffffffffu, lwi, o);
+            if (lane >= (unsigned)o) { cni += t0; ldi += t1; lwi += t2; }
+        }
+        const unsigned tot_c = __shfl_sync(0xffffffffu, cni, 31);
+        const unsigned tot_d = tot_c & 0xffffu, tot_w = tot_c >> 16;
+        const unsigned tot_ld = __shfl_sync(0xffffffffu, ldi, 31), tot_lw = __shfl_sync(0xffffffffu, lwi, 31);
+        if (nr + tot_d + tot_w > (unsigned)MAXR) break;  // table full: process it first
+        // pass 2: write this lane's runs (direct runs of the batch first, then wrapped ones)
+        unsigned sd = nr + (cni & 0xffffu) - nd, sw = nr + tot_d + (cni >> 16) - nw;
+        unsigned pd = T + ldi - ld, pw = T + tot_ld + lwi - lw;
+        if (ri < P.nrows)
+            gen_row_runs(g, fx, fy, fz, cx, cy, cz, row, [&](int c0, int c1, unsigned f) {
+                unsigned s = P.cell_startB[c0], len = P.cell_startB[c1 + 1] - s;
+                if (len) {
+                    if (f & 7u) {
+                        rstart[sw] = s; rpos[sw] = pw; rflag[sw] = (unsigned char)f;
+                        ++sw; pw += len;
+                    } else {
+                        rstart[sd] = s; rpos[sd] = pd; rflag[sd] = (unsigned char)f;
+                        ++sd; pd += len;
+                    }
+                }
+            });
+        nr += tot_d + tot_w;
+        T += tot_ld + tot_lw;
+        row0 += 32;
+    }
+    if (lane == 0) rpos[nr] = T;
+    __syncwarp();
+}
+
 // One warp per home tile = hx consecutive fine cells along x (dynamic work counter).
 //  Phase A  lanes work on different neighbour rows in parallel and build a table of runs: contiguous
 //           ranges of the sorted atom array (self cell, then direct runs, then wrapped runs).
@@ -580,64 +651,8 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32, 4) search_cells_kernel(cons
 #pragma unroll 1
         do {
             // ---------------- Phase A: fill the run table ----------------
-            unsigned nr = 0, T = 0;
-            __syncwarp();
-            if (first && !P.two_sets) {
-                if (lane == 0) {
-                    ws.rstart[0] = hs;
-                    ws.rpos[0] = 0;
-                    ws.rflag[0] = RUN_SELF;
-                }
-                nr = 1;
-                T = he - hs;
-            }
-#pragma unroll 1
-            while (row0 < P.nrows) {
-                const int ri = row0 + (int)lane;
-                NbrRow row = P.rows[min(ri, P.nrows - 1)];
-                // pass 1: count runs and atoms per class (direct / wrapped)
-                unsigned nd = 0, nw = 0, ld = 0, lw = 0;
-                if (ri < P.nrows)
-                    gen_row_runs(g, fx, fy, fz, cx, cy, cz, row, [&](int c0, int c1, unsigned f) {
-                        unsigned len = P.cell_startB[c1 + 1] - P.cell_startB[c0];
-                        if (len) {
-                            if (f & 7u) { ++nw; lw += len; } else { ++nd; ld += len; }
-                        }
-                    });
-                // warp scans: counts packed (direct low 16, wrapped high 16), lengths separately
-                unsigned cn = nd | (nw << 16), cni = cn, ldi = ld, lwi = lw;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    unsigned t0 = __shfl_up_sync(0xffffffffu, cni, o), t1 = __shfl_up_sync(0xffffffffu, ldi, o),
-                             t2 = __shfl_up_sync(0xffffffffu, lwi, o);
-                    if (lane >= (unsigned)o) { cni += t0; ldi += t1; lwi += t2; }
-                }
-                const unsigned tot_c = __shfl_sync(0xffffffffu, cni, 31);
-                const unsigned tot_d = tot_c & 0xffffu, tot_w = tot_c >> 16;
-                const unsigned tot_ld = __shfl_sync(0xffffffffu, ldi, 31), tot_lw = __shfl_sync(0xffffffffu, lwi, 31);
-                if (nr + tot_d + tot_w > (unsigned)MAX_RUNS) break;  // table full: process it first
-                // pass 2: write this lane's runs (direct runs of the batch first, then wrapped ones)
-                unsigned sd = nr + (cni & 0xffffu) - nd, sw = nr + tot_d + (cni >> 16) - nw;
-                unsigned pd = T + ldi - ld, pw = T + tot_ld + lwi - lw;
-                if (ri < P.nrows)
-                    gen_row_runs(g, fx, fy, fz, cx, cy, cz, row, [&](int c0, int c1, unsigned f) {
-                        unsigned s = P.cell_startB[c0], len = P.cell_startB[c1 + 1] - s;
-                        if (len) {
-                            if (f & 7u) {
-                                ws.rstart[sw] = s; ws.rpos[sw] = pw; ws.rflag[sw] = (unsigned char)f;
-                                ++sw; pw += len;
-                            } else {
-                                ws.rstart[sd] = s; ws.rpos[sd] = pd; ws.rflag[sd] = (unsigned char)f;
-                                ++sd; pd += len;
-                            }
-                        }
-                    });
-                nr += tot_d + tot_w;
-                T += tot_ld + tot_lw;
-                row0 += 32;
-            }
-            if (lane == 0) ws.rpos[nr] = T;
-            __syncwarp();
+            unsigned nr, T;
+            fill_run_table<MAX_RUNS>(P, ws.rstart, ws.rpos, ws.rflag, fx, fy, fz, cx, cy, cz, hs, he, first, lane, row0, nr, T);
 
             // ---------------- Phase B: consume the stream ----------------
 #pragma unroll 1

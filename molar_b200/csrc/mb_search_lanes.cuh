@@ -178,62 +178,10 @@ __global__ void __launch_bounds__(LANE_WARPS * 32, 3) search_lanes_kernel(const 
         bool first = true;
 #pragma unroll 1
         do {
-            // ---------------- Phase A: run table (as in search_cells_kernel) ----------------
-            unsigned nr = 0, T = 0;
-            __syncwarp();
-            if (first && !P.two_sets) {
-                if (lane == 0) {
-                    ws.rstart[0] = hs;
-                    ws.rpos[0] = 0;
-                    ws.rflag[0] = RUN_SELF;
-                }
-                nr = 1;
-                T = he - hs;
-            }
-#pragma unroll 1
-            while (row0 < P.nrows) {
-                const int ri = row0 + (int)lane;
-                NbrRow row = P.rows[min(ri, P.nrows - 1)];
-                unsigned nd = 0, nw = 0, ld = 0, lw = 0;
-                if (ri < P.nrows)
-                    gen_row_runs(g, fx, fy, fz, cx, cy, cz, row, [&](int c0, int c1, unsigned f) {
-                        unsigned len = P.cell_startB[c1 + 1] - P.cell_startB[c0];
-                        if (len) {
-                            if (f & 7u) { ++nw; lw += len; } else { ++nd; ld += len; }
-                        }
-                    });
-                unsigned cn = nd | (nw << 16), cni = cn, ldi = ld, lwi = lw;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    unsigned t0 = __shfl_up_sync(0xffffffffu, cni, o), t1 = __shfl_up_sync(0xffffffffu, ldi, o),
-                             t2 = __shfl_up_sync(0xffffffffu, lwi, o);
-                    if (lane >= (unsigned)o) { cni += t0; ldi += t1; lwi += t2; }
-                }
-                const unsigned tot_c = __shfl_sync(0xffffffffu, cni, 31);
-                const unsigned tot_d = tot_c & 0xffffu, tot_w = tot_c >> 16;
-                const unsigned tot_ld = __shfl_sync(0xffffffffu, ldi, 31), tot_lw = __shfl_sync(0xffffffffu, lwi, 31);
-                if (nr + tot_d + tot_w > (unsigned)LANE_MAX_RUNS) break;
-                unsigned sd = nr + (cni & 0xffffu) - nd, sw = nr + tot_d + (cni >> 16) - nw;
-                unsigned pd = T + ldi - ld, pw = T + tot_ld + lwi - lw;
-                if (ri < P.nrows)
-                    gen_row_runs(g, fx, fy, fz, cx, cy, cz, row, [&](int c0, int c1, unsigned f) {
-                        unsigned s = P.cell_startB[c0], len = P.cell_startB[c1 + 1] - s;
-                        if (len) {
-                            if (f & 7u) {
-                                ws.rstart[sw] = s; ws.rpos[sw] = pw; ws.rflag[sw] = (unsigned char)f;
-                                ++sw; pw += len;
-                            } else {
-                                ws.rstart[sd] = s; ws.rpos[sd] = pd; ws.rflag[sd] = (unsigned char)f;
-                                ++sd; pd += len;
-                            }
-                        }
-                    });
-                nr += tot_d + tot_w;
-                T += tot_ld + tot_lw;
-                row0 += 32;
-            }
-            if (lane == 0) ws.rpos[nr] = T;
-            __syncwarp();
+            // ---------------- Phase A: run table (shared with search_cells_kernel) ----------------
+            unsigned nr, T;
+            fill_run_table<LANE_MAX_RUNS>(P, ws.rstart, ws.rpos, ws.rflag, fx, fy, fz, cx, cy, cz, hs, he, first, lane, row0, nr,
+                                          T);
 
             // ---------------- Phase B: every lane tests its home atom against the stream ----------------
 #pragma unroll 1
