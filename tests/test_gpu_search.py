@@ -374,3 +374,49 @@ def test_stream_search_host_frames(mb):
     assert np.array_equal(counts, counts2)
     traj.close()
     s.close()
+
+
+@pytest.mark.parametrize("case", ["ortho", "tric", "exact_small_z", "two_sets"])
+def test_lane_kernel_option_parity(mb, case):
+    """search_lanes_kernel (option lane_kernel=1, one home atom per lane): same pair sets and distances as the oracle
+    on the direct, wrapped (filtered and exact) and two-set paths."""
+    if case == "ortho":
+        M = np.diag([6.0, 7.0, 8.0]).astype(np.float32)
+    elif case == "tric":
+        M = (TRIC * np.float32(0.3)).astype(np.float32)
+    else:
+        L = 6.0
+        M = np.array([[L, 0, L / 2], [0, L, L / 2], [0, 0, L / np.sqrt(2)]], np.float32)
+    xyz = orc.synth_frame(SEED + 31, 0, 26000, M, stray_permille=10)
+    if case == "two_sets":
+        from molar_b200.api import within
+        b = orc.Box(matrix=M)
+        ids1 = np.arange(0, 26000, 2, dtype=np.uint64)
+        ids2 = np.arange(1, 26000, 3, dtype=np.uint64)
+        ij, d, _ = orc.search_double(1.0, xyz, ids1, xyz, ids2, b, 7, 8)
+        op, od = orc.ordered_pairs(ij, d)
+        s = mb.System(xyz, box=M)
+        s.set_option("lane_kernel", 1)
+        s.set_option("two_set_cells_min", 0)
+        pairs, dist = mb.distance_search(1.0, s(ids1), s(ids2), dims=[True] * 3)
+        gp, gd = orc.ordered_pairs(pairs, dist)
+        assert len(gp) == len(pairs)
+        assert_same_pairs(gp, gd, op, od)
+        inner = np.arange(100, 400, dtype=np.uint64)
+        ref_ids = orc.search_within(0.7, xyz, None, xyz, inner, box=b, pbc=7, nthreads=4)
+        assert np.array_equal(within(0.7, s(), s(inner), dims=7), np.unique(ref_ids))
+        s.close()
+        return
+    op, od, dims = oracle_single(1.2, xyz, box=M, pbc=7)
+    gp, gd = run_single(mb, xyz, 1.2, box=M, dims=[True] * 3, lane_kernel=1)
+    assert_same_pairs(gp, gd, op, od)
+    # pairs-only mode and the count-only mode of the same kernel
+    s = mb.System(xyz, box=M)
+    s.set_option("lane_kernel", 1)
+    s.set_option("with_dist", 0)
+    cnt = mb._capi.check(s._lib.mb_search_single(s._h, 1.2, None, len(xyz), 7))
+    pairs = np.empty((cnt, 2), np.uint64)
+    mb._capi.check(s._lib.mb_fill_pairs(s._h, pairs.ctypes.data, None))
+    assert np.array_equal(orc.canonical_pairs(pairs), op)
+    assert mb._capi.check(s._lib.mb_count_single(s._h, 1.2, None, len(xyz), 7)) == len(op)
+    s.close()
