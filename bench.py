@@ -320,7 +320,7 @@ def run_ours(args, wl):
     # the trajectory-loop entry points: host frames in, per-frame results out, uploads overlapped with the work on
     # the previous chunk (mb_stream_*; the reference overlaps IO with analysis the same way, io.rs:209-233)
     e2e_extra["per_call_value"] = e2e_fps
-    ns = {"search": 8, "fit": 128, "pipeline": 8}[kind] if n >= 500_000 else 64
+    ns = {"search": 32, "fit": 128, "pipeline": 8}[kind] if n >= 500_000 else 64
     blockh = torch.from_numpy(np.stack([host[f % e2e_frames].numpy() for f in range(ns)])).pin_memory()
     st = mb.Trajectory(device=local)
     for kv in filter(None, args.opts.split(",")):

@@ -198,7 +198,7 @@ int mb_stream_search(MbCtx* h, float cutoff, uint8_t pbc_dims, const float* fram
     if (!h || !frames || n_frames == 0 || n_atoms == 0) return fail(MB_ERR_ARG, "mb_stream_search: bad argument");
     Ctx& c = h->c;
     MB_TRY(stream_box(c, box9));
-    return stream_chunks(c, frames, n_frames, n_atoms, n_atoms >= 500000 ? 4 : 32, [&](size_t b0, size_t nf, size_t f0) {
+    return stream_chunks(c, frames, n_frames, n_atoms, n_atoms >= 500000 ? 8 : 32, [&](size_t b0, size_t nf, size_t f0) {
         return batch_search_impl(&c, cutoff, pbc_dims & 7, b0, b0 + nf, mode, counts ? counts + f0 : nullptr, nullptr);
     });
 }
