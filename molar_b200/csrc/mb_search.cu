@@ -516,6 +516,7 @@ __device__ __forceinline__ void gen_row_runs(const GridSpec& g, int fx, int fy, 
 }
 
 constexpr int MAX_RUNS = 224;        // >= 1 + 32 rows * 6 runs
+constexpr int RUN_BITMAP_WORDS = 96;  // 3072 stream positions: the run of a candidate is found by a popcount
 constexpr unsigned RUN_SELF = 0x40u;  // flag bit: the home cell itself (pairs counted once by index order)
 
 // per-warp shared memory
@@ -524,6 +525,7 @@ struct __align__(16) WarpShared {
     unsigned rstart[MAX_RUNS];       // first atom (index into sorted4) of each run
     unsigned rpos[MAX_RUNS + 4];     // stream position of each run (exclusive prefix of run lengths)
     unsigned char rflag[MAX_RUNS];   // w | sgn << 3 | RUN_SELF
+    unsigned rbits[RUN_BITMAP_WORDS];  // bit p set <=> a run starts at stream position p (p < 32 * RUN_BITMAP_WORDS)
 };
 
 // Phase A of both pair kernels: lanes work on different neighbour rows of the home tile and append their runs
@@ -534,16 +536,26 @@ template <int MAXR>
 __device__ __forceinline__ void fill_run_table(const SearchParams& P, unsigned* __restrict__ rstart,
                                                unsigned* __restrict__ rpos, unsigned char* __restrict__ rflag, int fx,
                                                int fy, int fz, int cx, int cy, int cz, unsigned hs, unsigned he,
-                                               bool first, unsigned lane, int& row0, unsigned& nr, unsigned& T) {
+                                               bool first, unsigned lane, int& row0, unsigned& nr, unsigned& T,
+                                               unsigned* __restrict__ rbits = nullptr) {
     const GridSpec& g = P.g;
     nr = 0;
     T = 0;
     __syncwarp();
+    if (rbits) {
+#pragma unroll
+        for (int k = 0; k < RUN_BITMAP_WORDS / 32; ++k) rbits[k * 32 + lane] = 0u;
+        __syncwarp();
+    }
+    auto mark = [&](unsigned pos) {
+        if (rbits && pos < 32u * RUN_BITMAP_WORDS) atomicOr(&rbits[pos >> 5], 1u << (pos & 31u));
+    };
     if (first && !P.two_sets) {
         if (lane == 0) {
             rstart[0] = hs;
             rpos[0] = 0;
             rflag[0] = RUN_SELF;
+            mark(0u);
         }
         nr = 1;
         T = he - hs;
@@ -582,9 +594,11 @@ __device__ __forceinline__ void fill_run_table(const SearchParams& P, unsigned* 
                 if (len) {
                     if (f & 7u) {
                         rstart[sw] = s; rpos[sw] = pw; rflag[sw] = (unsigned char)f;
+                        mark(pw);
                         ++sw; pw += len;
                     } else {
                         rstart[sd] = s; rpos[sd] = pd; rflag[sd] = (unsigned char)f;
+                        mark(pd);
                         ++sd; pd += len;
                     }
                 }
@@ -652,7 +666,9 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32, 4) search_cells_kernel(cons
         do {
             // ---------------- Phase A: fill the run table ----------------
             unsigned nr, T;
-            fill_run_table<MAX_RUNS>(P, ws.rstart, ws.rpos, ws.rflag, fx, fy, fz, cx, cy, cz, hs, he, first, lane, row0, nr, T);
+            fill_run_table<MAX_RUNS>(P, ws.rstart, ws.rpos, ws.rflag, fx, fy, fz, cx, cy, cz, hs, he, first, lane, row0, nr, T,
+                                     ws.rbits);
+            const bool use_bits = T <= 32u * RUN_BITMAP_WORDS;  // every run start is in the bitmap
 
             // ---------------- Phase B: consume the stream ----------------
 #pragma unroll 1
@@ -662,21 +678,34 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32, 4) search_cells_kernel(cons
                 ws.home[lane] = (lane < (unsigned)nh) ? __ldg(&P.sorted[hb + lane]) : make_float4(pad_home, pad_home, pad_home, 0.f);
                 __syncwarp();
                 unsigned cur0 = 0, cur1 = 0;
+                unsigned runs_before = 0;  // run starts at stream positions < c0 (bitmap path)
+                const unsigned le_mask = (2u << lane) - 1u;
                 unsigned hit_any = 0;  // MODE 3: bit j = home atom j has a set-2 atom within the cutoff
 #pragma unroll 1
                 for (unsigned c0 = 0; c0 < T; c0 += 64) {
                     const unsigned p0 = c0 + lane, p1 = p0 + 32;
                     float4 n0 = make_float4(pad_cand, pad_cand, pad_cand, 0.f), n1 = n0;  // never within the cutoff
                     unsigned f0 = 0, f1 = 0, a0i = 0, a1i = 0;
+                    if (use_bits) {
+                        // run index of a stream position = (run starts at positions <= it) - 1: two broadcast words
+                        // and a popcount instead of a per-lane search
+                        const unsigned w0 = ws.rbits[c0 >> 5], w1 = ws.rbits[(c0 >> 5) + 1];
+                        cur0 = runs_before + __popc(w0 & le_mask) - 1u;
+                        cur1 = runs_before + __popc(w0) + __popc(w1 & le_mask) - 1u;
+                        runs_before += __popc(w0) + __popc(w1);
+                    }
                     if (p0 < T) {
-                        while (ws.rpos[cur0 + 1] <= p0) ++cur0;
+                        if (!use_bits)
+                            while (ws.rpos[cur0 + 1] <= p0) ++cur0;
                         a0i = ws.rstart[cur0] + (p0 - ws.rpos[cur0]);
                         f0 = ws.rflag[cur0];
                         n0 = __ldg(&P.sortedB[a0i]);
                     }
                     if (p1 < T) {
-                        cur1 = max(cur1, cur0);
-                        while (ws.rpos[cur1 + 1] <= p1) ++cur1;
+                        if (!use_bits) {
+                            cur1 = max(cur1, cur0);
+                            while (ws.rpos[cur1 + 1] <= p1) ++cur1;
+                        }
                         a1i = ws.rstart[cur1] + (p1 - ws.rpos[cur1]);
                         f1 = ws.rflag[cur1];
                         n1 = __ldg(&P.sortedB[a1i]);
