@@ -216,6 +216,13 @@ int mb_batch_fit(MbCtx* ctx, size_t ref_frame, size_t f0, size_t f1, int superpo
    mb_batch_scalars_device() for an NCCL gather by the host. */
 int mb_batch_pipeline(MbCtx* ctx, float cutoff, uint8_t pbc_dims, size_t f0, size_t f1, double* out);
 const void* mb_batch_scalars_device(MbCtx* ctx, size_t* n_rows, size_t* row_doubles);
+/* Host only, no device needed: the traversal plan of the cell kernels for a periodic search of n atoms in this box.
+   out_int: [0] cell kernel usable, [1..3] reference Grid::dims, [4..6] fine cells per reference cell, [7] x slices
+   per home tile, [8..10] fine grid dims, [11] neighbour rows, [12] shifted-image filter enabled, [13] row capacity.
+   rows4_out (4 x capacity signed chars): dy, dz, dxlo, dxhi per row, relative to the first cell of the home tile.
+   out_band: [rc2_lo, rc2_hi] of the filter.  For tests of the planning logic. */
+int mb_plan_describe(const float* box9_colmajor, float cutoff, uint8_t pbc_dims, size_t n, int full_shell,
+                     int out_int[16], signed char* rows4_out, float out_band[2]);
 /* number of kernels this context has launched since it was opened (for gpu_launches) */
 uint64_t mb_launch_count(MbCtx* ctx);
 /* Instrumentation.  With option "profile"=1 every pair-search kernel launch is bracketed by CUDA

@@ -2196,6 +2196,46 @@ int64_t mb_search_within(MbCtx* h, float cutoff, const uint64_t* ids1, size_t n1
     return rc < 0 ? rc : cnt;
 }
 
+// Host only (no device needed): the traversal plan the cell kernels would use for this box / cutoff / selection
+// size — reference grid, subdivision, neighbour-row table, filter band.  Exists so that the planning logic can be
+// tested exhaustively on the CPU (tests/test_plan_host.py).
+int mb_plan_describe(const float* box9_colmajor, float cutoff, uint8_t pbc_dims, size_t n, int full_shell, int out_int[16],
+                     signed char* rows4_out, float out_band[2]) {
+    if (!box9_colmajor || !out_int) return fail(MB_ERR_ARG, "null argument");
+    if (!(cutoff > 0.0f)) return fail(MB_ERR_ARG, "cutoff must be positive");
+    Ctx c;  // plain host state: no CUDA call is made on this path
+    MB_TRY(host_box_from_colmajor(box9_colmajor, &c.box));
+    c.has_box = true;
+    Plan pl;
+    memset(&pl, 0, sizeof(pl));
+    pl.full_shell = full_shell != 0;
+    MB_TRY(make_grid_pbc(&c, cutoff, pbc_dims & 7, pl.g));
+    plan_cells(&c, pl, cutoff, n);
+    out_int[0] = pl.use_cells ? 1 : 0;
+    for (int d = 0; d < 3; ++d) {
+        out_int[1 + d] = pl.g.dims[d];
+        out_int[4 + d] = pl.g.k[d];
+        out_int[8 + d] = pl.g.fd[d];
+    }
+    out_int[7] = pl.g.hx;
+    out_int[11] = pl.nrows;
+    out_int[12] = pl.fast_pbc;
+    out_int[13] = MAX_ROWS;
+    out_int[14] = out_int[15] = 0;
+    if (rows4_out)
+        for (int r = 0; r < pl.nrows; ++r) {
+            rows4_out[4 * r] = pl.rows[r].dy;
+            rows4_out[4 * r + 1] = pl.rows[r].dz;
+            rows4_out[4 * r + 2] = pl.rows[r].dxlo;
+            rows4_out[4 * r + 3] = pl.rows[r].dxhi;
+        }
+    if (out_band) {
+        out_band[0] = pl.rc2_lo;
+        out_band[1] = pl.rc2_hi;
+    }
+    return MB_OK;
+}
+
 __global__ void widen_pairs_kernel(const uint2* __restrict__ in, unsigned long long n, ulonglong2* __restrict__ out) {
     unsigned long long k = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
     if (k < n) {
