@@ -102,3 +102,23 @@ def test_filter_band_brackets_the_cutoff_and_degenerate_grids_fall_back():
     assert describe(np.diag([2.0, 9.0, 9.0]), 1.2, 50_000)["use_cells"] == 0
     # tiny selections do not use the cell path
     assert describe(np.diag([9.0, 9.0, 9.0]), 1.2, 1000)["use_cells"] == 0
+
+
+def test_reference_grid_dims_match_the_oracle_on_random_boxes():
+    """Grid::dims = max(floor(lab_extent / cutoff), 1) with lab extents = row sums of the box matrix
+    (distance_search.rs:103-110, periodic_box.rs:369-375): the planner and the oracle must agree, including where
+    extent / cutoff lands on an integer in f32."""
+    from oracle import oracle_py as orc
+    rng = np.random.default_rng(11)
+    pts = rng.random((64, 3)).astype(np.float32)
+    boxes = [np.diag([21.6, 14.4, 9.6]), np.diag([12.0, 12.0, 12.0]), TRIC.astype(np.float64)]
+    for _ in range(40):
+        a, b, c = rng.uniform(4.0, 25.0, 3)
+        sh = rng.uniform(-0.3, 0.3, 3)
+        boxes.append(np.array([[a, sh[0] * b, sh[1] * c], [0.0, b, sh[2] * c], [0.0, 0.0, c]]))
+    for M in boxes:
+        for cutoff in (1.2, 0.8, 2.0):
+            M32 = np.asarray(M, np.float32)
+            ij, d, dims = orc.search_single(cutoff, (pts @ M32.T).astype(np.float32), None, orc.Box(matrix=M32), 7, 1)
+            pl = describe(M32, cutoff, 100_000)
+            assert list(dims) == pl["dims"], (M, cutoff, list(dims), pl["dims"])
