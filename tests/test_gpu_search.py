@@ -336,21 +336,32 @@ def test_single_pbc_dense_system_multipass_emission(mb):
         s.close()
 
 
+_BIG_BOX_ORACLE = {}
+
+
+def _big_box_case(which):
+    """oracle answer of the two big-box cases, computed once for both parametrisations"""
+    if which not in _BIG_BOX_ORACLE:
+        if which == "tric":
+            M = (TRIC * np.float32(0.45)).astype(np.float32)
+            xyz = orc.synth_frame(SEED + 11, 0, 90000, M, stray_permille=20)
+        else:
+            M = np.diag([9.7, 10.3, 11.1]).astype(np.float32)
+            xyz = orc.synth_frame(SEED + 12, 0, 100000, M, stray_permille=20)
+        op, od, dims = oracle_single(1.2, xyz, box=M, pbc=7, nthreads=8)
+        _BIG_BOX_ORACLE[which] = (M, xyz, op, od, dims)
+    return _BIG_BOX_ORACLE[which]
+
+
 @pytest.mark.parametrize("exact", [0, 1])
 def test_single_pbc_big_box_filter_vs_exact_path(mb, exact):
     """Boxes large enough for the wrapped-pair filter (>= 4 reference cells per dim), strays
     included, against the oracle."""
-    M = (TRIC * np.float32(0.45)).astype(np.float32)
-    xyz = orc.synth_frame(SEED + 11, 0, 90000, M, stray_permille=20)
-    op, od, dims = oracle_single(1.2, xyz, box=M, pbc=7, nthreads=8)
-    assert min(dims) >= 4
-    gp, gd = run_single(mb, xyz, 1.2, box=M, dims=[True] * 3, exact_pbc=exact)
-    assert_same_pairs(gp, gd, op, od)
-    Mo = np.diag([9.7, 10.3, 11.1]).astype(np.float32)
-    xyz = orc.synth_frame(SEED + 12, 0, 100000, Mo, stray_permille=20)
-    op, od, dims = oracle_single(1.2, xyz, box=Mo, pbc=7, nthreads=8)
-    gp, gd = run_single(mb, xyz, 1.2, box=Mo, dims=[True] * 3, exact_pbc=exact)
-    assert_same_pairs(gp, gd, op, od)
+    for which in ("tric", "ortho"):
+        M, xyz, op, od, dims = _big_box_case(which)
+        assert min(dims) >= 4
+        gp, gd = run_single(mb, xyz, 1.2, box=M, dims=[True] * 3, exact_pbc=exact)
+        assert_same_pairs(gp, gd, op, od)
 
 
 def test_stream_search_host_frames(mb):
