@@ -644,6 +644,66 @@ OrcResult* orc_search_single_pbc(float cutoff, const float* xyz, const uint64_t*
     return res;
 }
 
+// Count + order-independent checksum of distance_search_single_pbc's output (distance_search.rs:928-954), computed
+// inside the worker pool WITHOUT materialising the pair list, so that the 3.6e8 pairs of a 1M-atom frame can be
+// compared with the CUDA path (mb_pairs_checksum / mb_batch_search checksums2: the same hash).  Every emitted
+// triple is hashed as mix64((min(i,j) << 32) | max(i,j)); out3 = {count, sum of hashes mod 2^64, xor of hashes}.
+static inline uint64_t orc_mix64(uint64_t x) {
+    x ^= x >> 33;
+    x *= 0xff51afd7ed558ccdULL;
+    x ^= x >> 33;
+    x *= 0xc4ceb9fe1a85ec53ULL;
+    x ^= x >> 33;
+    return x;
+}
+void orc_search_single_pbc_checksum(float cutoff, const float* xyz, const uint64_t* ids, size_t n, const OrcBox* box,
+                                    uint8_t pbc_dims, int nthreads, uint64_t* out3, uint64_t* dims3) {
+    Grid grid;
+    size_t sz[3];
+    Grid::dims_from_cutoff_and_extents(cutoff, lab_extents(box->b), sz);
+    grid.init(sz);
+    grid.populate_pbc(xyz, ids, n, box->b, pbc_dims);
+    auto plan = search_plan(grid, nullptr, pbc_dims);
+    const float c2 = cutoff * cutoff;
+    if (nthreads < 1) nthreads = 1;
+    std::vector<uint64_t> acc((size_t)nthreads * 3, 0);
+    std::atomic<size_t> next{0};
+    auto worker = [&](int t) {
+        uint64_t cnt = 0, sum = 0, x = 0;
+        std::vector<Triple> buf;
+        for (;;) {
+            size_t b = next.fetch_add(3);  // chunks of 3 plan entries (with_min_len(3), :950)
+            if (b >= plan.size()) break;
+            size_t e = std::min(plan.size(), b + 3);
+            for (size_t k = b; k < e; ++k) {
+                buf.clear();
+                search_cell_pair_single(c2, grid, plan[k].c1, plan[k].c2, plan[k].wrapped, &box->b, buf);
+                for (const Triple& tr : buf) {
+                    uint64_t lo = std::min(tr.i, tr.j), hi = std::max(tr.i, tr.j);
+                    uint64_t h = orc_mix64((lo << 32) | hi);
+                    ++cnt;
+                    sum += h;
+                    x ^= h;
+                }
+            }
+        }
+        acc[3 * t] = cnt;
+        acc[3 * t + 1] = sum;
+        acc[3 * t + 2] = x;
+    };
+    std::vector<std::thread> th;
+    for (int t = 0; t < nthreads; ++t) th.emplace_back(worker, t);
+    for (auto& t : th) t.join();
+    out3[0] = out3[1] = out3[2] = 0;
+    for (int t = 0; t < nthreads; ++t) {
+        out3[0] += acc[3 * t];
+        out3[1] += acc[3 * t + 1];
+        out3[2] ^= acc[3 * t + 2];
+    }
+    if (dims3)
+        for (int d = 0; d < 3; ++d) dims3[d] = sz[d];
+}
+
 // Modify::unwrap_connectivity_dim (modify.rs:72-131) with SearchConnectivity::from_iter (connectivity.rs:18-37).
 // xyz: whole frame, modified in place for the selected atoms.  roots_out[k] (k = position in the selection) = the
 // position of the atom the walk that reached k started from (its own position for a start atom).  The reference

@@ -69,6 +69,11 @@ OrcResult* orc_search_within(float cutoff, const float* xyz1, const uint64_t* id
 OrcResult* orc_search_within_pbc(float cutoff, const float* xyz1, const uint64_t* ids1, size_t n1,
                                  const float* xyz2, const uint64_t* ids2, size_t n2,
                                  const OrcBox* box, uint8_t pbc_dims, int nthreads); /* :560-598 */
+/* distance_search_single_pbc (:928-954) reduced to {count, sum, xor} of mix64((min(i,j)<<32)|max(i,j)) over every
+   emitted pair — the hash of mb_pairs_checksum — without materialising the list (full-size parity of config 3). */
+void orc_search_single_pbc_checksum(float cutoff, const float* xyz, const uint64_t* ids, size_t n,
+                                    const OrcBox* box, uint8_t pbc_dims, int nthreads, uint64_t* out3,
+                                    uint64_t* dims3 /* may be NULL */);
 /* van der Waals search (distance_search.rs:767-879): per-pair cutoff vdw1[i]+vdw2[j]+EPSILON, grid cutoff
    max(vdw1)+max(vdw2)+EPSILON; vdw arrays are per SELECTED atom and the returned indices are LOCAL
    (position within the selection), as in the reference.  box==NULL or pbc_dims==0: non-periodic. */

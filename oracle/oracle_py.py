@@ -55,6 +55,9 @@ def lib():
         L.orc_search_single.argtypes = [C.c_float, _f32p, _u64p, C.c_size_t, C.c_int]
         L.orc_search_single_pbc.restype = C.c_void_p
         L.orc_search_single_pbc.argtypes = [C.c_float, _f32p, _u64p, C.c_size_t, C.c_void_p, C.c_uint8, C.c_int]
+        L.orc_search_single_pbc_checksum.restype = None
+        L.orc_search_single_pbc_checksum.argtypes = [C.c_float, _f32p, _u64p, C.c_size_t, C.c_void_p, C.c_uint8, C.c_int,
+                                                      _u64p, _u64p]
         L.orc_search_double.restype = C.c_void_p
         L.orc_search_double.argtypes = [C.c_float, _f32p, _u64p, C.c_size_t, _f32p, _u64p, C.c_size_t, C.c_int]
         L.orc_search_double_pbc.restype = C.c_void_p
@@ -201,6 +204,41 @@ def search_single(cutoff, xyz, ids=None, box=None, pbc=0, nthreads=1):
     else:
         h = lib().orc_search_single(cutoff, xp, ip, n, nthreads)
     return _take_pairs(h)
+
+
+def mix64(x):
+    """The pair hash of checksum_kernel / orc_search_single_pbc_checksum, vectorised (numpy uint64, wrapping)."""
+    x = np.asarray(x, np.uint64).copy()
+    with np.errstate(over="ignore"):
+        x ^= x >> np.uint64(33)
+        x *= np.uint64(0xff51afd7ed558ccd)
+        x ^= x >> np.uint64(33)
+        x *= np.uint64(0xc4ceb9fe1a85ec53)
+        x ^= x >> np.uint64(33)
+    return x
+
+
+def pairs_checksum(ij):
+    """(count, sum, xor) of mix64((min<<32)|max) over a pair list, as mb_pairs_checksum computes it."""
+    ij = np.asarray(ij, np.uint64).reshape(-1, 2)
+    lo, hi = ij.min(1), ij.max(1)
+    h = mix64((lo << np.uint64(32)) | hi)
+    with np.errstate(over="ignore"):
+        s = int(h.sum(dtype=np.uint64)) if len(h) else 0
+    x = int(np.bitwise_xor.reduce(h)) if len(h) else 0
+    return len(h), s, x
+
+
+def search_single_pbc_checksum(cutoff, xyz, box, pbc=7, ids=None, nthreads=1):
+    """count, sum, xor, grid dims of distance_search_single_pbc without materialising the pair list."""
+    x, xp = _f32(xyz)
+    i, ip = _ids(ids)
+    n = len(i) if i is not None else x.size // 3
+    out = np.zeros(3, np.uint64)
+    dims = np.zeros(3, np.uint64)
+    lib().orc_search_single_pbc_checksum(cutoff, xp, ip, n, box.h, pbc, nthreads, out.ctypes.data_as(_u64p),
+                                         dims.ctypes.data_as(_u64p))
+    return int(out[0]), int(out[1]), int(out[2]), [int(d) for d in dims]
 
 
 def search_double(cutoff, xyz1, ids1, xyz2, ids2, box=None, pbc=0, nthreads=1):

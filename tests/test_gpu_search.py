@@ -312,6 +312,36 @@ def test_config3_1m_triclinic_properties(mb):
     t.close()
 
 
+@pytest.mark.parametrize("stray", [0, 10])
+def test_config3_1m_triclinic_vs_oracle_checksum(mb, stray):
+    """The headline configuration at FULL size against the oracle: one 1M-atom frame of the config-3 triclinic box
+    (13 x 15 x 17 reference grid), with and without 1 % stray atoms.  The oracle hashes every pair it emits inside its
+    worker pool (count, sum and xor of mix64((min << 32) | max) — the hash of checksum_kernel), so the 3.6e8 pairs
+    never have to be materialised on the host.  distance_search.rs:928-954."""
+    n = 1_000_000
+    xyz = orc.synth_frame(SEED, 3, n, TRIC, stray_permille=stray)
+    cnt, ssum, sxor, dims = orc.search_single_pbc_checksum(1.2, xyz, orc.Box(matrix=TRIC), 7, nthreads=os.cpu_count() or 4)
+    assert dims == [13, 15, 17]
+    t = mb.Trajectory()
+    t.synth(SEED, 3, 1, n, TRIC, stray_permille=stray)
+    assert np.array_equal(t.frame(0), xyz)
+    counts, chk = t.search(1.2, checksums=True)
+    assert int(counts[0]) == cnt
+    assert int(chk[0, 0]) == ssum and int(chk[0, 1]) == sxor
+    # the count-only kernel (config 5's contact count) at full size
+    assert int(t.search(1.2, count_only=True)[0]) == cnt
+    # ... and through the per-call entry point with the pair list checksummed on the device
+    t.close()
+    import ctypes as C
+    s = mb.System(xyz, box=TRIC)
+    s.set_option("with_dist", 0)
+    assert s._lib.mb_search_single(s._h, 1.2, None, n, 7) == cnt
+    out2 = (C.c_uint64 * 2)()
+    assert s._lib.mb_pairs_checksum(s._h, out2) == 0
+    assert (int(out2[0]), int(out2[1])) == (ssum, sxor)
+    s.close()
+
+
 def test_single_pbc_dense_system_multipass_emission(mb):
     """450 atoms/nm^3: one 64-candidate step finds more pairs than the per-warp staging buffer holds,
     so the masks are expanded in several passes."""

@@ -187,3 +187,26 @@ def test_double_vdw_vs_bruteforce():
         assert len(got) == len(bi)
         assert np.array_equal(got, np.stack([bi, bj], 1).astype(np.uint64))
         assert got[:, 0].max() < len(ids1) and got[:, 1].max() < len(ids2)  # local indices
+
+
+def test_checksum_variant_equals_hash_of_materialised_pairs():
+    """orc_search_single_pbc_checksum (used for the full-size config-3 parity test on the GPU) must be the
+    count / sum / xor of mix64 over exactly the pairs orc_search_single_pbc materialises."""
+    import numpy as np
+    from oracle import oracle_py as orc
+    M = (np.array([[21.5, -2.7, -2.7], [0.0, 21.5, -2.7], [0.0, 0.0, 21.5]], np.float32) * np.float32(0.3)).astype(np.float32)
+    box = orc.Box(matrix=M)
+    for stray in (0, 20):
+        xyz = orc.synth_frame(20260, 1, 27000, M, stray_permille=stray)
+        ij, d, dims = orc.search_single(1.2, xyz, None, box, 7, 4)
+        want = orc.pairs_checksum(ij)
+        for nt in (1, 4):
+            cnt, ssum, sxor, dims2 = orc.search_single_pbc_checksum(1.2, xyz, box, 7, nthreads=nt)
+            assert (cnt, ssum, sxor) == want and list(dims2) == [int(v) for v in dims]
+    # the vectorised hash equals the scalar definition
+    x = 0x0000000500000007
+    def mix(v):
+        m = (1 << 64) - 1
+        v ^= v >> 33; v = (v * 0xff51afd7ed558ccd) & m; v ^= v >> 33; v = (v * 0xc4ceb9fe1a85ec53) & m; v ^= v >> 33
+        return v
+    assert int(orc.mix64(np.array([x], np.uint64))[0]) == mix(x)
