@@ -3,11 +3,11 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl ours|reference]
 
-One rank per GPU (torchrun for N>1), frames sharded across ranks (weak scaling: every rank owns
-`--frames` resident frames and one step = one pass of the hot path over all of them).  Prints ONE
-JSON line on rank 0.  torch is used for plumbing only (torch.distributed barrier / NCCL gather of
-the per-frame scalars, CUDA events on the library's own stream); every number is produced by
-libmolar_b200.so through its C ABI.
+One rank per GPU (torchrun launches the processes for N>1), frames sharded across ranks (weak scaling:
+every rank owns `--frames` resident frames and one step = one pass of the hot path over all of them).
+Prints ONE JSON line on rank 0.  Everything — kernels, CUDA-event timing, the NCCL communicator, the
+gather of the per-frame scalars, barrier and max over ranks — goes through libmolar_b200.so's C ABI;
+torch is not imported.
 
 Workloads (BASELINE.json configs):
   search1m   configs[2]  1M-atom triclinic box, 1.2 nm neighbour-pair enumeration   (default, headline)
@@ -164,6 +164,8 @@ def cpu_frames_per_sec(wl, n_frames, nthreads, first_frame=0, budget_s=60.0):
 
 
 def run_reference(args, wl):
+    """The reference's own CPU path for this workload on the host cores (oracle port: MolAR is Rust and there is
+    no cargo here).  Loads nothing of the product: no libmolar_b200.so, no CUDA."""
     rank, world, local = dist_env()
     if rank != 0:
         return 0
@@ -171,13 +173,14 @@ def run_reference(args, wl):
     nthreads = cores if wl["kind"] != "fit" else 1  # measure.rs paths are serial in the reference
     for _ in range(args.warmup if args.warmup < 2 else 1):
         cpu_frames_per_sec(wl, 1, nthreads)
-    fps, dt, done = cpu_frames_per_sec(wl, max(1, args.steps), nthreads, first_frame=1, budget_s=90.0)
+    fps, dt, done = cpu_frames_per_sec(wl, max(1, args.steps), nthreads, first_frame=1, budget_s=60.0)
     line = {
         "impl": "reference", "metric": "frames/sec", "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * dt / done,
+        "steps": done, "steps_requested": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": 1000.0 * dt / done,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": wl["desc"], "n_atoms": wl["n_atoms"], "cutoff_nm": CUTOFF,
-                   "frames_per_step": 1, "note": "one step = one frame on the host cores"},
+                   "frames_per_step": 1, "note": "one step = one frame on the host cores; steps = frames actually "
+                                                 "timed (bounded sample of 60 s of CPU work)"},
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": nthreads, "kind": "port",
                          "sample": f"{done} frames of the workload ({dt:.1f} s); C++ restatement of MolAR's "
                                    f"CPU algorithm (MolAR is Rust; no cargo in this image)"},
@@ -188,30 +191,33 @@ def run_reference(args, wl):
 
 
 # ---------------------------------------------------------------------------------------------
-# our arm
+# our arm: everything through libmolar_b200.so (C ABI via ctypes); no torch anywhere on this path.
+# Ranks are the launcher's processes (torchrun exports RANK / LOCAL_RANK / WORLD_SIZE); the rank
+# plumbing — NCCL communicator, scalar gather, barrier, max over ranks — is the library's mb_comm_*.
 # ---------------------------------------------------------------------------------------------
+FP32_LANE_OPS_PER_TEST = 9  # 3 sub, 3 mul, 2 add (as fma by 1.0), 1 sub against cutoff^2 — one f32 lane op each
+
+
+def fp32_peak_lane_ops(sm_count, sm_mhz):
+    """Non-tensor FP32 issue peak: 128 FP32 lanes per SM, one op per lane per clock (an FMA counts as ONE op here,
+    since the bit-exact test may not fuse).  Source: 4 SMSP x 32 lanes (B300_MICROARCH.md) x measured SM clock."""
+    return sm_count * 128.0 * sm_mhz * 1e6
+
+
 def run_ours(args, wl):
-    import torch
-    import torch.distributed as dist
     import molar_b200 as mb
+    from molar_b200 import comm as mbc
 
     rank, world, local = dist_env()
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device; libmolar_b200 has no CPU fallback")
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n, box, F, kind = wl["n_atoms"], wl["box"], args.frames or wl["frames"], wl["kind"]
-
-    import shard
-    traj = mb.Trajectory(device=local)
-    f_first, f_last = shard.frame_block(rank, F)  # rank r owns global frames [r*F, (r+1)*F)
+    traj = mb.Trajectory(device=local)  # raises without a CUDA device: there is no CPU fallback
+    cm = mbc.Comm(traj, rank, world)    # NCCL communicator inside the library (no-op for one rank)
+    f_first, f_last = mbc.frame_block(rank, F)  # rank r owns global frames [r*F, (r+1)*F)
     traj.synth(SEED, f_first, F, n, box, mass_seed=SEED)
     for kv in filter(None, args.opts.split(",")):
         key, val = kv.split("=")
         traj.set_option(key, float(val))
     traj.set_option("profile", 1)
-    ext = torch.cuda.ExternalStream(traj.stream(), device=local)
 
     def step():
         if kind == "search":
@@ -221,69 +227,64 @@ def run_ours(args, wl):
         return traj.pipeline(CUTOFF)
 
     def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+        cm.barrier()
+        traj.synchronize()
 
-    dev = torch.device("cuda", local)
     ncol = {"search": 1, "fit": 1, "pipeline": 5}[kind]
-    scal_host = torch.zeros((F, ncol), dtype=torch.float64).pin_memory()
-    gathered = torch.empty((world * F, ncol), dtype=torch.float64, device=dev)
 
     def gather(res):
-        # per-frame scalars -> every rank (NCCL over NVLink; the only collective on the path)
-        return shard.gather_rows(np.asarray(res, dtype=np.float64).reshape(F, ncol), world, device=dev,
-                                 out=gathered, stage=scal_host)
+        # per-frame scalars -> every rank (NCCL all-gather over NVLink inside mb_gather_scalars; the only collective)
+        return cm.gather(np.asarray(res, dtype=np.float64).reshape(F, ncol))
 
     for _ in range(max(args.warmup, 3)):
         res = step()
-    gather(res)  # warm the torch allocator / NCCL communicator outside the timed region
+    allrows = gather(res)  # warm the communicator outside the timed region
     traj.set_option("profile", 1)  # reset the kernel-time accumulators
     l0 = traj.launch_count()
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
     barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(ext)
+    traj.timer_record(0)
     for _ in range(args.steps):
         res = step()
-    gather(res)
-    torch.cuda.current_stream().synchronize()
-    e1.record(ext)
+    allrows = gather(res)
+    traj.timer_record(1)
     barrier()
-    ms = e0.elapsed_time(e1)
-    if world > 1:
-        t = torch.tensor([ms], device=f"cuda:{local}", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    ms = float(cm.max([traj.timer_ms(0, 1)])[0])  # device time, max over ranks
     clk = clocks.stop() if rank == 0 else None
     launches = traj.launch_count() - l0
     k_ms = traj.stat("search_kernel_ms")
     k_n = traj.stat("search_kernel_launches")
+    tests_per_frame = traj.stat("search_tests_per_frame") if kind == "pipeline" else 0.0
+    sm_count = traj.stat("sm_count")
     fps = world * F * args.steps / (ms / 1000.0)
+    assert allrows.shape == (world * F, ncol)
 
     if args.no_e2e:
         if rank == 0:
             emit({"tuning": True, "opts": args.opts, "value": fps, "ms_per_frame": ms / (F * args.steps),
-                              "search_kernel_ms": k_ms / max(k_n, 1), "workload": args.workload})
+                  "search_kernel_ms": k_ms / max(k_n, 1), "workload": args.workload})
         traj.close()
-        if world > 1:
-            dist.destroy_process_group()
         return 0
-    # ---- end-to-end through the public per-call API with HOST buffers (pinned), rank-local -------
-    from oracle import oracle_py as orc  # only to synthesise host-side input frames
-    e2e_frames = min(F, 4)
-    host = [torch.from_numpy(orc.synth_frame(SEED, rank * F + f, n, box)).pin_memory() for f in range(e2e_frames)]
-    sysm = mb.System(host[0].numpy(), masses=orc.synth_masses(SEED, n), box=box, device=local)
-    refsys = (mb.System(host[0].numpy(), masses=orc.synth_masses(SEED, n), box=box, device=local)
-              if kind == "fit" else None)
 
-    e2e_t = {"set": 0.0, "call": 0.0}
+    # ---- end to end through the public API with HOST buffers (page-locked), rank-local --------------------------
+    # host frames come from the library's own generator (mb_batch_synth + mb_batch_download): the oracle stays out
+    # of the product arm until the cpu_baseline leg
+    e2e_frames = min(F, 4)
+    host = mbc.pinned_empty((e2e_frames, n, 3), np.float32)
+    host[:] = traj.frames(0, e2e_frames)
+    gen = mb.Trajectory(device=local)
+    gen.synth(SEED, 0, 1, n, box, mass_seed=SEED)
+    masses_h = gen.masses_host()
+    gen.close()
+    sysm = mb.System(host[0], masses=masses_h, box=box, device=local)
+    refsys = mb.System(host[0], masses=masses_h, box=box, device=local) if kind == "fit" else None
+    e2e_t = {"set": 0.0}
 
     def e2e_once(x):
         ta = time.perf_counter()
-        sysm.set_state(x.numpy(), box)  # H2D of the frame (12 B/atom) from pinned memory
+        sysm.set_state(x, box)  # H2D of the frame (12 B/atom) from pinned memory
         e2e_t["set"] += time.perf_counter() - ta
         if kind == "search":
             lib, h = sysm._lib, sysm._h
@@ -303,53 +304,74 @@ def run_ours(args, wl):
     t0 = time.perf_counter()
     reps = max(1, min(args.steps, 4))
     for _ in range(reps):
-        for x in host:
-            e2e_once(x)
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    if os.environ.get("MB_DEBUG_TIMING"):
-        sys.stderr.write(f"[bench] rank {rank}: e2e {e2e_s * 1e3:.1f} ms for {reps * e2e_frames} calls, "
-                         f"set_state {e2e_t['set'] * 1e3:.1f} ms\n")
-    if world > 1:
-        t = torch.tensor([e2e_s], device=f"cuda:{local}", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    e2e_fps = world * reps * e2e_frames / e2e_s
+        for f in range(e2e_frames):
+            e2e_once(host[f])
+    sysm.synchronize()
+    e2e_s = float(cm.max([time.perf_counter() - t0])[0])
+    per_call_fps = world * reps * e2e_frames / e2e_s
     d2h = {"search": 8, "fit": 8 + 96, "pipeline": 40}[kind]
-    e2e_extra = {}
+    e2e_extra = {"per_call_value": per_call_fps}
+
+    # what a drop-in distance_search_single_pbc call returns is the PAIR LIST (distance_search.rs:948-953): search +
+    # fetch of the canonical (i<j) pairs into page-locked host memory as u32 x 2 (8 B/pair; the usize widening of
+    # mb_fill_pairs doubles the PCIe bytes and is the binding's choice)
+    if kind == "search":
+        cnt = int(e2e_once(host[0]))
+        pairs_h = mbc.pinned_empty((cnt + cnt // 8 + 4096, 2), np.uint32)
+        sysm.fill_pairs_u32(pairs_h)
+        barrier()
+        t0 = time.perf_counter()
+        nfr = min(e2e_frames, 3)
+        tot_pairs = 0
+        for f in range(nfr):
+            c = int(e2e_once(host[f]))
+            sysm.fill_pairs_u32(pairs_h)
+            tot_pairs += c
+        wp_s = float(cm.max([time.perf_counter() - t0])[0])
+        e2e_extra["with_pairs_value"] = world * nfr / wp_s
+        e2e_extra["with_pairs_d2h_bytes_per_step"] = 8.0 * tot_pairs / nfr
+        e2e_extra["with_pairs_note"] = ("mb_set_frame + mb_search_single + mb_fill_pairs_u32 per frame: the pair "
+                                        "list (u32 x 2, canonical i<j) lands in page-locked host memory; PCIe-bound")
+        mbc.pinned_free(pairs_h)
+
     # the trajectory-loop entry points: host frames in, per-frame results out, uploads overlapped with the work on
-    # the previous chunk (mb_stream_*; the reference overlaps IO with analysis the same way, io.rs:209-233)
-    e2e_extra["per_call_value"] = e2e_fps
+    # the previous chunks (mb_stream_*; the reference overlaps IO with analysis the same way, io.rs:209-233)
     ns = {"search": 32, "fit": 128, "pipeline": 8}[kind] if n >= 500_000 else 64
-    blockh = torch.from_numpy(np.stack([host[f % e2e_frames].numpy() for f in range(ns)])).pin_memory()
+    blockh = mbc.pinned_empty((ns, n, 3), np.float32)
+    for f in range(ns):
+        blockh[f] = host[f % e2e_frames]
     st = mb.Trajectory(device=local)
     for kv in filter(None, args.opts.split(",")):
         key, val = kv.split("=")
         st.set_option(key, float(val))
-    masses_h = orc.synth_masses(SEED, n)
+
+    # pure upload bandwidth of this rank while all ranks upload at once (what bounds e2e at N > 1)
+    barrier()
+    t0 = time.perf_counter()
+    st.upload(blockh[:min(ns, 16)], box=box)
+    up_s = float(cm.max([time.perf_counter() - t0])[0])
+    e2e_extra["h2d_gbs_per_rank_all_ranks_uploading"] = min(ns, 16) * n * 12 / up_s / 1e9
 
     def stream_once():
         if kind == "search":
-            return st.stream_search(blockh.numpy(), CUTOFF, box)
+            return st.stream_search(blockh, CUTOFF, box)
         if kind == "fit":
-            return st.stream_fit(blockh.numpy(), masses_h)
-        return st.stream_pipeline(blockh.numpy(), CUTOFF, box, masses=masses_h)
+            return st.stream_fit(blockh, masses_h)
+        return st.stream_pipeline(blockh, CUTOFF, box, masses=masses_h)
 
     stream_once()
     barrier()
     t0 = time.perf_counter()
     for _ in range(reps):
         stream_once()
-    torch.cuda.synchronize()
-    s_s = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([s_s], device=f"cuda:{local}", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        s_s = float(t.item())
+    st.synchronize()
+    s_s = float(cm.max([time.perf_counter() - t0])[0])
     e2e_fps = world * reps * ns / s_s
-    e2e_note = ("mb_stream_%s: host frames (pinned) in, per-frame results on the host; uploads overlap the work on the "
-                "previous chunk; per_call_value = blocking per-frame calls (mb_set_frame + ...)" % kind)
+    e2e_extra["h2d_gbs_per_rank_streaming"] = reps * ns * n * 12 / s_s / 1e9
+    e2e_note = ("mb_stream_%s: host frames (page-locked) in, per-frame results on the host; uploads overlap the work "
+                "on the previous chunks; per_call_value = blocking per-frame calls (mb_set_frame + ...)" % kind)
     st.close()
+    mbc.pinned_free(blockh)
 
     if rank == 0:
         peak, which = peaks()
@@ -362,13 +384,35 @@ def run_ours(args, wl):
         else:
             pairs = 0.0
             alg_bytes = 24.0 * n
-            kern = "fit_moments_kernel+superpose_rmsd_kernel (whole step)"
+            kern = "fit (whole step: moments + superposition)"
             k_avg_ms = ms / (F * args.steps)
         # launches of consecutive frames overlap on alternating streams (small frames: up to three at once), which
         # stretches each launch's own duration; the time the kernel costs per frame is bounded by the step time
         k_event_ms = k_avg_ms
         k_avg_ms = min(k_avg_ms, ms / (F * args.steps))
         achieved = alg_bytes / (k_avg_ms * 1e-3) / 1e9 if k_avg_ms > 0 else 0.0
+        roof = {"bound": "hbm", "kernel": kern, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": measured_traffic(args.workload), "peak_source": which,
+                "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": k_avg_ms,
+                "avg_launch_event_ms": k_event_ms,
+                "kernel_share_of_step": min(1.0, k_ms / ms) if kind != "fit" else 1.0,
+                "note": "avg_launch_event_ms = CUDA-event time of a launch on its own stream; consecutive "
+                        "frames run on alternating streams and overlap, so avg_launch_ms = min(event time, "
+                        "step time per frame)"}
+        if kind == "pipeline":
+            # the count-only search is bound by the FP32 pipes, not by HBM
+            sm_mhz = (clk or {}).get("sm_mhz") or 1965.0
+            fpeak = fp32_peak_lane_ops(sm_count, sm_mhz) / FP32_LANE_OPS_PER_TEST
+            tps = tests_per_frame / (k_avg_ms * 1e-3) if k_avg_ms > 0 else 0.0
+            roof = {"bound": "fp32", "kernel": "search_cells_kernel<count only>", "achieved": tps / 1e12,
+                    "peak": fpeak / 1e12, "unit": "Ttests/s", "frac": tps / fpeak if fpeak else 0.0, "traffic": None,
+                    "tests_per_launch": tests_per_frame, "avg_launch_ms": k_avg_ms,
+                    "peak_source": f"non-tensor FP32 issue peak: {int(sm_count)} SMs x 128 lanes x {sm_mhz:.0f} MHz "
+                                   f"(SM clock sampled during the run) / {FP32_LANE_OPS_PER_TEST} lane ops per "
+                                   f"unfused distance test",
+                    "hbm": {"achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                            "algorithmic_bytes_per_launch": alg_bytes, "peak_source": which},
+                    "kernel_share_of_step": min(1.0, k_ms / ms)}
         line = {
             "metric": "frames/sec", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -376,15 +420,9 @@ def run_ours(args, wl):
             "config": {"workload": wl["desc"], "n_atoms": n, "cutoff_nm": CUTOFF, "frames_per_step_per_gpu": F,
                        "pairs_per_frame": pairs, "l2": f"inputs {F * n * 12 / 1e6:.0f} MB/GPU > 126 MB L2"
                        if F * n * 12 > 126e6 else "pair output per frame exceeds L2; inputs re-streamed",
-                       "parallelism": f"frames sharded over {world} GPU(s)"},
-            "roofline": {"bound": "hbm", "kernel": kern, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": measured_traffic(args.workload), "peak_source": which,
-                         "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": k_avg_ms,
-                         "avg_launch_event_ms": k_event_ms,
-                         "kernel_share_of_step": min(1.0, k_ms / ms) if kind != "fit" else 1.0,
-                         "note": "avg_launch_event_ms = CUDA-event time of a launch on its own stream; consecutive "
-                                 "frames run on alternating streams and overlap, so avg_launch_ms = min(event time, "
-                                 "step time per frame)"},
+                       "parallelism": f"frames sharded over {world} GPU(s); scalar gather by mb_gather_scalars "
+                                      f"(NCCL {cm.info()[2]})"},
+            "roofline": roof,
             "e2e": dict({"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": 12 * n, "d2h_bytes_per_step": d2h,
                          "note": e2e_note}, **e2e_extra),
             "gpu_launches": int(launches),
@@ -399,12 +437,11 @@ def run_ours(args, wl):
                                     "sample": f"{nfr} frames of the same workload ({cdt:.1f} s); C++ restatement "
                                               f"of MolAR's CPU algorithm, not MolAR itself"}
         emit(line)
+    mbc.pinned_free(host)
     traj.close()
     sysm.close()
     if refsys:
         refsys.close()
-    if world > 1:
-        dist.destroy_process_group()
     return 0
 
 
@@ -427,10 +464,13 @@ def main():
     sys.stdout.flush()
     _REAL_STDOUT = os.fdopen(os.dup(1), "w")
     os.dup2(2, 1)
+    if args.impl == "reference":
+        # the reference arm builds and loads ONLY the CPU oracle: the product library stays out of this process
+        from oracle import oracle_py
+        oracle_py.build()
+        return run_reference(args, wl)
     import __graft_entry__
     __graft_entry__.build()
-    if args.impl == "reference":
-        return run_reference(args, wl)
     return run_ours(args, wl)
 
 

@@ -34,7 +34,8 @@
  *   box          nalgebra Matrix3<f32> storage = COLUMN-major 9 floats; columns are the box
  *                vectors a,b,c (periodic_box.rs:9-13).  NULL = no box.
  *   selections   sorted global atom indices as usize = uint64_t (providers.rs:45-48);
- *                ids == NULL means the identity selection 0..n.
+ *                ids == NULL means the identity selection 0..n.  Every entry point checks that ids are
+ *                STRICTLY INCREASING and < n_atoms (one O(n) host pass) and returns MB_ERR_ARG otherwise.
  *   pbc_dims     PbcDims bit mask, bit d = dimension d periodic (periodic_box.rs:70-128);
  *                0 selects the non-periodic variant of a search.
  *
@@ -89,6 +90,8 @@ int mb_set_frame_device(MbCtx* ctx, const float* xyz_dev, size_t n_atoms, const 
 int mb_get_frame(MbCtx* ctx, float* xyz_out, size_t n_atoms);
 /* Whole-system mass column. */
 int mb_set_masses(MbCtx* ctx, const float* masses, size_t n_atoms);
+/* Copies the mass column back (e.g. after mb_batch_synth_masses). */
+int mb_get_masses(MbCtx* ctx, float* masses_out, size_t n_atoms);
 /* A second coordinate set (e.g. the reference structure for rmsd / fit); same layout. */
 int mb_set_frame2(MbCtx* ctx, const float* xyz, size_t n_atoms);
 
@@ -117,6 +120,9 @@ int64_t mb_search_within(MbCtx* ctx, float cutoff, const uint64_t* ids1, size_t 
 int64_t mb_count_single(MbCtx* ctx, float cutoff, const uint64_t* ids, size_t n, uint8_t pbc_dims);
 /* ij: 2*P entries (usize pairs) ; dist: P entries or NULL */
 int mb_fill_pairs(MbCtx* ctx, uint64_t* ij, float* dist);
+/* The same list in the device's own form, u32 x 2 per pair (8 B: half the PCIe bytes; BondStorage likewise caps
+   systems at 2^32 atoms), single-set pairs canonical i < j.  ij32 should be page-locked (mb_host_alloc). */
+int mb_fill_pairs_u32(MbCtx* ctx, uint32_t* ij32, float* dist);
 int mb_fill_ids(MbCtx* ctx, uint64_t* ids);
 /* Device-side view of the last pair list: packed (uint32, uint32), P entries.  For a single-set
    search the two ids of an entry are in no particular order (mb_fill_pairs and mb_pairs_checksum
@@ -140,6 +146,19 @@ int mb_fit_transform(MbCtx* ctx, const uint64_t* ids1, size_t n1, const uint64_t
 /* in place on the current frame (device copy; fetch with mb_get_frame) */
 int mb_apply_transform(MbCtx* ctx, const uint64_t* ids, size_t n, const double R9_colmajor[9],
                        const double t3[3]);
+
+/* ---- many small selections in one launch ---------------------------------------------------
+ * The reference analyses per-residue / per-molecule quantities with a rayon loop over thousands of small selections,
+ * each calling Measure::center_of_mass / center_of_geometry / gyration (selection.rs:318-322,
+ * selection/par_split.rs:100-125).  Here all of them go to the device in one call: selection s is
+ * ids[offsets[s] .. offsets[s+1]) (global atom ids, strictly increasing inside a selection; selections may overlap),
+ * one warp (one CTA for large selections) per selection.  out: n_sel rows of
+ *   MB_REDUCE_COM 3 doubles | MB_REDUCE_COG 3 | MB_REDUCE_GYRATION 1 | MB_REDUCE_COM_GYRATION 4 {com, rg}.
+ * status_out (may be NULL): per selection 0 ok, 1 zero mass, 2 empty.  Returns MB_ERR_ZERO_MASS / MB_ERR_ARG if any
+ * selection failed (its row is NaN; the other rows are valid). */
+enum { MB_REDUCE_COM = 0, MB_REDUCE_COG = 1, MB_REDUCE_GYRATION = 2, MB_REDUCE_COM_GYRATION = 3 };
+int mb_reduce_many(MbCtx* ctx, const uint64_t* ids, const uint64_t* offsets, size_t n_sel, int what, double* out,
+                   int* status_out);
 
 /* ---- periodic variants, inertia tensor, principal axes ----------------------------------- */
 int mb_center_of_geometry(MbCtx* ctx, const uint64_t* ids, size_t n, double out3[3]);
@@ -223,11 +242,43 @@ const void* mb_batch_scalars_device(MbCtx* ctx, size_t* n_rows, size_t* row_doub
    out_band: [rc2_lo, rc2_hi] of the filter.  For tests of the planning logic. */
 int mb_plan_describe(const float* box9_colmajor, float cutoff, uint8_t pbc_dims, size_t n, int full_shell,
                      int out_int[16], signed char* rows4_out, float out_band[2]);
+/* ---- multi-GPU: frames shard across ranks, the per-frame scalars are gathered over NCCL ------------------------
+ * The per-frame loop (analysis_task.rs:113-280) is embarrassingly parallel over frames: rank r (one GPU, one context)
+ * processes its block of frames with the mb_batch_* / mb_stream_* calls and nothing is exchanged until the end of a
+ * pass, when every rank contributes its rows of per-frame scalars to one NCCL all-gather (NVLink / NVSwitch).
+ * libnccl.so.2 is opened with dlopen on first use (override the path with MOLAR_B200_NCCL).
+ *   multi-process (one rank per GPU): rank 0 calls mb_comm_unique_id and hands the 128 bytes to the other ranks by
+ *   any host channel (file, socket, MPI); every rank then calls mb_comm_init.
+ *   single process: mb_comm_init_all over n contexts (one per device); collective calls must then come from one
+ *   host thread per context, like any NCCL communicator created with ncclCommInitAll. */
+#define MB_COMM_ID_BYTES 128
+int mb_comm_unique_id(unsigned char* id128);
+int mb_comm_init(MbCtx* ctx, int rank, int world, const unsigned char* id128);
+int mb_comm_init_all(int n_ctx, MbCtx* const* ctxs);
+void mb_comm_destroy(MbCtx* ctx);   /* also done by mb_close */
+/* rank / world of the context's communicator (0 / 1 without one) and the NCCL version in use (0 = not loaded) */
+int mb_comm_info(MbCtx* ctx, int* rank, int* world, int* nccl_version);
+/* All-gather of per-frame scalar rows: every rank contributes n_rows x n_cols doubles; out_all (host) receives
+   world x n_rows x n_cols doubles in rank order on EVERY rank.  rows == NULL contributes the rows the last
+   mb_batch_pipeline / mb_batch_fit left on the device (mb_batch_scalars_device) without a host round trip.
+   Without a communicator (single GPU) it degenerates to a copy. */
+int mb_gather_scalars(MbCtx* ctx, const double* rows, size_t n_rows, size_t n_cols, double* out_all);
+/* element-wise maximum over ranks (in place; how multi-GPU timings are reduced) and a barrier */
+int mb_comm_max(MbCtx* ctx, double* inout, size_t n);
+int mb_comm_barrier(MbCtx* ctx);
+/* CUDA-event timing on the context stream for hosts without a CUDA binding of their own: slots 0..7 */
+int mb_timer_record(MbCtx* ctx, int slot);
+int mb_timer_elapsed_ms(MbCtx* ctx, int slot_begin, int slot_end, double* ms);
+/* page-locked host memory (frames handed to mb_stream_* should live in it) */
+void* mb_host_alloc(size_t bytes);
+void mb_host_free(void* p);
+
 /* number of kernels this context has launched since it was opened (for gpu_launches) */
 uint64_t mb_launch_count(MbCtx* ctx);
 /* Instrumentation.  With option "profile"=1 every pair-search kernel launch is bracketed by CUDA
    events on the context stream; "search_kernel_ms" / "search_kernel_launches" return the totals
-   since the option was last set.  Other keys: "pair_capacity", "sm_count". */
+   since the option was last set.  Other keys: "pair_capacity", "sm_count", "search_tests_per_frame" (distance tests
+   per frame evaluated by the last count-only batch search: the numerator of its FP32-pipe roofline). */
 int mb_get_stat(MbCtx* ctx, const char* key, double* out);
 
 #ifdef __cplusplus

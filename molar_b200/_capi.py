@@ -28,6 +28,7 @@ SIGNATURES = {
     "mb_get_frame": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "mb_set_masses": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "mb_set_frame2": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "mb_get_masses": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "mb_search_single": (C.c_int64, [C.c_void_p, C.c_float, u64p, C.c_size_t, C.c_uint8]),
     "mb_search_double": (C.c_int64, [C.c_void_p, C.c_float, u64p, C.c_size_t, u64p, C.c_size_t, C.c_int, C.c_uint8]),
     "mb_search_double_vdw": (C.c_int64, [C.c_void_p, u64p, C.c_size_t, f32p, u64p, C.c_size_t, f32p, C.c_int, C.c_uint8]),
@@ -35,6 +36,7 @@ SIGNATURES = {
                                      f32p, f32p]),
     "mb_count_single": (C.c_int64, [C.c_void_p, C.c_float, u64p, C.c_size_t, C.c_uint8]),
     "mb_fill_pairs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mb_fill_pairs_u32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "mb_fill_ids": (C.c_int, [C.c_void_p, C.c_void_p]),
     "mb_pairs_device": (C.c_void_p, [C.c_void_p, i64p]),
     "mb_pairs_checksum": (C.c_int, [C.c_void_p, u64p]),
@@ -47,6 +49,7 @@ SIGNATURES = {
     "mb_connectivity": (C.c_int64, [C.c_void_p, C.c_size_t, u64p]),
     "mb_fill_connectivity": (C.c_int, [C.c_void_p, u64p]),
     "mb_unwrap_connectivity": (C.c_int64, [C.c_void_p, C.c_float, u64p, C.c_size_t, C.c_uint8, i64p]),
+    "mb_reduce_many": (C.c_int, [C.c_void_p, u64p, u64p, C.c_size_t, C.c_int, f64p, C.POINTER(C.c_int)]),
     "mb_center_of_geometry": (C.c_int, [C.c_void_p, u64p, C.c_size_t, f64p]),
     "mb_center_pbc": (C.c_int, [C.c_void_p, u64p, C.c_size_t, C.c_int, C.c_uint8, f64p]),
     "mb_gyration_pbc": (C.c_int, [C.c_void_p, u64p, C.c_size_t, f64p]),
@@ -67,6 +70,18 @@ SIGNATURES = {
     "mb_batch_pipeline": (C.c_int, [C.c_void_p, C.c_float, C.c_uint8, C.c_size_t, C.c_size_t, f64p]),
     "mb_batch_scalars_device": (C.c_void_p, [C.c_void_p, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "mb_plan_describe": (C.c_int, [f32p, C.c_float, C.c_uint8, C.c_size_t, C.c_int, C.POINTER(C.c_int), C.c_void_p, f32p]),
+    "mb_comm_unique_id": (C.c_int, [C.c_void_p]),
+    "mb_comm_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "mb_comm_init_all": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
+    "mb_comm_destroy": (None, [C.c_void_p]),
+    "mb_comm_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "mb_gather_scalars": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p]),
+    "mb_comm_max": (C.c_int, [C.c_void_p, f64p, C.c_size_t]),
+    "mb_comm_barrier": (C.c_int, [C.c_void_p]),
+    "mb_timer_record": (C.c_int, [C.c_void_p, C.c_int]),
+    "mb_timer_elapsed_ms": (C.c_int, [C.c_void_p, C.c_int, C.c_int, f64p]),
+    "mb_host_alloc": (C.c_void_p, [C.c_size_t]),
+    "mb_host_free": (None, [C.c_void_p]),
     "mb_launch_count": (C.c_uint64, [C.c_void_p]),
     "mb_get_stat": (C.c_int, [C.c_void_p, C.c_char_p, f64p]),
 }

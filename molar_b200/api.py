@@ -122,6 +122,40 @@ class System:
     def launch_count(self):
         return int(self._lib.mb_launch_count(self._h))
 
+    def synchronize(self):
+        check(self._lib.mb_synchronize(self._h))
+
+    def fill_pairs_u32(self, out):
+        """Last pair list as u32 pairs (canonical i<j) into `out` (uint32 [>=P, 2], ideally page-locked)."""
+        check(self._lib.mb_fill_pairs_u32(self._h, out.ctypes.data, None))
+
+    _REDUCE = {"com": (0, 3), "cog": (1, 3), "gyration": (2, 1), "com_gyration": (3, 4)}
+
+    def reduce_many(self, selections, what="com", return_status=False):
+        """COM / COG / gyration of MANY selections in one launch (mb_reduce_many) — the device form of the reference's
+        rayon loop over split selections (selection.rs:318-322, selection/par_split.rs:100-125).
+        selections: a list of index arrays, or a tuple (ids, offsets) in CSR form.  Returns [n_sel, width] float64."""
+        if isinstance(selections, tuple):
+            ids = np.ascontiguousarray(selections[0], dtype=np.uint64)
+            offsets = np.ascontiguousarray(selections[1], dtype=np.uint64)
+        else:
+            arrs = [np.unique(np.asarray(a, dtype=np.uint64)) for a in selections]
+            offsets = np.zeros(len(arrs) + 1, np.uint64)
+            offsets[1:] = np.cumsum([len(a) for a in arrs])
+            ids = np.concatenate(arrs) if arrs else np.zeros(0, np.uint64)
+        code, width = self._REDUCE[what]
+        n_sel = len(offsets) - 1
+        out = np.empty((n_sel, width), np.float64)
+        status = np.zeros(n_sel, np.int32)
+        rc = self._lib.mb_reduce_many(self._h, ids.ctypes.data_as(u64p), offsets.ctypes.data_as(u64p), n_sel, code,
+                                      out.ctypes.data_as(f64p), status.ctypes.data_as(C.POINTER(C.c_int)))
+        if return_status:
+            if rc < 0 and not status.any():
+                check(rc)
+            return out, status
+        check(rc)
+        return out
+
     def connectivity(self):
         """Adjacency of the last pair list as CSR (row_ptr[n+1], cols): SearchConnectivity (connectivity.rs:8-38)."""
         row_ptr = np.zeros(self._n + 1, np.uint64)
@@ -507,6 +541,11 @@ class Trajectory:
         check(self._lib.mb_batch_pipeline(self._h, cutoff, _pbc_bits(dims), f0, f1, out.ctypes.data_as(f64p)))
         return out
 
+    def masses_host(self):
+        out = np.empty(self.n_atoms, np.float32)
+        check(self._lib.mb_get_masses(self._h, out.ctypes.data, self.n_atoms))
+        return out
+
     def scalars_device(self):
         rows, rd = C.c_size_t(0), C.c_size_t(0)
         p = self._lib.mb_batch_scalars_device(self._h, C.byref(rows), C.byref(rd))
@@ -514,6 +553,15 @@ class Trajectory:
 
     def stream(self):
         return self._lib.mb_stream(self._h)
+
+    def timer_record(self, slot):
+        """CUDA event on the context stream (mb_timer_record); slots 0..7."""
+        check(self._lib.mb_timer_record(self._h, slot))
+
+    def timer_ms(self, slot_begin, slot_end):
+        out = C.c_double(0.0)
+        check(self._lib.mb_timer_elapsed_ms(self._h, slot_begin, slot_end, C.byref(out)))
+        return out.value
 
     def stat(self, key):
         out = C.c_double(0.0)

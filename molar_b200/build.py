@@ -7,8 +7,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libmolar_b200.so")
-SOURCES = ["mb_api.cu", "mb_search.cu", "mb_measure.cu", "mb_measure_pbc.cu", "mb_batch.cu", "mb_traj.cu", "mb_connect.cu"]
-HEADERS = ["mb_common.cuh", "mb_reduce.cuh", "mb_search_lanes.cuh", os.path.join("..", "..", "include", "molar_b200.h")]
+SOURCES = ["mb_api.cu", "mb_search.cu", "mb_measure.cu", "mb_measure_pbc.cu", "mb_batch.cu", "mb_traj.cu", "mb_connect.cu", "mb_comm.cu", "mb_reduce_many.cu"]
+HEADERS = ["mb_common.cuh", "mb_reduce.cuh", os.path.join("..", "..", "include", "molar_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -17,6 +17,7 @@ NVCC_FLAGS = [
     "-Xptxas", "-v",
     "--expt-relaxed-constexpr", "--extended-lambda",
     "-shared",
+    "-ldl",
 ]
 
 

@@ -160,6 +160,22 @@ int Ctx::pinned_reserve(size_t bytes) {
     return MB_OK;
 }
 
+int validate_sel(const uint64_t* ids, size_t n, size_t n_atoms, const char* what) {
+    if (n == 0) return fail(MB_ERR_ARG, "%s: empty selection", what);
+    if (n > 0x7fffffffull) return fail(MB_ERR_ARG, "%s: selection too large", what);
+    if (!ids) {
+        if (n > n_atoms) return fail(MB_ERR_ARG, "%s: identity selection of %zu > %zu atoms", what, n, n_atoms);
+        return MB_OK;
+    }
+    if (ids[0] >= n_atoms) return fail(MB_ERR_ARG, "%s: index %llu out of range (%zu atoms)", what, (unsigned long long)ids[0], n_atoms);
+    uint64_t bad = 0;  // branch-free scan: any non-increasing step sets it
+    for (size_t k = 1; k < n; ++k) bad |= (uint64_t)(ids[k] <= ids[k - 1]);
+    if (bad) return fail(MB_ERR_ARG, "%s: selection indices must be strictly increasing (a sorted set)", what);
+    if (ids[n - 1] >= n_atoms)
+        return fail(MB_ERR_ARG, "%s: index %llu out of range (%zu atoms)", what, (unsigned long long)ids[n - 1], n_atoms);
+    return MB_OK;
+}
+
 }  // namespace mb
 
 using namespace mb;
@@ -222,6 +238,13 @@ void mb_close(MbCtx* h) {
         if (sl.stream) cudaStreamDestroy(sl.stream);
     }
     free_plan_cache(&c);
+    comm_destroy(&c);
+    c.comm_send.release();
+    c.comm_recv.release();
+    c.many_tmp.release();
+    for (cudaEvent_t& e : c.timer_ev)
+        if (e) cudaEventDestroy(e);
+    if (c.copy_stream) cudaStreamDestroy(c.copy_stream);
     if (c.h_pinned) cudaFreeHost(c.h_pinned);
     for (int i = 0; i < 2; ++i)
         if (c.aux_stream[i]) cudaStreamDestroy(c.aux_stream[i]);
@@ -252,7 +275,6 @@ int mb_set_option(MbCtx* h, const char* key, double value) {
     else if (!strcmp(key, "with_dist")) c.opt_with_dist = (int)value;
     else if (!strcmp(key, "exact_pbc")) c.opt_exact_pbc = (int)value;
     else if (!strcmp(key, "fused_fit")) c.opt_fused_fit = (int)value;
-    else if (!strcmp(key, "lane_kernel")) c.opt_lane_kernel = (int)value;
     else if (!strcmp(key, "batch_streams")) c.opt_batch_streams = (int)value;
     else if (!strcmp(key, "two_set_cells_min")) c.opt_two_set_cells_min = value;
     else if (!strcmp(key, "profile")) {
@@ -330,6 +352,16 @@ int mb_set_frame2(MbCtx* h, const float* xyz, size_t n_atoms) {
     return MB_OK;
 }
 
+int mb_get_masses(MbCtx* h, float* out, size_t n_atoms) {
+    if (!h || !out) return fail(MB_ERR_ARG, "null argument");
+    Ctx& c = h->c;
+    if (!c.masses.p || n_atoms != c.n_masses) return fail(MB_ERR_ARG, "mb_get_masses: no masses or size mismatch");
+    MB_CUDA(cudaSetDevice(c.device));
+    MB_CUDA(cudaMemcpyAsync(out, c.masses.p, n_atoms * sizeof(float), cudaMemcpyDeviceToHost, c.stream));
+    MB_CUDA(cudaStreamSynchronize(c.stream));
+    return MB_OK;
+}
+
 uint64_t mb_launch_count(MbCtx* h) { return h ? h->c.launches : 0; }
 
 int mb_get_stat(MbCtx* h, const char* key, double* out) {
@@ -339,6 +371,7 @@ int mb_get_stat(MbCtx* h, const char* key, double* out) {
     else if (!strcmp(key, "search_kernel_launches")) *out = (double)c.prof_search_launches;
     else if (!strcmp(key, "pair_capacity")) *out = (double)c.pair_cap;
     else if (!strcmp(key, "sm_count")) *out = (double)c.sm_count;
+    else if (!strcmp(key, "search_tests_per_frame")) *out = c.last_tests_per_frame;  // last count-only batch search
     else if (!strcmp(key, "traj_h2d_ms")) *out = c.traj_h2d_ms;        // last mb_batch_load_traj: raw bytes to the device
     else if (!strcmp(key, "traj_decode_ms")) *out = c.traj_decode_ms;  // ... all decode kernels (CUDA events)
     else if (!strcmp(key, "traj_scan_ms")) *out = c.traj_scan_ms;      // ... of which xtc_scan_kernel

@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(256) synth_masses_kernel(float* __restrict__ o
     out[a] = xadd(1.0f, xmul(15.0f, s));
 }
 
-// rows8 (com xyz, rg, M, status, -, -) + u64 counters (stride 2) -> rows5 {com, rg, count}
+// rows8 (com xyz, rg, M, status, -, -) + u64 counters (stride 4: pairs, work, tests, -) -> rows5 {com, rg, count}
 __global__ void assemble_rows_kernel(const double* __restrict__ rows8, const unsigned long long* __restrict__ counters,
                                      int nf, double* __restrict__ rows5) {
     int f = blockIdx.x * blockDim.x + threadIdx.x;
@@ -64,53 +64,60 @@ __global__ void assemble_rows_kernel(const double* __restrict__ rows8, const uns
     rows5[5 * f + 1] = rows8[8 * f + 1];
     rows5[5 * f + 2] = rows8[8 * f + 2];
     rows5[5 * f + 3] = rows8[8 * f + 3];
-    rows5[5 * f + 4] = (double)counters[2 * f];
+    rows5[5 * f + 4] = (double)counters[4 * f];
 }
 
 // Streaming over HOST frames: what the reference's trajectory loop does with an IO thread feeding a bounded
-// channel while the consumer analyses (io.rs:209-233, analysis_task.rs:113-280), done with a copy stream: frames are
-// uploaded in chunks into one half of a two-chunk ring while the previous chunk is being processed.
+// channel while the consumer analyses (io.rs:209-233, analysis_task.rs:113-280), done with a copy stream of its own
+// and a ring of three chunks: uploads are issued two chunks ahead of the chunk being processed, so the copy engine
+// always has work queued while work() (which is synchronous) runs, and never waits behind a compute stream.
 // work(b0, nf, f0): process ring frames [b0, b0+nf) = stream frames [f0, f0+nf); synchronous.
 template <class Work>
 static int stream_chunks(Ctx& c, const float* frames, size_t n_frames, size_t n_atoms, size_t chunk, Work&& work) {
     MB_CUDA(cudaSetDevice(c.device));
+    constexpr size_t RING = 3;
     chunk = std::max<size_t>(1, std::min(chunk, n_frames));
     const size_t fbytes = n_atoms * 3 * sizeof(float);
-    MB_TRY(c.batch.reserve(2 * chunk * fbytes));
-    c.batch_frames = 2 * chunk;
+    MB_TRY(c.batch.reserve(RING * chunk * fbytes));
+    c.batch_frames = RING * chunk;
     c.batch_atoms = n_atoms;
     c.d_xyz = c.batch.as<float>();
     c.n_atoms = n_atoms;
-    if (!c.aux_stream[0]) MB_CUDA(cudaStreamCreateWithFlags(&c.aux_stream[0], cudaStreamNonBlocking));
-    cudaStream_t copy = c.aux_stream[0];
-    cudaEvent_t up[2] = {nullptr, nullptr};
-    for (int k = 0; k < 2; ++k) MB_CUDA(cudaEventCreateWithFlags(&up[k], cudaEventDisableTiming));
+    if (!c.copy_stream) MB_CUDA(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
+    cudaStream_t copy = c.copy_stream;
+    cudaEvent_t up[RING] = {nullptr, nullptr, nullptr};
+    for (size_t k = 0; k < RING; ++k) MB_CUDA(cudaEventCreateWithFlags(&up[k], cudaEventDisableTiming));
     const size_t nchunks = (n_frames + chunk - 1) / chunk;
     auto upload = [&](size_t k) -> int {
         const size_t f0 = k * chunk, nf = std::min(chunk, n_frames - f0);
-        MB_CUDA(cudaMemcpyAsync(c.batch.as<char>() + (k & 1) * chunk * fbytes, frames + f0 * n_atoms * 3, nf * fbytes,
+        MB_CUDA(cudaMemcpyAsync(c.batch.as<char>() + (k % RING) * chunk * fbytes, frames + f0 * n_atoms * 3, nf * fbytes,
                                 cudaMemcpyHostToDevice, copy));
-        MB_CUDA(cudaEventRecord(up[k & 1], copy));
+        MB_CUDA(cudaEventRecord(up[k % RING], copy));
         return MB_OK;
     };
     int rc = upload(0);
+    if (rc == MB_OK && nchunks > 1) rc = upload(1);
     for (size_t k = 0; k < nchunks && rc == MB_OK; ++k) {
-        // the other half was processed by the previous (synchronous) work() call: free to overwrite
-        if (k + 1 < nchunks) rc = upload(k + 1);
+        // ring slot (k+2) % 3 held chunk k-1, which the previous (synchronous) work() call has finished with
+        if (k + 2 < nchunks) rc = upload(k + 2);
         if (rc != MB_OK) break;
-        cudaStreamWaitEvent(c.stream, up[k & 1], 0);
+        cudaStreamWaitEvent(c.stream, up[k % RING], 0);
         const size_t f0 = k * chunk, nf = std::min(chunk, n_frames - f0);
-        rc = work((k & 1) * chunk, nf, f0);
+        rc = work((k % RING) * chunk, nf, f0);
     }
     cudaStreamSynchronize(copy);
-    for (int k = 0; k < 2; ++k) cudaEventDestroy(up[k]);
+    for (size_t k = 0; k < RING; ++k) cudaEventDestroy(up[k]);
     return rc;
 }
 
+// box9 == NULL means "no box", exactly as in mb_set_frame / mb_batch_upload: a box set by an earlier call is not
+// inherited (the periodic entry points then fail with MB_ERR_NO_PBC instead of searching with a stale box)
 static int stream_box(Ctx& c, const float* box9) {
     if (box9) {
         MB_TRY(host_box_from_colmajor(box9, &c.box));
         c.has_box = true;
+    } else {
+        c.has_box = false;
     }
     return MB_OK;
 }
@@ -240,7 +247,7 @@ int mb_batch_pipeline(MbCtx* h, float cutoff, uint8_t pbc_dims, size_t f0, size_
     const size_t n = c.batch_atoms, nf = f1 - f0;
     // moments scratch lives in pipe_tmp: [tickets 64 KB][rows8 nf*8][partials nf*nb*5];
     // the contact counts come from batch_search (count-only mode), whose per-frame device counters
-    // stay in batch_tmp at stride 2
+    // stay in batch_tmp at stride 4
     int nb = (int)std::max<size_t>(1, std::min<size_t>((n + 256 * 8 - 1) / (256 * 8), 64));
     size_t tick_bytes = 64 * 1024;
     if (nf * sizeof(unsigned) > tick_bytes) return fail(MB_ERR_ARG, "batch_pipeline: at most 16384 frames per call");

@@ -127,6 +127,7 @@ struct Ctx {
     DevBuf reduce_tmp;      // per-block partials
     DevBuf pbc_tmp;         // ticket + results + partials of the periodic reductions (mb_measure_pbc.cu)
     SearchResult last;
+    double last_tests_per_frame = 0.0;  // distance tests per frame of the last count-only batch search
     size_t pair_cap = 0;
     SearchSlot alt[2];        // alternate slots for batch_search (streams created lazily)
     int installed_slot = 0;   // which slot currently lives in the members above
@@ -143,7 +144,6 @@ struct Ctx {
     int opt_fused_fit = 0;  // 1: batch_fit uses the persistent TMA-staged kernel (slower than the two-kernel path so far)
     int opt_exact_pbc = 0;    // 1: wrapped cell pairs always use the exact PeriodicBox path (no filter)
     int opt_profile = 0;      // record CUDA events around every search-kernel launch
-    int opt_lane_kernel = 0;  // 1: search_lanes_kernel (home atom per lane, measured slower); 0: search_cells_kernel (hit masks)
     std::vector<cudaEvent_t> prof_events;  // begin/end pairs not yet harvested
     double prof_search_ms = 0.0;
     uint64_t prof_search_launches = 0;
@@ -163,6 +163,14 @@ struct Ctx {
 
     // memoised search plan (owned by mb_search.cu)
     void* plan_cache = nullptr;
+
+    // multi-GPU (mb_comm.cu): NCCL communicator of the frame-sharded ranks, staging for the scalar gather
+    void* nccl_comm = nullptr;
+    int comm_rank = 0, comm_world = 1;
+    DevBuf comm_send, comm_recv;
+    DevBuf many_tmp;  // mb_reduce_many: ids | offsets | results | status
+    cudaEvent_t timer_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaStream_t copy_stream = nullptr;  // uploads of mb_stream_* (own stream: never queues behind the work streams)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -237,6 +245,11 @@ __device__ __forceinline__ void shortest_vector_dev(const DevBox& bx, float v0, 
 }
 #endif  // __CUDACC__
 
+// Selection check shared by every entry point that takes ids: non-empty, at most 2^31-1 entries, and — when ids are
+// given — STRICTLY INCREASING and < n_atoms (a Sel's index vector is a sorted set, providers.rs:45-48; kernels rely
+// on it for bounds and for the lower_bound in unwrap_connectivity).  One O(n) host pass, cheap next to the H2D copy.
+int validate_sel(const uint64_t* ids, size_t n, size_t n_atoms, const char* what);
+
 // implemented in the respective translation units
 int search_single_impl(Ctx* c, float cutoff, const uint64_t* ids, size_t n, uint8_t pbc, int mode,
                        int64_t* count_out);
@@ -245,6 +258,7 @@ int batch_search_impl(Ctx* c, float cutoff, uint8_t pbc, size_t f0, size_t f1, i
 int enqueue_count_frame(Ctx* c, const float* xyz, size_t n, float cutoff, uint8_t pbc,
                         unsigned long long* d_counter2);
 void free_plan_cache(Ctx* c);
+void comm_destroy(Ctx* c);  // mb_comm.cu
 // exclusive scan of n u32 on the context stream, out[n] = total (mb_search.cu)
 int exclusive_scan_u32(Ctx* c, const unsigned* in, int n, unsigned* out);
 int batch_fit_impl(Ctx* c, size_t ref_frame, size_t f0, size_t f1, int superpose, double* rmsd_out);

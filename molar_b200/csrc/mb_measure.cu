@@ -572,15 +572,7 @@ static int upload_ids(Ctx* c, DevBuf& buf, const uint64_t* ids, size_t n, const 
 }
 
 static int check_sel(const uint64_t* ids, size_t n, size_t n_atoms, const char* what) {
-    if (n == 0) return fail(MB_ERR_ARG, "%s: empty selection", what);
-    if (n > 0x7fffffffull) return fail(MB_ERR_ARG, "%s: selection too large", what);
-    if (!ids) {
-        if (n > n_atoms) return fail(MB_ERR_ARG, "%s: identity selection of %zu > %zu atoms", what, n, n_atoms);
-        return MB_OK;
-    }
-    if (ids[n - 1] >= n_atoms || ids[0] >= n_atoms)
-        return fail(MB_ERR_ARG, "%s: index out of range (%zu atoms)", what, n_atoms);
-    return MB_OK;
+    return validate_sel(ids, n, n_atoms, what);
 }
 
 static int red_blocks(const Ctx* c, size_t n, int per_thread) {

@@ -144,11 +144,7 @@ static int pbc_prepare(Ctx* c, const uint64_t* ids, size_t n, bool need_mass, bo
                        PbcRedParams& P, int* nb_out) {
     if (!c->d_xyz) return fail(MB_ERR_STATE, "no frame set");
     MB_CUDA(cudaSetDevice(c->device));
-    if (n == 0) return fail(MB_ERR_ARG, "%s: empty selection", what);
-    if (n > 0x7fffffffull) return fail(MB_ERR_ARG, "%s: selection too large", what);
-    if (!ids && n > c->n_atoms) return fail(MB_ERR_ARG, "%s: identity selection of %zu > %zu atoms", what, n, c->n_atoms);
-    if (ids && (ids[n - 1] >= c->n_atoms || ids[0] >= c->n_atoms))
-        return fail(MB_ERR_ARG, "%s: index out of range (%zu atoms)", what, c->n_atoms);
+    MB_TRY(validate_sel(ids, n, c->n_atoms, what));
     if (need_mass && (!c->masses.p || c->n_masses < c->n_atoms))
         return fail(MB_ERR_STATE, "masses not set (mb_set_masses) for %zu atoms", c->n_atoms);
     if (need_box && !c->has_box) return fail(MB_ERR_NO_PBC, "%s: the frame has no periodic box", what);

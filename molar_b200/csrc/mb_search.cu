@@ -36,6 +36,8 @@ constexpr int MAX_REACH = 7;
 constexpr int MAX_ROWS = (2 * MAX_REACH + 1) * (2 * MAX_REACH + 1);
 constexpr int STAGE_CAP = 512;  // pairs staged per warp before a flush (>= 16 lanes * 32 home atoms)
 constexpr int SEARCH_WARPS = 8;
+constexpr int CNT_STRIDE = 4;  // u64 words per search: [0] pairs, [1] tile work counter, [2] distance tests, [3] spare
+constexpr int PAD_CANDS = 64;  // finite far-away records behind each sorted array (read by idle lanes of the candidate stream)
 
 struct GridSpec {
     int periodic_variant;  // 1: populate_pbc binning, 0: populate (bounds) binning
@@ -66,13 +68,18 @@ struct SearchParams {
     float rc2_lo, rc2_hi;  // band around cutoff^2 outside which the shifted-image filter is decisive
     int fast_pbc;          // 1: wrapped cell pairs may use the filter (see plan_cells)
     int nrows;
+    int dx_min, dx_max;  // smallest dxlo / largest dxhi over all rows (x reach of the whole table)
     NbrRow rows[MAX_ROWS];
     uint2* pairs;
     float* dists;
     unsigned long long pair_cap;
-    unsigned long long* counter;  // [0] pairs found, [1] work counter (as u64)
+    unsigned long long* counter;  // [0] pairs found, [1] work counter (as u64), [2] distance tests (MODE 2)
     unsigned long long n_sortedB;  // atoms in the candidate set
     float one;                     // 1.0f, opaque to ptxas: multiplier of the exact packed sums (see d2_pair_fma)
+    // vdW search (distance_search.rs:767-879): radii per selected atom of the home / candidate set, indexed by the LOCAL
+    // id stored in .w of the records; NULL for a plain cutoff search
+    const float* vdwA;
+    const float* vdwB;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -196,6 +203,8 @@ __global__ void __launch_bounds__(256) scatter_kernel(const float4* __restrict__
                                                       const unsigned* __restrict__ cell_start, int n,
                                                       float4* __restrict__ sorted) {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
+    // far-away finite records behind the array: what idle lanes of the candidate stream read (PAD_CANDS entries)
+    if (k < PAD_CANDS) sorted[n + k] = make_float4(-1.0e18f, -1.0e18f, -1.0e18f, 0.f);
     if (k >= n) return;
     unsigned c = cellid[k];
     if (c == DROPPED) return;
@@ -327,9 +336,34 @@ __device__ __forceinline__ float lds32f(unsigned addr) {
 // A staged entry is (j, candidate id) with j the slot of the home atom in ws.home: the home id is looked
 // up here, 32 pairs per instruction, instead of once per pair in the expansion loop — so the buffer must
 // be flushed before the home batch changes.  Fully unrolled, predicated on the entry count.
-template <bool DIST>
+// One 32-entry chunk of a MODE 0 flush, straight-line predicated code (a branch per chunk costs three more
+// instructions than the work it skips).  Entries hold the candidate's remaining hit bits — the home slot is the
+// lowest one (brev + bfind.shiftamt = count of trailing zeros) — and the candidate id; the home id is looked up in the
+// warp's home batch, 32 entries per instruction.
+template <int Q>
+__device__ __forceinline__ void flush_chunk_bits(int r, unsigned sa, unsigned home_sa, uint2* d) {
+    asm volatile(
+        "{ .reg .pred p; .reg .b32 e, id, j;\n"
+        "  setp.gt.s32 p, %0, %1;\n"
+        "  mov.b32 e, 1;\n"
+        "  @p ld.shared.v2.u32 {e, id}, [%2+%3];\n"
+        "  brev.b32 j, e;\n"
+        "  bfind.shiftamt.u32 j, j;\n"
+        "  shl.b32 j, j, 4;\n"
+        "  add.u32 j, j, %4;\n"
+        "  @p ld.shared.u32 e, [j+12];\n"
+        "  @p st.global.v2.u32 [%5+%3], {e, id};\n"
+        "}"
+        :
+        : "r"(r), "n"(Q * 32), "r"(sa), "n"(Q * 256), "r"(home_sa), "l"(d)
+        : "memory");
+}
+
+template <int MODE>
 __device__ __forceinline__ void warp_flush(unsigned stage_sa, unsigned staged_sa, unsigned home_sa, int& stage_n,
                                            const SearchParams& P, unsigned lane) {
+    constexpr bool DIST = MODE == 1;
+    static_assert(STAGE_CAP == 512, "the flush is written out for 16 chunks");
     __syncwarp();
     if (stage_n == 0) return;
     const int n = stage_n;
@@ -337,21 +371,40 @@ __device__ __forceinline__ void warp_flush(unsigned stage_sa, unsigned staged_sa
     if (lane == 0) base = atomicAdd(P.counter, (unsigned long long)n);
     base = __shfl_sync(0xffffffffu, base, 0);
     if (base + (unsigned long long)n <= P.pair_cap) {
-        uint2* d = P.pairs + base + lane;
-        unsigned sa = stage_sa + lane * 8u;
-        int r = n - (int)lane;  // entry q*32 + lane exists iff r > q*32
-        asm volatile("" : "+r"(sa), "+r"(r));  // keep both in registers (ptxas otherwise re-derives them from %tid per chunk)
+        if (MODE == 0) {
+            // four chunks per round of a real loop (fully unrolled, ptxas hoists all sixteen loads and spills)
+            uint2* d = P.pairs + base + lane;
+            unsigned sa = stage_sa + lane * 8u;
+            int r = n - (int)lane;  // entry q*32 + lane exists iff r > q*32
+            asm volatile("" : "+r"(sa), "+r"(r));
+#pragma unroll 1
+            for (int q = 0; q < n; q += 128) {
+                flush_chunk_bits<0>(r, sa, home_sa, d);
+                flush_chunk_bits<1>(r, sa, home_sa, d);
+                flush_chunk_bits<2>(r, sa, home_sa, d);
+                flush_chunk_bits<3>(r, sa, home_sa, d);
+                r -= 128;
+                sa += 1024u;
+                d += 128;
+            }
+        } else {
+            uint2* d = P.pairs + base + lane;
+            unsigned sa = stage_sa + lane * 8u;
+            int r = n - (int)lane;  // entry q*32 + lane exists iff r > q*32
+            asm volatile("" : "+r"(sa), "+r"(r));  // keep both in registers (ptxas otherwise re-derives them from %tid per chunk)
 #pragma unroll
-        for (int q = 0; q < STAGE_CAP / 32; ++q) {
-            if (r > q * 32) {
-                uint2 v = lds64(sa + (unsigned)q * 256u);
-                v.x = lds32(home_sa + 16u * v.x + 12u);
-                d[q * 32] = v;
+            for (int q = 0; q < STAGE_CAP / 32; ++q) {
+                if (r > q * 32) {
+                    uint2 v = lds64(sa + (unsigned)q * 256u);  // (home slot, candidate id)
+                    v.x = lds32(home_sa + 16u * v.x + 12u);
+                    d[q * 32] = v;
+                }
             }
         }
         if (DIST) {
             float* dd = P.dists + base + lane;
             const unsigned sd = staged_sa + lane * 4u;
+            const int r = n - (int)lane;
 #pragma unroll
             for (int q = 0; q < STAGE_CAP / 32; ++q)
                 if (r > q * 32) dd[q * 32] = lds32f(sd + (unsigned)q * 128u);
@@ -432,6 +485,19 @@ __device__ __forceinline__ unsigned long long rc2_minus_d2(unsigned long long nx
     return sub2(rc22, s);
 }
 
+// vdW variant: c2 - ((dx*dx + dy*dy) + dz*dz) with c2 = the pair's own squared cutoff (already rounded).  The final
+// subtraction is fma(s, -1.0, c2) with a run-time -1.0: one rounding of the exact difference, and nothing ptxas could
+// contract the product c*c into.
+__device__ __forceinline__ unsigned long long cut2_minus_d2(unsigned long long nx, unsigned long long ny,
+                                                            unsigned long long nz, const float4& h,
+                                                            unsigned long long one2, unsigned long long mone2,
+                                                            unsigned long long c2) {
+    const unsigned long long dx = sub2(nx, pk2(h.x, h.x)), dy = sub2(ny, pk2(h.y, h.y)), dz = sub2(nz, pk2(h.z, h.z));
+    const unsigned long long xx = mul2(dx, dx), yy = mul2(dy, dy), zz = mul2(dz, dz);
+    const unsigned long long s = fma2(fma2(xx, one2, yy), one2, zz);
+    return fma2(s, mone2, c2);
+}
+
 // Out-of-line copy of the exact periodic distance for the rare paths of the cell kernel (band
 // resolution, distance output of wrapped pairs): keeps the hot loop inside the instruction cache.
 __device__ __noinline__ float d2_pbc_call(const DevBox& bx, float ax, float ay, float az, float bxx, float byy,
@@ -461,6 +527,24 @@ __device__ __forceinline__ bool ref_adjacent(int ch, int cn, int dim, bool perio
 // Runs of one neighbour row (dy,dz,[dxlo,dxhi]) of home fine cell (fx,fy,fz): contiguous x-ranges of
 // fine cells that lie in reference cells MASK-adjacent to the home reference cell, each with a
 // uniform wrapped-dims flag.  emit(first_cell, last_cell, flag) with flag = w | sgn << 3.
+// y / z part of a neighbour row: wrapped fine coordinates, MASK adjacency of the reference cells and the wrapped /
+// sign flags of the two dims.  Returns false when the row does not exist for this home tile.
+__device__ __forceinline__ bool row_yz(const GridSpec& g, int fy, int fz, int cy, int cz, NbrRow row, int& row_base,
+                                       unsigned& fyz) {
+    const int fdy = g.fd[1], fdz = g.fd[2];
+    const bool pery = g.pbc & 2u, perz = g.pbc & 4u;
+    int ny = fy + row.dy, nz = fz + row.dz;
+    if (ny < 0) { if (!pery) return false; ny += fdy; } else if (ny >= fdy) { if (!pery) return false; ny -= fdy; }
+    if (nz < 0) { if (!perz) return false; nz += fdz; } else if (nz >= fdz) { if (!perz) return false; nz -= fdz; }
+    unsigned wy, wz, sy, sz;
+    if (!ref_adjacent(cy, div_k(ny, g.k[1], g.kmagic[1]), g.dims[1], pery, wy, sy)) return false;
+    if (!ref_adjacent(cz, div_k(nz, g.k[2], g.kmagic[2]), g.dims[2], perz, wz, sz)) return false;
+    row_base = (nz * fdy + ny) * g.fd[0];
+    const unsigned w = (wy << 1) | (wz << 2);
+    fyz = w | ((((sy << 1) | (sz << 2)) & w) << 3);
+    return true;
+}
+
 template <class F>
 __device__ __forceinline__ void gen_row_runs(const GridSpec& g, int fx, int fy, int fz, int cx, int cy, int cz,
                                              NbrRow row, F&& emit) {
@@ -521,52 +605,67 @@ constexpr unsigned RUN_SELF = 0x40u;  // flag bit: the home cell itself (pairs c
 
 // per-warp shared memory
 struct __align__(16) WarpShared {
-    float4 home[32];                 // home batch (position + id bits), NaN padded
-    unsigned rstart[MAX_RUNS];       // first atom (index into sorted4) of each run
-    unsigned rpos[MAX_RUNS + 4];     // stream position of each run (exclusive prefix of run lengths)
-    unsigned char rflag[MAX_RUNS];   // w | sgn << 3 | RUN_SELF
-    unsigned rbits[RUN_BITMAP_WORDS];  // bit p set <=> a run starts at stream position p (p < 32 * RUN_BITMAP_WORDS)
+    float4 home[32];                     // home batch (position + id bits), padded with far-away finite points
+    // One record per run of the candidate stream: x = first atom (index into the sorted array) MINUS the run's stream
+    // position, so that a candidate's address is x + its stream position; y = flags (w | sgn << 3 | RUN_SELF) in the
+    // low byte, the run's stream position above it.  Entry nr is the sentinel behind the last run: it maps stream
+    // positions >= T onto the padding records behind the sorted array.
+    uint2 rec[MAX_RUNS + 1];
+    unsigned rbits[RUN_BITMAP_WORDS + 2];
+    float hvdw[32];                      // vdW search: radii of the home batch  // bit p set <=> a run starts at stream position p (p < 32 * RUN_BITMAP_WORDS)
 };
 
-// Phase A of both pair kernels: lanes work on different neighbour rows of the home tile and append their runs
+// Phase A of the pair kernel: lanes work on different neighbour rows of the home tile and append their runs
 // (contiguous ranges of the sorted candidate array) to the warp's run table, direct runs of a batch of 32 rows
 // first, wrapped runs after them; `first` adds the self run in front.  Fills rows from row0 on until all rows are
 // in or the table (MAXR entries) is full; returns the number of runs (nr) and of candidates (T) and advances row0.
 template <int MAXR>
-__device__ __forceinline__ void fill_run_table(const SearchParams& P, unsigned* __restrict__ rstart,
-                                               unsigned* __restrict__ rpos, unsigned char* __restrict__ rflag, int fx,
-                                               int fy, int fz, int cx, int cy, int cz, unsigned hs, unsigned he,
-                                               bool first, unsigned lane, int& row0, unsigned& nr, unsigned& T,
-                                               unsigned* __restrict__ rbits = nullptr) {
+__device__ __forceinline__ void fill_run_table(const SearchParams& P, uint2* __restrict__ rec, int fx, int fy, int fz,
+                                               int cx, int cy, int cz, unsigned hs, unsigned he, bool first,
+                                               unsigned lane, int& row0, unsigned& nr, unsigned& T,
+                                               unsigned* __restrict__ rbits) {
     const GridSpec& g = P.g;
     nr = 0;
     T = 0;
     __syncwarp();
-    if (rbits) {
 #pragma unroll
-        for (int k = 0; k < RUN_BITMAP_WORDS / 32; ++k) rbits[k * 32 + lane] = 0u;
-        __syncwarp();
-    }
+    for (int k = 0; k < RUN_BITMAP_WORDS / 32; ++k) rbits[k * 32 + lane] = 0u;
+    if (lane < 2) rbits[RUN_BITMAP_WORDS + lane] = 0u;
+    __syncwarp();
     auto mark = [&](unsigned pos) {
-        if (rbits && pos < 32u * RUN_BITMAP_WORDS) atomicOr(&rbits[pos >> 5], 1u << (pos & 31u));
+        if (pos < 32u * RUN_BITMAP_WORDS) atomicOr(&rbits[pos >> 5], 1u << (pos & 31u));
     };
     if (first && !P.two_sets) {
         if (lane == 0) {
-            rstart[0] = hs;
-            rpos[0] = 0;
-            rflag[0] = RUN_SELF;
+            rec[0] = make_uint2(hs, RUN_SELF);
             mark(0u);
         }
         nr = 1;
         T = he - hs;
     }
+    // Tiles whose whole x reach stays inside the grid AND inside the reference cells next to the home one (most of
+    // them): every row is ONE run along x with no x flags, so the general run generator (periodic split, one
+    // adjacency decision per reference cell) is not needed — two cell_start loads per row.
+    const bool fast_x = fx + P.dx_min >= 0 && fx + P.dx_max < g.fd[0] &&
+                        div_k(fx + P.dx_min, g.k[0], g.kmagic[0]) >= cx - 1 &&
+                        div_k(fx + P.dx_max, g.k[0], g.kmagic[0]) <= cx + 1;
 #pragma unroll 1
     while (row0 < P.nrows) {
         const int ri = row0 + (int)lane;
         NbrRow row = P.rows[min(ri, P.nrows - 1)];
         // pass 1: count runs and atoms per class (direct / wrapped)
         unsigned nd = 0, nw = 0, ld = 0, lw = 0;
-        if (ri < P.nrows)
+        unsigned fs = 0, flen = 0, ff = 0;  // fast path: the row's single run
+        if (fast_x) {
+            int row_base;
+            if (ri < P.nrows && row_yz(g, fy, fz, cy, cz, row, row_base, ff)) {
+                fs = P.cell_startB[row_base + fx + row.dxlo];
+                flen = P.cell_startB[row_base + fx + row.dxhi + 1] - fs;
+                if (flen) {
+                    if (ff & 7u) { nw = 1; lw = flen; } else { nd = 1; ld = flen; }
+                }
+            }
+        } else if (ri < P.nrows)
             gen_row_runs(g, fx, fy, fz, cx, cy, cz, row, [&](int c0, int c1, unsigned f) {
                 unsigned len = P.cell_startB[c1 + 1] - P.cell_startB[c0];
                 if (len) {
@@ -588,16 +687,22 @@ __device__ __forceinline__ void fill_run_table(const SearchParams& P, unsigned* 
         // pass 2: write this lane's runs (direct runs of the batch first, then wrapped ones)
         unsigned sd = nr + (cni & 0xffffu) - nd, sw = nr + tot_d + (cni >> 16) - nw;
         unsigned pd = T + ldi - ld, pw = T + tot_ld + lwi - lw;
-        if (ri < P.nrows)
+        if (fast_x) {
+            if (flen) {
+                const unsigned at = (ff & 7u) ? sw : sd, pos = (ff & 7u) ? pw : pd;
+                rec[at] = make_uint2(fs - pos, ff | (pos << 8));
+                mark(pos);
+            }
+        } else if (ri < P.nrows)
             gen_row_runs(g, fx, fy, fz, cx, cy, cz, row, [&](int c0, int c1, unsigned f) {
                 unsigned s = P.cell_startB[c0], len = P.cell_startB[c1 + 1] - s;
                 if (len) {
                     if (f & 7u) {
-                        rstart[sw] = s; rpos[sw] = pw; rflag[sw] = (unsigned char)f;
+                        rec[sw] = make_uint2(s - pw, f | (pw << 8));
                         mark(pw);
                         ++sw; pw += len;
                     } else {
-                        rstart[sd] = s; rpos[sd] = pd; rflag[sd] = (unsigned char)f;
+                        rec[sd] = make_uint2(s - pd, f | (pd << 8));
                         mark(pd);
                         ++sd; pd += len;
                     }
@@ -607,8 +712,50 @@ __device__ __forceinline__ void fill_run_table(const SearchParams& P, unsigned* 
         T += tot_ld + tot_lw;
         row0 += 32;
     }
-    if (lane == 0) rpos[nr] = T;
+    if (lane == 0) {
+        rec[nr] = make_uint2((unsigned)P.n_sortedB - T, T << 8);  // sentinel: positions >= T read the padding records
+        mark(T);
+    }
     __syncwarp();
+}
+
+// inclusive warp scan step: v += (value of lane - o) for lanes >= o; the shuffle's own predicate says whether the
+// source lane exists, so no lane compare is needed
+__device__ __forceinline__ void scan_step(int& v, int o) {
+    asm volatile(
+        "{ .reg .pred p; .reg .b32 t;\n"
+        "  shfl.sync.up.b32 t|p, %0, %1, 0, 0xffffffff;\n"
+        "  @p add.s32 %0, %0, t; }"
+        : "+r"(v)
+        : "r"(o));
+}
+
+// Stage up to four entries (remaining hit bits, candidate id) of one candidate at [sp], [sp+8], ... and clear those
+// hits: entry k holds the mask with its k lowest hits removed, so the home slot of an entry is its lowest set bit.
+// lop3 with a predicate result clears the lowest bit and tells whether anything is left in one instruction.
+template <int OFF>
+__device__ __forceinline__ unsigned stage_hits4(unsigned e, unsigned id, unsigned sp) {
+    asm volatile(
+        "{ .reg .pred p, q; .reg .b32 t;\n"
+        "  setp.ne.u32 p, %0, 0;\n"
+        "  setp.eq.u32 q, 0, 0;\n"
+        "  @p st.shared.v2.u32 [%1+%3], {%0, %2};\n"
+        "  add.u32 t, %0, -1;\n"
+        "  lop3.and.b32 %0|p, %0, t, 0, 0xc0, q;\n"
+        "  @p st.shared.v2.u32 [%1+%4], {%0, %2};\n"
+        "  add.u32 t, %0, -1;\n"
+        "  lop3.and.b32 %0|p, %0, t, 0, 0xc0, q;\n"
+        "  @p st.shared.v2.u32 [%1+%5], {%0, %2};\n"
+        "  add.u32 t, %0, -1;\n"
+        "  lop3.and.b32 %0|p, %0, t, 0, 0xc0, q;\n"
+        "  @p st.shared.v2.u32 [%1+%6], {%0, %2};\n"
+        "  add.u32 t, %0, -1;\n"
+        "  and.b32 %0, %0, t;\n"
+        "}"
+        : "+r"(e)
+        : "r"(sp), "r"(id), "n"(OFF), "n"(OFF + 8), "n"(OFF + 16), "n"(OFF + 24)
+        : "memory");
+    return e;
 }
 
 // One warp per home tile = hx consecutive fine cells along x (dynamic work counter).
@@ -619,7 +766,13 @@ __device__ __forceinline__ void fill_run_table(const SearchParams& P, unsigned* 
 //           are broadcast from shared memory (one LDS.128 per home atom), hits are kept as per-lane
 //           bit masks and expanded into the staging buffer afterwards.
 // MODE: 0 pairs, 1 pairs + distances, 2 count only, 3 `within` flags (two sets)
-template <int MODE>
+//
+// Staging entries.  MODE 1: (home slot j, candidate id).  MODE 0: (remaining hit bits of the candidate, candidate id):
+// the home slot is the LOWEST set bit, decoded in the flush 32 entries per instruction — the expansion loop then
+// needs no bit search at all: store, clear the lowest bit (x & (x - 1)), repeat, both candidates of a lane in the
+// same iteration.
+// VDW: the cutoff of a pair is (vdw1[i] + vdw2[j]) + EPSILON instead of one number for all (two-set searches only).
+template <int MODE, bool VDW = false>
 __global__ void __launch_bounds__(SEARCH_WARPS * 32, 4) search_cells_kernel(const __grid_constant__ SearchParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const unsigned lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
@@ -632,10 +785,11 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32, 4) search_cells_kernel(cons
                                      wid * STAGE_CAP
                                : nullptr;
     const float4* __restrict__ home = ws.home;
-    const unsigned home_sa = smem_addr(ws.home);
+    const unsigned home_sa = smem_addr(ws.home), rec_sa = smem_addr(ws.rec), rbits_sa = smem_addr(ws.rbits);
     const unsigned stage_sa = stage ? smem_addr(stage) : 0u, staged_sa = stage_d ? smem_addr(stage_d) : 0u;
     int stage_n = 0;
     unsigned long long count = 0;
+    unsigned ntests = 0;  // MODE 2: distance tests this lane evaluated (FP32-pipe roofline of the count-only search)
     const GridSpec& g = P.g;
     const int fdx = g.fd[0], fdy = g.fd[1], fdz = g.fd[2];
     const int hx = g.hx, tdx = fdx / hx;  // tiles per x-row
@@ -645,6 +799,7 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32, 4) search_cells_kernel(cons
     // never produces a NaN (the direct path reads the SIGN of rc2 - d2)
     const float pad_home = 1.0e18f, pad_cand = -1.0e18f;
     const float finf = __int_as_float(0x7f800000);
+    const unsigned le_mask = (2u << lane) - 1u;
 
     for (;;) {
         unsigned tile = 0;
@@ -666,53 +821,89 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32, 4) search_cells_kernel(cons
         do {
             // ---------------- Phase A: fill the run table ----------------
             unsigned nr, T;
-            fill_run_table<MAX_RUNS>(P, ws.rstart, ws.rpos, ws.rflag, fx, fy, fz, cx, cy, cz, hs, he, first, lane, row0, nr, T,
-                                     ws.rbits);
-            const bool use_bits = T <= 32u * RUN_BITMAP_WORDS;  // every run start is in the bitmap
+            fill_run_table<MAX_RUNS>(P, ws.rec, fx, fy, fz, cx, cy, cz, hs, he, first, lane, row0, nr, T, ws.rbits);
+            const bool use_bits = T < 32u * RUN_BITMAP_WORDS;  // every run start AND the sentinel are in the bitmap
+            const unsigned selfT = (first && !P.two_sets) ? he - hs : 0u;  // stream positions of the self run
 
             // ---------------- Phase B: consume the stream ----------------
 #pragma unroll 1
             for (unsigned hb = hs; hb < he; hb += 32) {
                 const int nh = min(32u, he - hb);
                 __syncwarp();
-                ws.home[lane] = (lane < (unsigned)nh) ? __ldg(&P.sorted[hb + lane]) : make_float4(pad_home, pad_home, pad_home, 0.f);
+                {
+                    const float4 hrec = (lane < (unsigned)nh) ? __ldg(&P.sorted[hb + lane]) : make_float4(pad_home, pad_home, pad_home, 0.f);
+                    ws.home[lane] = hrec;
+                    if (VDW) ws.hvdw[lane] = (lane < (unsigned)nh) ? __ldg(&P.vdwA[__float_as_uint(hrec.w)]) : 0.f;
+                }
                 __syncwarp();
+                const unsigned valid_slots = nh >= 32 ? 0xffffffffu : ((1u << nh) - 1u);
                 unsigned cur0 = 0, cur1 = 0;
                 unsigned runs_before = 0;  // run starts at stream positions < c0 (bitmap path)
-                const unsigned le_mask = (2u << lane) - 1u;
-                unsigned hit_any = 0;  // MODE 3: bit j = home atom j has a set-2 atom within the cutoff
+                unsigned hit_any = 0;      // MODE 3: bit j = home atom j has a set-2 atom within the cutoff
 #pragma unroll 1
                 for (unsigned c0 = 0; c0 < T; c0 += 64) {
                     const unsigned p0 = c0 + lane, p1 = p0 + 32;
-                    float4 n0 = make_float4(pad_cand, pad_cand, pad_cand, 0.f), n1 = n0;  // never within the cutoff
-                    unsigned f0 = 0, f1 = 0, a0i = 0, a1i = 0;
+                    float4 n0, n1;
+                    unsigned f0, f1, a0i, a1i;
                     if (use_bits) {
                         // run index of a stream position = (run starts at positions <= it) - 1: two broadcast words
-                        // and a popcount instead of a per-lane search
-                        const unsigned w0 = ws.rbits[c0 >> 5], w1 = ws.rbits[(c0 >> 5) + 1];
-                        cur0 = runs_before + __popc(w0 & le_mask) - 1u;
-                        cur1 = runs_before + __popc(w0) + __popc(w1 & le_mask) - 1u;
-                        runs_before += __popc(w0) + __popc(w1);
-                    }
-                    if (p0 < T) {
-                        if (!use_bits)
-                            while (ws.rpos[cur0 + 1] <= p0) ++cur0;
-                        a0i = ws.rstart[cur0] + (p0 - ws.rpos[cur0]);
-                        f0 = ws.rflag[cur0];
+                        // and a popcount instead of a per-lane search.  Positions >= T fall into the sentinel run,
+                        // whose records are the far-away padding behind the sorted array: no bounds checks.
+                        const uint2 bw = lds64(rbits_sa + (c0 >> 5) * 4u);
+                        const unsigned pw0 = __popc(bw.x);
+                        cur0 = runs_before + __popc(bw.x & le_mask) - 1u;
+                        cur1 = runs_before + pw0 + __popc(bw.y & le_mask) - 1u;
+                        runs_before += pw0 + __popc(bw.y);
+                        const uint2 r0 = lds64(rec_sa + cur0 * 8u), r1 = lds64(rec_sa + cur1 * 8u);
+                        a0i = r0.x + p0;
+                        a1i = r1.x + p1;
                         n0 = __ldg(&P.sortedB[a0i]);
-                    }
-                    if (p1 < T) {
-                        if (!use_bits) {
-                            cur1 = max(cur1, cur0);
-                            while (ws.rpos[cur1 + 1] <= p1) ++cur1;
-                        }
-                        a1i = ws.rstart[cur1] + (p1 - ws.rpos[cur1]);
-                        f1 = ws.rflag[cur1];
                         n1 = __ldg(&P.sortedB[a1i]);
+                        f0 = r0.y;
+                        f1 = r1.y;
+                    } else {
+                        // very long streams (dense systems): per-lane forward search over the run positions
+                        n0 = make_float4(pad_cand, pad_cand, pad_cand, 0.f);
+                        n1 = n0;
+                        f0 = f1 = a0i = a1i = 0;
+                        if (p0 < T) {
+                            while ((ws.rec[cur0 + 1].y >> 8) <= p0) ++cur0;
+                            const uint2 r0 = ws.rec[cur0];
+                            a0i = r0.x + p0;
+                            f0 = r0.y;
+                            n0 = __ldg(&P.sortedB[a0i]);
+                        }
+                        if (p1 < T) {
+                            cur1 = max(cur1, cur0);
+                            while ((ws.rec[cur1 + 1].y >> 8) <= p1) ++cur1;
+                            const uint2 r1 = ws.rec[cur1];
+                            a1i = r1.x + p1;
+                            f1 = r1.y;
+                            n1 = __ldg(&P.sortedB[a1i]);
+                        }
                     }
                     unsigned m0 = 0, m1 = 0;
-                    const unsigned valid_slots = nh >= 32 ? 0xffffffffu : ((1u << nh) - 1u);
-                    if (!__any_sync(0xffffffffu, (f0 | f1) != 0u)) {
+                    float vc0 = 0.f, vc1 = 0.f;  // vdW radii of the two candidates (padding records carry local id 0)
+                    if (VDW) {
+                        vc0 = __ldg(&P.vdwB[__float_as_uint(n0.w)]);
+                        vc1 = __ldg(&P.vdwB[__float_as_uint(n1.w)]);
+                    }
+                    const bool any_wrapped = __any_sync(0xffffffffu, ((f0 | f1) & 7u) != 0u);
+                    if (VDW && any_wrapped) {
+                        // vdW search, step with wrapped cell pairs: every test with the reference's own expression
+                        // (direct difference or PeriodicBox::distance_squared) against the pair's own cutoff
+                        for (int j = 0; j < nh; ++j) {
+                            const float4 hh = home[j];
+                            const float hv = ws.hvdw[j];
+                            const float cut0 = xadd(xadd(hv, vc0), FLT_EPSILON), cut1 = xadd(xadd(hv, vc1), FLT_EPSILON);
+                            const float d0 = (f0 & 7u) ? d2_pbc_call(P.g.box, hh.x, hh.y, hh.z, n0.x, n0.y, n0.z, f0 & 7u)
+                                                       : d2_direct(hh.x, hh.y, hh.z, n0.x, n0.y, n0.z);
+                            const float d1 = (f1 & 7u) ? d2_pbc_call(P.g.box, hh.x, hh.y, hh.z, n1.x, n1.y, n1.z, f1 & 7u)
+                                                       : d2_direct(hh.x, hh.y, hh.z, n1.x, n1.y, n1.z);
+                            if (d0 <= xmul(cut0, cut0)) m0 |= 1u << j;
+                            if (d1 <= xmul(cut1, cut1)) m1 |= 1u << j;
+                        }
+                    } else if (!any_wrapped) {
                         // ---- all 64 candidates come from un-wrapped cell pairs: direct difference ----
                         // x + 0 is exact: the FADD2 only serves to give each packed coordinate its own aligned
                         // register pair (ptxas otherwise re-packs the halves in front of every use)
@@ -723,13 +914,25 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32, 4) search_cells_kernel(cons
                         // (the sign of rc2 - d2) into the accumulators with one funnel shift, so that slot j ends
                         // up at bit j.
                         const unsigned long long one2 = pk2_once(P.one, P.one), rc22 = pk2_once(rc2, rc2);
+                        const unsigned long long mone2 = pk2(-P.one, -P.one), vc2 = pk2(vc0, vc1),
+                                                 eps2 = pk2(FLT_EPSILON, FLT_EPSILON);
                         const int nh4 = (nh + 3) & ~3;
                         unsigned a0 = 0, a1 = 0;
 #pragma unroll 1
                         for (int gj = nh4 - 4; gj >= 0; gj -= 4) {
 #pragma unroll
                             for (int jj = 3; jj >= 0; --jj) {
-                                const unsigned long long t = rc2_minus_d2(nx, ny, nz, home[gj + jj], one2, rc22);
+                                unsigned long long t;
+                                if (VDW) {
+                                    // cutoff = (vdw1[i] + vdw2[j]) + EPSILON, squared (distance_search.rs:392-393): packed,
+                                    // every operation rounded on its own; c*c - d2 as fma(d2, -1.0, c*c) with a run-time
+                                    // -1.0 so that ptxas cannot contract the product into the subtraction
+                                    const float hv = ws.hvdw[gj + jj];
+                                    const unsigned long long cc = add2(add2(pk2(hv, hv), vc2), eps2);
+                                    t = cut2_minus_d2(nx, ny, nz, home[gj + jj], one2, mone2, mul2(cc, cc));
+                                } else {
+                                    t = rc2_minus_d2(nx, ny, nz, home[gj + jj], one2, rc22);
+                                }
                                 float t0, t1;
                                 upk2(t, t0, t1);
                                 a0 = __funnelshift_l(__float_as_uint(t0), a0, 1);
@@ -738,8 +941,19 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32, 4) search_cells_kernel(cons
                         }
                         m0 = ~a0 & valid_slots;
                         m1 = ~a1 & valid_slots;
+                        // home cell against itself (first stream positions): keep (home j, atom a) only for a > hb + j
+                        if (c0 < selfT) {
+                            if (f0 & RUN_SELF) {
+                                const int lim = min(max((int)a0i - (int)hb, 0), 32);
+                                m0 &= lim >= 32 ? 0xffffffffu : ((1u << lim) - 1u);
+                            }
+                            if (f1 & RUN_SELF) {
+                                const int lim = min(max((int)a1i - (int)hb, 0), 32);
+                                m1 &= lim >= 32 ? 0xffffffffu : ((1u << lim) - 1u);
+                            }
+                        }
                     } else {
-                        // ---- mixed step: self cell (index-order filter) and/or wrapped cell pairs.
+                        // ---- mixed step: wrapped cell pairs (and possibly the self cell).
                         // Wrapped candidates are tested on the lattice-shifted image; outside the band
                         // [lo,hi] around cutoff^2 that test is decisive, inside it (and always, when the
                         // filter's preconditions do not hold: lo=-1, hi=inf) the reference's exact
@@ -814,69 +1028,85 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32, 4) search_cells_kernel(cons
                     const int c0n = __popc(m0), c1n = __popc(m1);
                     if (MODE == 2) {
                         count += c0n + c1n;
+                        ntests += 2u * (unsigned)((nh + 3) & ~3);  // per lane: two candidates x the home slots visited
                         continue;
                     }
-                    // one scan for both atoms of the lane: low 16 bits = first, high 16 bits = second
-                    int inc = c0n | (c1n << 16);
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-                        int t = __shfl_up_sync(0xffffffffu, inc, o);
-                        if (lane >= (unsigned)o) inc += t;
-                    }
+                    // inclusive scan of the hits per lane (both candidates together: a lane's second candidate is
+                    // staged right behind its first)
+                    const int cnt = c0n + c1n;
+                    int inc = cnt;
+                    scan_step(inc, 1);
+                    scan_step(inc, 2);
+                    scan_step(inc, 4);
+                    scan_step(inc, 8);
+                    scan_step(inc, 16);
                     const int tot = __shfl_sync(0xffffffffu, inc, 31);
-                    const int t0 = tot & 0xffff, t1 = tot >> 16;
-                    if (t0 + t1 == 0) continue;
-                    // Expand the masks into the staging buffer.  Normally one pass; if the step found more
-                    // pairs than the buffer holds, per half (<= 1024) or per half and 16-lane group (<= 512).
-                    const int i0 = inc & 0xffff, i1 = inc >> 16;  // inclusive prefixes per half
-                    const int g15 = __shfl_sync(0xffffffffu, inc, 15);
-                    const int q0 = g15 & 0xffff, q1 = g15 >> 16;  // hits of lanes 0..15 per half
-                    const int npass = (t0 + t1 <= STAGE_CAP) ? 1 : ((t0 <= STAGE_CAP && t1 <= STAGE_CAP) ? 2 : 4);
+                    if (tot == 0) continue;
+                    // Expand the masks into the staging buffer.  Normally one pass; a step that found more pairs
+                    // than the buffer holds goes through four (one candidate per lane x one 16-lane group: <= 512).
+                    const int npass = tot <= STAGE_CAP ? 1 : 4;
 #pragma unroll 1
                     for (int pass = 0; pass < npass; ++pass) {
-                        bool use0 = true, use1 = true;
-                        int base0 = 0, base1 = t0, need = t0 + t1;
-                        if (npass == 2) {
-                            use0 = pass == 0;
-                            use1 = pass == 1;
-                            base1 = 0;
-                            need = pass ? t1 : t0;
-                        } else if (npass == 4) {
-                            const int hh = pass >> 1, grp = pass & 1;
-                            const bool act = (int)(lane >> 4) == grp;
-                            use0 = act && hh == 0;
-                            use1 = act && hh == 1;
-                            base0 = grp ? -q0 : 0;
-                            base1 = grp ? -q1 : 0;
-                            need = hh ? (grp ? t1 - q1 : q1) : (grp ? t0 - q0 : q0);
+                        unsigned e0 = m0, e1 = m1;
+                        int off = inc - cnt, need = tot;  // exclusive prefix of this lane, entries of this pass
+                        if (npass != 1) {
+                            const bool act = (int)(lane >> 4) == (pass & 1);
+                            e0 = (act && pass < 2) ? m0 : 0u;
+                            e1 = (act && pass >= 2) ? m1 : 0u;
+                            int v = __popc(e0) + __popc(e1), vi = v;
+                            scan_step(vi, 1);
+                            scan_step(vi, 2);
+                            scan_step(vi, 4);
+                            scan_step(vi, 8);
+                            scan_step(vi, 16);
+                            need = __shfl_sync(0xffffffffu, vi, 31);
+                            off = vi - v;
                         }
-                        if (stage_n + need > STAGE_CAP) warp_flush<MODE == 1>(stage_sa, staged_sa, home_sa, stage_n, P, lane);
-                        unsigned e0 = use0 ? m0 : 0u;
-                        unsigned e1 = use1 ? m1 : 0u;
-                        unsigned sp0 = stage_sa + 8u * (unsigned)(stage_n + base0 + i0 - c0n);
-                        unsigned sp1 = stage_sa + 8u * (unsigned)(stage_n + base1 + i1 - c1n);
-                        unsigned dp0 = staged_sa + 4u * (unsigned)(stage_n + base0 + i0 - c0n);
-                        unsigned dp1 = staged_sa + 4u * (unsigned)(stage_n + base1 + i1 - c1n);
+                        if (stage_n + need > STAGE_CAP) warp_flush<MODE>(stage_sa, staged_sa, home_sa, stage_n, P, lane);
+                        unsigned sp0 = stage_sa + 8u * (unsigned)(stage_n + off);
+                        unsigned sp1 = sp0 + 8u * (unsigned)__popc(e0);
                         const unsigned id0 = __float_as_uint(n0.w), id1 = __float_as_uint(n1.w);
-                        while (e0) {
-                            const int j = bfind32(e0);
-                            e0 ^= 1u << j;
-                            sts64(sp0, (unsigned)j, id0);
-                            sp0 += 8u;
-                            if (MODE == 1) {
+                        if (MODE == 0) {
+                            // both candidates of the lane advance together, four entries each per round; the
+                            // number of rounds is warp-uniform (largest hit count of any candidate)
+                            const int kmax = __reduce_max_sync(0xffffffffu, max(__popc(e0), __popc(e1)));
+                            // straight-line for the first twelve hits per candidate (warp-uniform branches), a loop beyond
+                            e0 = stage_hits4<0>(e0, id0, sp0);
+                            e1 = stage_hits4<0>(e1, id1, sp1);
+                            if (kmax > 4) {
+                                e0 = stage_hits4<32>(e0, id0, sp0);
+                                e1 = stage_hits4<32>(e1, id1, sp1);
+                                if (kmax > 8) {
+                                    e0 = stage_hits4<64>(e0, id0, sp0);
+                                    e1 = stage_hits4<64>(e1, id1, sp1);
+#pragma unroll 1
+                                    for (int k = 12; k < kmax; k += 4) {
+                                        sp0 += 32u;
+                                        sp1 += 32u;
+                                        e0 = stage_hits4<64>(e0, id0, sp0);
+                                        e1 = stage_hits4<64>(e1, id1, sp1);
+                                    }
+                                }
+                            }
+                        } else {
+                            unsigned dp0 = staged_sa + 4u * (unsigned)(stage_n + off);
+                            unsigned dp1 = dp0 + 4u * (unsigned)__popc(e0);
+                            while (e0) {
+                                const int j = bfind32(e0);
+                                e0 ^= 1u << j;
+                                sts64(sp0, (unsigned)j, id0);
+                                sp0 += 8u;
                                 const float4 h = home[j];
                                 float d2 = (f0 & 7u) ? d2_pbc_call(P.g.box, h.x, h.y, h.z, n0.x, n0.y, n0.z, f0 & 7u)
                                                      : d2_direct(h.x, h.y, h.z, n0.x, n0.y, n0.z);
                                 sts32f(dp0, __fsqrt_rn(d2));
                                 dp0 += 4u;
                             }
-                        }
-                        while (e1) {
-                            const int j = bfind32(e1);
-                            e1 ^= 1u << j;
-                            sts64(sp1, (unsigned)j, id1);
-                            sp1 += 8u;
-                            if (MODE == 1) {
+                            while (e1) {
+                                const int j = bfind32(e1);
+                                e1 ^= 1u << j;
+                                sts64(sp1, (unsigned)j, id1);
+                                sp1 += 8u;
                                 const float4 h = home[j];
                                 float d2 = (f1 & 7u) ? d2_pbc_call(P.g.box, h.x, h.y, h.z, n1.x, n1.y, n1.z, f1 & 7u)
                                                      : d2_direct(h.x, h.y, h.z, n1.x, n1.y, n1.z);
@@ -892,7 +1122,7 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32, 4) search_cells_kernel(cons
                     if (lane < (unsigned)nh && ((hit_any >> lane) & 1u)) P.flags[__float_as_uint(home[lane].w)] = 1;
                 }
                 // staged entries name home atoms by their slot in ws.home: write them out before it changes
-                if (MODE == 0 || MODE == 1) warp_flush<MODE == 1>(stage_sa, staged_sa, home_sa, stage_n, P, lane);
+                if (MODE == 0 || MODE == 1) warp_flush<MODE>(stage_sa, staged_sa, home_sa, stage_n, P, lane);
             }
             first = false;
         } while (row0 < P.nrows);
@@ -901,10 +1131,10 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32, 4) search_cells_kernel(cons
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) count += __shfl_xor_sync(0xffffffffu, count, o);
         if (lane == 0 && count) atomicAdd(P.counter, count);
+        if (lane == 0 && ntests) atomicAdd(P.counter + 2, 32ull * ntests);  // every lane evaluated the same number
     }
 }
 
-#include "mb_search_lanes.cuh"
 
 // ---------------------------------------------------------------------------------------------
 // general all-pairs kernel: any grid (degenerate dims, partial PBC), two sets, `within`.
@@ -1231,7 +1461,6 @@ struct Plan {
     GridSpec g;
     bool use_cells;
     bool full_shell;  // two-set search: rows cover both half-spaces and the home row entirely
-    bool lane_tiles;  // tile size chosen for search_lanes_kernel (one home atom per lane)
     int fast_pbc;
     float rc2_lo, rc2_hi;
     int nrows;
@@ -1245,7 +1474,6 @@ struct Plan {
 static void plan_cells(const Ctx* c, Plan& pl, float cutoff, size_t n) {
     GridSpec& g = pl.g;
     pl.use_cells = false;
-    pl.lane_tiles = c->opt_lane_kernel != 0;
     for (int d = 0; d < 3; ++d) {
         g.k[d] = 1;
         g.kmagic[d] = 0;
@@ -1304,41 +1532,6 @@ static void plan_cells(const Ctx* c, Plan& pl, float cutoff, size_t n) {
         }
     }
     int hx_auto = 3;  // x slices per home tile (swept on B200)
-    if (pl.lane_tiles && c->opt_subdiv <= 0) {
-        // search_lanes_kernel: one home atom per lane, so a tile should hold close to (but rarely more
-        // than) 32 atoms.  Pick the subdivision that minimises the modelled cost per pair:
-        //   cost(tile) = batches * candidates * c_slot + c_tile,   pairs(tile) ~ mean population m
-        // with candidates = rho/2 * volume of the tile dilated by the cutoff, batches = E[ceil(X/32)],
-        // X ~ Poisson(m) (normal tail), c_slot = 32 lanes * 0.32 instructions, c_tile = 1500 instructions.
-        const double rho = pl.volume > 0 ? (double)n / pl.volume : 0.0;
-        double best = -1.0;
-        int kb[3] = {k[0], k[1], k[2]};
-        for (int k0 = 1; k0 <= 8; ++k0)
-            for (int k1 = 1; k1 <= 8; ++k1)
-                for (int k2 = 1; k2 <= 8; ++k2) {
-                    const double t0 = tref[0] / k0, t1 = tref[1] / k1, t2 = tref[2] / k2;
-                    const double m = (double)n / ((double)pl.ncells * k0 * k1 * k2);
-                    if (m < 2.0 && !(k0 == 1 && k1 == 1 && k2 == 1)) continue;
-                    double batches = 1.0;
-                    for (int j = 1; j < 64; ++j) {
-                        const double pj = 0.5 * std::erfc((32.0 * j + 0.5 - m) / std::sqrt(2.0 * std::max(m, 1e-9)));
-                        if (pj < 1e-9) break;
-                        batches += pj;
-                    }
-                    const double V = t0 * t1 * t2 + 2.0 * rc * (t0 * t1 + t1 * t2 + t0 * t2) +
-                                     3.14159265 * rc * rc * (t0 + t1 + t2) + 4.18879 * rc * rc * rc;
-                    const double cost = batches * (0.5 * rho * V) * 32.0 * 0.32 + 1500.0;
-                    const double score = m / cost;
-                    if (score > best) {
-                        best = score;
-                        kb[0] = k0;
-                        kb[1] = k1;
-                        kb[2] = k2;
-                    }
-                }
-        for (int d = 0; d < 3; ++d) k[d] = kb[d];
-        hx_auto = std::max(1, std::min(8, (int)std::floor(tref[0] / k[0] / (0.16 * rc) + 0.5)));
-    }
     // optional per-dimension overrides and the x slicing of the home tile
     if (c->opt_subdiv_xyz[0] > 0) k[0] = std::min(c->opt_subdiv_xyz[0], 8);
     if (c->opt_subdiv_xyz[1] > 0) k[1] = std::min(c->opt_subdiv_xyz[1], 8);
@@ -1468,7 +1661,7 @@ struct PlanKey {
     unsigned pbc;
     size_t n;
     float m[9];
-    int subdiv, brute, exact_pbc, sx, sy, sz, slice, full, lane;
+    int subdiv, brute, exact_pbc, sx, sy, sz, slice, full;
     double apc;
 };
 struct PlanCache {
@@ -1490,17 +1683,8 @@ static int upload_ids(Ctx* c, DevBuf& buf, const uint64_t* ids, size_t n, const 
     return MB_OK;
 }
 
-static int check_sel(const Ctx* c, const uint64_t* ids, size_t n, size_t n_atoms, const char* what) {
-    if (n == 0) return fail(MB_ERR_ARG, "%s: empty selection", what);
-    if (!ids) {
-        if (n > n_atoms) return fail(MB_ERR_ARG, "%s: identity selection of %zu > %zu atoms", what, n, n_atoms);
-        return MB_OK;
-    }
-    // sorted global indices (providers.rs:45-48): checking the last one bounds them all
-    if (ids[n - 1] >= n_atoms || ids[0] >= n_atoms)
-        return fail(MB_ERR_ARG, "%s: index %llu out of range (%zu atoms)", what, (unsigned long long)ids[n - 1], n_atoms);
-    (void)c;
-    return MB_OK;
+static int check_sel(const Ctx*, const uint64_t* ids, size_t n, size_t n_atoms, const char* what) {
+    return validate_sel(ids, n, n_atoms, what);
 }
 
 // bounds of a selection on the device -> host (one small sync)
@@ -1556,7 +1740,6 @@ static int get_plan_pbc(Ctx* c, float cutoff, uint8_t pbc, size_t n, Plan& out, 
     k.sz = c->opt_subdiv_xyz[2];
     k.slice = c->opt_slice_x;
     k.full = full_shell ? 1 : 0;
-    k.lane = c->opt_lane_kernel;
     k.apc = c->opt_atoms_per_cell;
     PlanCache* pc = static_cast<PlanCache*>(c->plan_cache);
     if (!pc) {
@@ -1623,29 +1806,17 @@ static int bin_set(Ctx* c, const float* xyz, const unsigned long long* d_ids, si
     return MB_OK;
 }
 
-static bool lanes_enabled(const Ctx* c, int mode, const SearchParams& P) {
-    if (!c->opt_lane_kernel) return false;
-    if (mode == 1 && P.n_sortedB >= (1ull << 28)) return false;
-    return true;
-}
-
 template <int MODE>
 static int launch_search_cells(Ctx* c, const SearchParams& P) {
-    // search_lanes_kernel (one home atom per lane) unless switched off; its distance entries hold a
-    // 28-bit sorted index, so very large selections keep the mask kernel when distances are wanted
-    const bool use_lanes = lanes_enabled(c, MODE, P);
     size_t smem = SEARCH_WARPS * sizeof(WarpShared);
     if (MODE == 0 || MODE == 1) smem += SEARCH_WARPS * STAGE_CAP * sizeof(uint2);
     if (MODE == 1) smem += SEARCH_WARPS * STAGE_CAP * sizeof(float);
     int per_sm = 1;
-    if (use_lanes) {
-        smem = LANE_WARPS * sizeof(LaneShared);
-        MB_CUDA(cudaFuncSetAttribute(search_lanes_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        MB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, search_lanes_kernel<MODE>, LANE_WARPS * 32, smem));
-    } else {
-        MB_CUDA(cudaFuncSetAttribute(search_cells_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        MB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, search_cells_kernel<MODE>, SEARCH_WARPS * 32, smem));
-    }
+    constexpr bool CAN_VDW = MODE == 0 || MODE == 1;
+    const bool vdw = CAN_VDW && P.vdwA != nullptr;
+    auto kern = vdw ? search_cells_kernel<MODE, CAN_VDW> : search_cells_kernel<MODE, false>;
+    MB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, SEARCH_WARPS * 32, smem));
     if (per_sm < 1) per_sm = 1;
     int blocks = c->sm_count * per_sm;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -1654,11 +1825,7 @@ static int launch_search_cells(Ctx* c, const SearchParams& P) {
         MB_CUDA(cudaEventCreate(&e1));
         MB_CUDA(cudaEventRecord(e0, c->stream));
     }
-    if (use_lanes) {
-        search_lanes_kernel<MODE><<<blocks, LANE_WARPS * 32, smem, c->stream>>>(P);
-    } else {
-        search_cells_kernel<MODE><<<blocks, SEARCH_WARPS * 32, smem, c->stream>>>(P);
-    }
+    kern<<<blocks, SEARCH_WARPS * 32, smem, c->stream>>>(P);
     c->launches++;
     if (c->opt_profile) {
         MB_CUDA(cudaEventRecord(e1, c->stream));
@@ -1676,9 +1843,9 @@ int enqueue_cells_search(Ctx* c, const float* xyz, const unsigned long long* d_i
     const GridSpec& g = pl.g;
     MB_TRY(c->cell_count.reserve((pl.ncells + 1) * sizeof(unsigned)));
     MB_TRY(c->cell_start.reserve((pl.ncells + 2) * sizeof(unsigned)));
-    MB_TRY(c->sorted4.reserve((n + 32) * sizeof(float4)));
+    MB_TRY(c->sorted4.reserve((n + PAD_CANDS) * sizeof(float4)));
     MB_CUDA(cudaMemsetAsync(c->cell_count.p, 0, (pl.ncells + 1) * sizeof(unsigned), c->stream));
-    MB_CUDA(cudaMemsetAsync(d_counter, 0, 2 * sizeof(unsigned long long), c->stream));
+    MB_CUDA(cudaMemsetAsync(d_counter, 0, CNT_STRIDE * sizeof(unsigned long long), c->stream));
     MB_TRY(bin_set(c, xyz, d_ids, n, g, c->tmp4a, c->cellid_a, &c->rank_a, c->cell_count.as<unsigned>(), nullptr));
     MB_TRY(exclusive_scan_u32(c, c->cell_count.as<unsigned>(), (int)pl.ncells, c->cell_start.as<unsigned>()));
     scatter_kernel<<<(int)((n + 255) / 256), 256, 0, c->stream>>>(c->tmp4a.as<float4>(), c->cellid_a.as<unsigned>(),
@@ -1692,6 +1859,7 @@ int enqueue_cells_search(Ctx* c, const float* xyz, const unsigned long long* d_i
     P.cell_startB = P.cell_start;
     P.two_sets = 0;
     P.flags = nullptr;
+    P.vdwA = P.vdwB = nullptr;
     P.g = g;
     P.rc2 = cutoff * cutoff;
     P.one = 1.0f;
@@ -1700,6 +1868,12 @@ int enqueue_cells_search(Ctx* c, const float* xyz, const unsigned long long* d_i
     P.fast_pbc = pl.fast_pbc;
     P.nrows = pl.nrows;
     memcpy(P.rows, pl.rows, sizeof(NbrRow) * pl.nrows);
+    P.dx_min = 127;
+    P.dx_max = -128;
+    for (int r = 0; r < pl.nrows; ++r) {
+        P.dx_min = std::min(P.dx_min, (int)pl.rows[r].dxlo);
+        P.dx_max = std::max(P.dx_max, (int)pl.rows[r].dxhi);
+    }
     P.pairs = c->pairs.as<uint2>();
     P.dists = c->dists.as<float>();
     P.pair_cap = c->pair_cap;
@@ -1714,20 +1888,22 @@ int enqueue_cells_search(Ctx* c, const float* xyz, const unsigned long long* d_i
 // binned on the same fine grid; the neighbour table covers the full shell.  kmode 0/1 pairs, 3 flags.
 static int enqueue_cells_search2(Ctx* c, const float* xyz1, const unsigned long long* d_ids1, size_t n1,
                                  const float* xyz2, const unsigned long long* d_ids2, size_t n2, const Plan& pl,
-                                 float cutoff, int kmode, unsigned long long* d_counter) {
+                                 float cutoff, int kmode, unsigned long long* d_counter,
+                                 const float* d_vdw1 = nullptr, const float* d_vdw2 = nullptr) {
     const GridSpec& g = pl.g;
     const size_t cb = (pl.ncells + 2) * sizeof(unsigned);
     MB_TRY(c->cell_count.reserve(cb));
     MB_TRY(c->cell_start.reserve(cb));
     MB_TRY(c->cell_count_b.reserve(cb));
     MB_TRY(c->cell_start_b.reserve(cb));
-    MB_TRY(c->sorted4.reserve((n1 + 32) * sizeof(float4)));
-    MB_TRY(c->sorted4_b.reserve((n2 + 32) * sizeof(float4)));
+    MB_TRY(c->sorted4.reserve((n1 + PAD_CANDS) * sizeof(float4)));
+    MB_TRY(c->sorted4_b.reserve((n2 + PAD_CANDS) * sizeof(float4)));
     MB_CUDA(cudaMemsetAsync(c->cell_count.p, 0, (pl.ncells + 1) * sizeof(unsigned), c->stream));
     MB_CUDA(cudaMemsetAsync(c->cell_count_b.p, 0, (pl.ncells + 1) * sizeof(unsigned), c->stream));
-    MB_CUDA(cudaMemsetAsync(d_counter, 0, 2 * sizeof(unsigned long long), c->stream));
-    MB_TRY(bin_set(c, xyz1, d_ids1, n1, g, c->tmp4a, c->cellid_a, &c->rank_a, c->cell_count.as<unsigned>(), nullptr));
-    MB_TRY(bin_set(c, xyz2, d_ids2, n2, g, c->tmp4b, c->cellid_b, &c->rank_b, c->cell_count_b.as<unsigned>(), nullptr));
+    MB_CUDA(cudaMemsetAsync(d_counter, 0, CNT_STRIDE * sizeof(unsigned long long), c->stream));
+    const int local_ids = d_vdw1 ? 1 : 0;  // vdW searches report LOCAL indices, which also index the radii
+    MB_TRY(bin_set(c, xyz1, d_ids1, n1, g, c->tmp4a, c->cellid_a, &c->rank_a, c->cell_count.as<unsigned>(), nullptr, local_ids));
+    MB_TRY(bin_set(c, xyz2, d_ids2, n2, g, c->tmp4b, c->cellid_b, &c->rank_b, c->cell_count_b.as<unsigned>(), nullptr, local_ids));
     MB_TRY(exclusive_scan_u32(c, c->cell_count.as<unsigned>(), (int)pl.ncells, c->cell_start.as<unsigned>()));
     MB_TRY(exclusive_scan_u32(c, c->cell_count_b.as<unsigned>(), (int)pl.ncells, c->cell_start_b.as<unsigned>()));
     scatter_kernel<<<(int)((n1 + 255) / 256), 256, 0, c->stream>>>(c->tmp4a.as<float4>(), c->cellid_a.as<unsigned>(),
@@ -1744,6 +1920,8 @@ static int enqueue_cells_search2(Ctx* c, const float* xyz1, const unsigned long 
     P.cell_startB = c->cell_start_b.as<unsigned>();
     P.two_sets = 1;
     P.flags = c->flags.as<unsigned char>();
+    P.vdwA = d_vdw1;
+    P.vdwB = d_vdw2;
     P.g = g;
     P.rc2 = cutoff * cutoff;
     P.one = 1.0f;
@@ -1752,6 +1930,12 @@ static int enqueue_cells_search2(Ctx* c, const float* xyz1, const unsigned long 
     P.fast_pbc = pl.fast_pbc;
     P.nrows = pl.nrows;
     memcpy(P.rows, pl.rows, sizeof(NbrRow) * pl.nrows);
+    P.dx_min = 127;
+    P.dx_max = -128;
+    for (int r = 0; r < pl.nrows; ++r) {
+        P.dx_min = std::min(P.dx_min, (int)pl.rows[r].dxlo);
+        P.dx_max = std::max(P.dx_max, (int)pl.rows[r].dxhi);
+    }
     P.pairs = c->pairs.as<uint2>();
     P.dists = c->dists.as<float>();
     P.pair_cap = c->pair_cap;
@@ -1851,7 +2035,7 @@ int search_single_impl(Ctx* c, float cutoff, const uint64_t* ids, size_t n, uint
         if (pl.use_cells) {
             MB_TRY(enqueue_cells_search(c, c->d_xyz, d_ids, n, pl, cutoff, kmode, d_counter));
         } else {
-            MB_CUDA(cudaMemsetAsync(d_counter, 0, 2 * sizeof(unsigned long long), c->stream));
+            MB_CUDA(cudaMemsetAsync(d_counter, 0, CNT_STRIDE * sizeof(unsigned long long), c->stream));
             MB_TRY(bin_set(c, c->d_xyz, d_ids, n, pl.g, c->tmp4a, c->cellid_a, nullptr, nullptr, &c->refcell_a));
             MB_TRY(enqueue_brute(c, pl, cutoff, 0, with_dist, mode == 2, n, n, c->tmp4a.as<float4>(),
                                  c->refcell_a.as<unsigned long long>(), c->tmp4a.as<float4>(),
@@ -1927,10 +2111,10 @@ static int search_two_sets(Ctx* c, float cutoff, const uint64_t* ids1, size_t n1
     }
     const bool with_dist = !within && c->opt_with_dist;
     // Cell path when the all-pairs product is large and the grid is not degenerate; the general
-    // all-pairs kernel otherwise (small sets, 1-2 reference cells in a periodic dim, vdW radii).
+    // all-pairs kernel otherwise (small sets, 1-2 reference cells in a periodic dim).
     pl.full_shell = true;
     bool cells = false;
-    if (!vdw && (double)n1 * (double)n2 > c->opt_two_set_cells_min && n1 <= 0x7fffffffull && n2 <= 0x7fffffffull) {
+    if ((double)n1 * (double)n2 > c->opt_two_set_cells_min && n1 <= 0x7fffffffull && n2 <= 0x7fffffffull) {
         if (pbc) {
             MB_TRY(get_plan_pbc(c, cutoff, pbc, std::max(n1, (size_t)4096), pl, true));
         } else {
@@ -1994,9 +2178,9 @@ static int search_two_sets(Ctx* c, float cutoff, const uint64_t* ids1, size_t n1
         for (int attempt = 0; attempt < 3; ++attempt) {
             if (cells) {
                 MB_TRY(enqueue_cells_search2(c, c->d_xyz, d_ids1, n1, xyz2, d_ids2, n2, pl, cutoff, with_dist ? 1 : 0,
-                                             d_counter));
+                                             d_counter, d_vdw1, d_vdw2));
             } else {
-                MB_CUDA(cudaMemsetAsync(d_counter, 0, 2 * sizeof(unsigned long long), c->stream));
+                MB_CUDA(cudaMemsetAsync(d_counter, 0, CNT_STRIDE * sizeof(unsigned long long), c->stream));
                 MB_TRY(enqueue_brute(c, pl, cutoff, 1, with_dist, 0, n1, n2, c->tmp4a.as<float4>(),
                                      c->refcell_a.as<unsigned long long>(), c->tmp4b.as<float4>(),
                                      c->refcell_b.as<unsigned long long>(), d_counter, d_vdw1, d_vdw2));
@@ -2065,12 +2249,12 @@ int batch_search_impl(Ctx* c, float cutoff, uint8_t pbc, size_t f0, size_t f1, i
             MB_TRY(ensure_pair_capacity(c, std::max(want, c->pair_cap), false));
         }
     install_slot(c, 0);
-    // per-frame counters: [2*f] pairs, [2*f+1] work ; checksums after them
-    MB_TRY(c->batch_tmp.reserve(nf * 4 * sizeof(unsigned long long)));
+    // per-frame counters at stride CNT_STRIDE (pairs, work, tests, -) ; checksums after them
+    MB_TRY(c->batch_tmp.reserve(nf * (CNT_STRIDE + 2) * sizeof(unsigned long long)));
     unsigned long long* d_cnt = c->batch_tmp.as<unsigned long long>();
-    unsigned long long* d_chk = d_cnt + 2 * nf;
+    unsigned long long* d_chk = d_cnt + CNT_STRIDE * nf;
     if (checksums2) MB_CUDA(cudaMemsetAsync(d_chk, 0, nf * 2 * sizeof(unsigned long long), main_stream));
-    std::vector<unsigned long long> h_cnt(2 * nf);
+    std::vector<unsigned long long> h_cnt(CNT_STRIDE * nf);
     const bool dbg = getenv("MB_DEBUG_TIMING") != nullptr;
     for (int attempt = 0; attempt < 2; ++attempt) {
         auto t_a = std::chrono::steady_clock::now();
@@ -2080,7 +2264,7 @@ int batch_search_impl(Ctx* c, float cutoff, uint8_t pbc, size_t f0, size_t f1, i
         for (size_t f = 0; f < nf; ++f) {
             install_slot(c, (int)(f % NS));
             const float* xyz = c->batch.as<float>() + (f0 + f) * n * 3;
-            int rc = enqueue_cells_search(c, xyz, nullptr, n, pl, cutoff, kmode, d_cnt + 2 * f);
+            int rc = enqueue_cells_search(c, xyz, nullptr, n, pl, cutoff, kmode, d_cnt + CNT_STRIDE * f);
             if (rc < 0) {
                 install_slot(c, 0);
                 return rc;
@@ -2092,7 +2276,7 @@ int batch_search_impl(Ctx* c, float cutoff, uint8_t pbc, size_t f0, size_t f1, i
             MB_CUDA(cudaStreamWaitEvent(main_stream, c->aux_event, 0));
         }
         auto t_b = std::chrono::steady_clock::now();
-        MB_CUDA(cudaMemcpyAsync(h_cnt.data(), d_cnt, 2 * nf * sizeof(unsigned long long), cudaMemcpyDeviceToHost, main_stream));
+        MB_CUDA(cudaMemcpyAsync(h_cnt.data(), d_cnt, CNT_STRIDE * nf * sizeof(unsigned long long), cudaMemcpyDeviceToHost, main_stream));
         MB_CUDA(cudaStreamSynchronize(main_stream));
         auto t_c = std::chrono::steady_clock::now();
         c->harvest_profile();
@@ -2102,7 +2286,7 @@ int batch_search_impl(Ctx* c, float cutoff, uint8_t pbc, size_t f0, size_t f1, i
                     std::chrono::duration<double, std::milli>(t_c - t_b).count(), nf, c->pair_cap, pl.ncells,
                     pl.g.k[0], pl.g.k[1], pl.g.k[2], pl.g.hx, pl.nrows, NS);
         unsigned long long mx = 0;
-        for (size_t f = 0; f < nf; ++f) mx = std::max(mx, h_cnt[2 * f]);
+        for (size_t f = 0; f < nf; ++f) mx = std::max(mx, h_cnt[CNT_STRIDE * f]);
         size_t min_cap = c->pair_cap;
         for (int s = 1; s < NS; ++s) min_cap = std::min(min_cap, c->alt[s - 1].pair_cap);
         if (kmode == 2 || mx <= min_cap) break;
@@ -2113,14 +2297,14 @@ int batch_search_impl(Ctx* c, float cutoff, uint8_t pbc, size_t f0, size_t f1, i
         install_slot(c, 0);
     }
     if (counts)
-        for (size_t f = 0; f < nf; ++f) counts[f] = (int64_t)h_cnt[2 * f];
+        for (size_t f = 0; f < nf; ++f) counts[f] = (int64_t)h_cnt[CNT_STRIDE * f];
     if (checksums2 && kmode != 2) {
         // verification path (not the timed one): redo frame by frame on the context stream so the
         // checksum kernel knows the pair count
         for (size_t f = 0; f < nf; ++f) {
             const float* xyz = c->batch.as<float>() + (f0 + f) * n * 3;
-            MB_TRY(enqueue_cells_search(c, xyz, nullptr, n, pl, cutoff, kmode, d_cnt + 2 * f));
-            unsigned long long cnt = h_cnt[2 * f];
+            MB_TRY(enqueue_cells_search(c, xyz, nullptr, n, pl, cutoff, kmode, d_cnt + CNT_STRIDE * f));
+            unsigned long long cnt = h_cnt[CNT_STRIDE * f];
             int blocks = (int)std::min<unsigned long long>((cnt + 255) / 256 + 1, (unsigned long long)c->sm_count * 16);
             checksum_kernel<<<blocks, 256, 0, c->stream>>>(c->pairs.as<uint2>(), cnt, 1, d_chk + 2 * f);
             c->launches++;
@@ -2137,7 +2321,12 @@ int batch_search_impl(Ctx* c, float cutoff, uint8_t pbc, size_t f0, size_t f1, i
         }
     }
     c->last.kind = kmode == 2 ? 4 : 1;
-    c->last.count = (int64_t)h_cnt[2 * (nf - 1)];
+    c->last.count = (int64_t)h_cnt[CNT_STRIDE * (nf - 1)];
+    if (kmode == 2) {
+        double t = 0;
+        for (size_t f = 0; f < nf; ++f) t += (double)h_cnt[CNT_STRIDE * f + 2];
+        c->last_tests_per_frame = t / (double)nf;
+    }
     c->last.has_dist = false;
     for (int d = 0; d < 3; ++d) c->last.grid_dims[d] = pl.g.dims[d];
     return MB_OK;
@@ -2279,6 +2468,39 @@ int mb_fill_pairs(MbCtx* h, uint64_t* ij, float* dist) {
         MB_CUDA(cudaMemcpyAsync(dist, c.dists.p, P * sizeof(float), cudaMemcpyDeviceToHost, c.stream));
         MB_CUDA(cudaStreamSynchronize(c.stream));
     }
+    return MB_OK;
+}
+
+__global__ void canonical_pairs_kernel(uint2* __restrict__ pairs, unsigned long long n) {
+    unsigned long long k = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    if (k < n) {
+        uint2 p = pairs[k];
+        if (p.x > p.y) pairs[k] = make_uint2(p.y, p.x);
+    }
+}
+
+// The pair list as the device holds it: u32 x 2 per pair (8 B — half the PCIe bytes of the usize form), single-set
+// pairs made canonical (i < j) in place first.  ij32 should be page-locked for the copy to run at full PCIe speed.
+int mb_fill_pairs_u32(MbCtx* h, uint32_t* ij32, float* dist) {
+    if (!h) return fail(MB_ERR_ARG, "null context");
+    Ctx& c = h->c;
+    if (c.last.kind != 1 && c.last.kind != 2) return fail(MB_ERR_STATE, "no pair list on this context");
+    MB_CUDA(cudaSetDevice(c.device));
+    const size_t P = (size_t)c.last.count;
+    if (P == 0) return MB_OK;
+    if (ij32) {
+        if (c.last.kind == 1) {
+            canonical_pairs_kernel<<<(unsigned)((P + 255) / 256), 256, 0, c.stream>>>(c.pairs.as<uint2>(), P);
+            c.launches++;
+            MB_CUDA(cudaGetLastError());
+        }
+        MB_CUDA(cudaMemcpyAsync(ij32, c.pairs.p, P * sizeof(uint2), cudaMemcpyDeviceToHost, c.stream));
+    }
+    if (dist) {
+        if (!c.last.has_dist) return fail(MB_ERR_STATE, "distances were not computed (option with_dist=0)");
+        MB_CUDA(cudaMemcpyAsync(dist, c.dists.p, P * sizeof(float), cudaMemcpyDeviceToHost, c.stream));
+    }
+    MB_CUDA(cudaStreamSynchronize(c.stream));
     return MB_OK;
 }
 

@@ -435,14 +435,29 @@ __global__ void __launch_bounds__(128) xtc_decode_kernel(const uint8_t* __restri
         }
         return;
     }
-    const unsigned ng = g_count[f];
+    // The stream is untrusted input and this kernel runs before the scan's verdict is read back, so it is safe on
+    // its own: the group table never exceeds natoms entries (one group holds at least one atom), a group whose bits
+    // would run past the end of the compressed block or whose small-integer width is invalid is skipped, and every
+    // store is clamped to the frame.  (A corrupt stream is still reported through `status` by the scan.)
+    const unsigned ng = min(g_count[f], (unsigned)natoms);
     const uint8_t* d = raw + F.data_off;
     const float inv = F.inv_precision;
+    const unsigned long long total_bits = (unsigned long long)F.nbytes * 8ull;
+    const unsigned fullbits = (unsigned)(F.bitsize ? F.bitsize : F.bitsizeint[0] + F.bitsizeint[1] + F.bitsizeint[2]);
+    auto put = [&](int at, const int v[3]) {
+        if (at >= 0 && at < natoms) {
+            o[3 * (size_t)at] = (float)v[0] * inv;
+            o[3 * (size_t)at + 1] = (float)v[1] * inv;
+            o[3 * (size_t)at + 2] = (float)v[2] * inv;
+        }
+    };
     for (unsigned g = blockIdx.x * blockDim.x + threadIdx.x; g < ng; g += gridDim.x * blockDim.x) {
         const size_t e = F.group_off + g;
         unsigned long long bp = g_bit[e];
         int i = (int)g_atom[e];
         const int smallidx = g_meta[e] & 0xff, run = g_meta[e] >> 8;
+        if (run > 0 && (smallidx < XTC_FIRSTIDX || smallidx >= XTC_LASTIDX || c_magicints[smallidx] == 0)) continue;
+        if (bp + fullbits + 1ull + (unsigned long long)(run / 3) * (unsigned)smallidx > total_bits) continue;
         int cur[3];
         if (F.bitsize == 0) {
             cur[0] = (int)xtc_bits(d, bp, F.bitsizeint[0]);
@@ -471,13 +486,9 @@ __global__ void __launch_bounds__(128) xtc_decode_kernel(const uint8_t* __restri
                 t[2] += prev[2] - smallnum;
                 if (k == 0) {
                     // the first small atom is stored BEFORE the full one (water: O H H -> H O H on disk)
-                    o[3 * (size_t)i] = (float)t[0] * inv;
-                    o[3 * (size_t)i + 1] = (float)t[1] * inv;
-                    o[3 * (size_t)i + 2] = (float)t[2] * inv;
+                    put(i, t);
                     ++i;
-                    o[3 * (size_t)i] = (float)cur[0] * inv;
-                    o[3 * (size_t)i + 1] = (float)cur[1] * inv;
-                    o[3 * (size_t)i + 2] = (float)cur[2] * inv;
+                    put(i, cur);
                     ++i;
                     // after the swap the delta chain continues from the small atom
                     prev[0] = t[0];
@@ -487,16 +498,12 @@ __global__ void __launch_bounds__(128) xtc_decode_kernel(const uint8_t* __restri
                     prev[0] = t[0];
                     prev[1] = t[1];
                     prev[2] = t[2];
-                    o[3 * (size_t)i] = (float)t[0] * inv;
-                    o[3 * (size_t)i + 1] = (float)t[1] * inv;
-                    o[3 * (size_t)i + 2] = (float)t[2] * inv;
+                    put(i, t);
                     ++i;
                 }
             }
         } else {
-            o[3 * (size_t)i] = (float)cur[0] * inv;
-            o[3 * (size_t)i + 1] = (float)cur[1] * inv;
-            o[3 * (size_t)i + 2] = (float)cur[2] * inv;
+            put(i, cur);
         }
     }
 }
@@ -584,6 +591,10 @@ static int xtc_parse(const uint8_t* b, size_t nb, std::vector<XtcHostFrame>& fra
                 sizeint[k] = (unsigned)(mx - H.dev.minint[k] + 1);
                 H.dev.sizeint[k] = sizeint[k];
             }
+            if (sizeint[0] == 0 || sizeint[1] == 0 || sizeint[2] == 0)
+                return fail(MB_ERR_ARG, "xtc: frame %zu: empty coordinate range (maxint < minint)", frames.size());
+            if (!(precision > 0.0f) || !std::isfinite(precision))
+                return fail(MB_ERR_ARG, "xtc: frame %zu: bad precision", frames.size());
             H.dev.smallidx = (int)rd_u32(b + off + 84, true);
             H.dev.nbytes = rd_u32(b + off + 88, true);
             H.size = 92 + ((size_t)H.dev.nbytes + 3) / 4 * 4;

@@ -234,3 +234,51 @@ def test_stream_entry_points_multi_chunk_500k(mb):
     assert np.allclose(b.stream_pipeline(frames, 1.2, box, masses=m), want_rows, rtol=1e-12, atol=0)
     assert np.allclose(b.stream_fit(frames, m), want_rmsd, rtol=1e-12, atol=1e-12)
     b.close()
+
+
+def test_reduce_many_small_selections_vs_oracle(mb):
+    """Thousands of per-residue selections in ONE launch (mb_reduce_many): every row equals the oracle's f64 result for
+    that selection; zero-mass and empty selections are reported per selection (MeasureError::ZeroMass)."""
+    rng = np.random.default_rng(11)
+    n = 60_000
+    xyz = orc.synth_frame(SEED + 3, 0, n, M)
+    m = orc.synth_masses(SEED + 3, n)
+    m[100:110] = 0.0  # a massless residue
+    s = mb.System(xyz, masses=m, box=M)
+    # residues of 3..40 consecutive atoms, plus a few scattered and a few large selections
+    bounds = [0]
+    while bounds[-1] < n - 50:
+        bounds.append(bounds[-1] + int(rng.integers(3, 41)))
+    sels = [np.arange(a, b, dtype=np.uint64) for a, b in zip(bounds[:-1], bounds[1:])]
+    sels += [np.sort(rng.choice(n, size=k, replace=False)).astype(np.uint64) for k in (1, 2, 33, 500, 5000)]
+    sels = [a for a in sels if not (a.min() >= 100 and a.max() < 110)]
+    assert len(sels) > 2000
+    com = s.reduce_many(sels, "com")
+    cog = s.reduce_many(sels, "cog")
+    rg = s.reduce_many(sels, "gyration")
+    both = s.reduce_many(sels, "com_gyration")
+    for k in list(range(0, len(sels), 97)) + list(range(len(sels) - 5, len(sels))):
+        ids = sels[k]
+        rc, c = orc.center_of_mass(xyz, m, ids)
+        rc2, g = orc.gyration(xyz, m, ids)
+        assert rc == 0 and np.allclose(com[k], c, rtol=RTOL, atol=1e-12)
+        assert np.allclose(cog[k], xyz[ids.astype(np.int64)].astype(np.float64).mean(0), rtol=RTOL, atol=1e-9)
+        assert abs(rg[k, 0] - g) <= RTOL * max(g, 1e-9) + 1e-7
+        assert np.array_equal(both[k, :3], com[k]) and both[k, 3] == rg[k, 0]
+    # the same through the CTA-per-selection kernel (large mean size)
+    big = [np.sort(rng.choice(n, size=3000, replace=False)).astype(np.uint64) for _ in range(6)]
+    cb = s.reduce_many(big, "com_gyration")
+    for k, ids in enumerate(big):
+        rc, c = orc.center_of_mass(xyz, m, ids)
+        rc2, g = orc.gyration(xyz, m, ids)
+        assert np.allclose(cb[k, :3], c, rtol=RTOL) and abs(cb[k, 3] - g) <= RTOL * g
+    # per-selection errors: zero mass -> MB_ERR_ZERO_MASS with that row NaN and the others intact
+    bad = [np.arange(0, 10, dtype=np.uint64), np.arange(100, 110, dtype=np.uint64), np.arange(20, 25, dtype=np.uint64)]
+    out, status = s.reduce_many(bad, "com", return_status=True)
+    assert list(status) == [0, 1, 0] and np.isnan(out[1]).all() and np.array_equal(out[0], s(bad[0]).com())
+    with pytest.raises(mb.MolarB200Error) as e:
+        s.reduce_many(bad, "com")
+    assert e.value.code == -1
+    # cog needs no masses
+    assert np.isfinite(s.reduce_many(bad, "cog")).all()
+    s.close()

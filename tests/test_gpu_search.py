@@ -219,6 +219,47 @@ def test_double_vdw_search_vs_oracle(mb, pbc):
     assert_same_pairs(gp, gd, op[order], od[order])
 
 
+@pytest.mark.parametrize("pbc", [0, 7])
+def test_double_vdw_search_cell_path_100k_vs_oracle(mb, pbc):
+    """vdW contact search at 10^5 x 10^5 atoms: the cell kernel with a per-pair cutoff (grid cutoff = max + max + eps,
+    distance_search.rs:781-783,845-847) against the oracle, and its time against the plain two-set search at the same
+    grid cutoff (must be within 2x: it was an all-pairs scan before)."""
+    import time
+    M = (TRIC * np.float32(0.47)).astype(np.float32)  # ~103k atoms at water density
+    n = 200_000
+    xyz = orc.synth_frame(SEED + 41, 0, n, M, stray_permille=5)
+    rng = np.random.default_rng(9)
+    vdw = (0.10 + 0.11 * rng.random(n)).astype(np.float32)
+    ids1 = np.arange(0, n, 2, dtype=np.uint64)
+    ids2 = np.arange(1, n, 2, dtype=np.uint64)
+    box = orc.Box(matrix=M)
+    ij, d, dims = orc.search_double_vdw(xyz, ids1, vdw[ids1.astype(int)], xyz, ids2, vdw[ids2.astype(int)],
+                                        box if pbc else None, pbc, 8)
+    op, od = orc.ordered_pairs(ij, d)
+    op = np.stack([ids1[op[:, 0].astype(int)], ids2[op[:, 1].astype(int)]], 1)
+    order = np.lexsort((op[:, 1], op[:, 0]))
+    s = mb.System(xyz, box=M, vdw=vdw)
+    pairs, dist = mb.distance_search("vdw", s(ids1), s(ids2), dims=[bool(pbc)] * 3)
+    gp, gd = orc.ordered_pairs(pairs, dist)
+    assert len(gp) == len(pairs) and len(gp) > 10000
+    assert_same_pairs(gp, gd, op[order], od[order])
+    # timing: vdW vs plain two-set search with the grid cutoff of the vdW search
+    grid_cut = float(vdw[ids1.astype(int)].max() + vdw[ids2.astype(int)].max() + np.finfo(np.float32).eps)
+    s.set_option("with_dist", 0)
+
+    def timed(fn):
+        fn()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            fn()
+        return (time.perf_counter() - t0) / 3
+
+    t_vdw = timed(lambda: mb.distance_search("vdw", s(ids1), s(ids2), dims=[bool(pbc)] * 3))
+    t_plain = timed(lambda: mb.distance_search(grid_cut, s(ids1), s(ids2), dims=[bool(pbc)] * 3))
+    s.close()
+    assert t_vdw < 2.0 * t_plain + 2e-3, (t_vdw, t_plain)
+
+
 CASES = ["within_0.5_resid10", "within_0.3_resid20", "within_0.5_resid555", "within_0.5_pbc_resid555"]
 
 
@@ -248,6 +289,16 @@ def test_empty_and_error_paths(mb):
     assert pairs.shape == (0, 2) and dist.shape == (0,)
     with pytest.raises(IndexError):
         s([1000])
+    # the C ABI is the boundary a Rust binding calls directly: unsorted / repeated / out-of-range ids are rejected
+    # there (MB_ERR_ARG) instead of reaching a kernel
+    from molar_b200 import _capi
+    for bad in ([5, 3, 9], [1, 1, 2], [0, 50, 100], [2 ** 40, 2 ** 40 + 1]):
+        ids = np.asarray(bad, np.uint64)
+        rc = s._lib.mb_search_single(s._h, 1.0, ids.ctypes.data_as(_capi.u64p), len(ids), 0)
+        assert rc == _capi.MB_ERR_ARG, (bad, rc)
+        out = (np.zeros(3))
+        rc = s._lib.mb_center_of_geometry(s._h, ids.ctypes.data_as(_capi.u64p), len(ids), out.ctypes.data_as(_capi.f64p))
+        assert rc == _capi.MB_ERR_ARG, (bad, rc)
     s.close()
 
 
@@ -414,50 +465,4 @@ def test_stream_search_host_frames(mb):
     counts2 = traj.stream_search(frames, 1.2, box, count_only=True)
     assert np.array_equal(counts, counts2)
     traj.close()
-    s.close()
-
-
-@pytest.mark.parametrize("case", ["ortho", "tric", "exact_small_z", "two_sets"])
-def test_lane_kernel_option_parity(mb, case):
-    """search_lanes_kernel (option lane_kernel=1, one home atom per lane): same pair sets and distances as the oracle
-    on the direct, wrapped (filtered and exact) and two-set paths."""
-    if case == "ortho":
-        M = np.diag([6.0, 7.0, 8.0]).astype(np.float32)
-    elif case == "tric":
-        M = (TRIC * np.float32(0.3)).astype(np.float32)
-    else:
-        L = 6.0
-        M = np.array([[L, 0, L / 2], [0, L, L / 2], [0, 0, L / np.sqrt(2)]], np.float32)
-    xyz = orc.synth_frame(SEED + 31, 0, 26000, M, stray_permille=10)
-    if case == "two_sets":
-        from molar_b200.api import within
-        b = orc.Box(matrix=M)
-        ids1 = np.arange(0, 26000, 2, dtype=np.uint64)
-        ids2 = np.arange(1, 26000, 3, dtype=np.uint64)
-        ij, d, _ = orc.search_double(1.0, xyz, ids1, xyz, ids2, b, 7, 8)
-        op, od = orc.ordered_pairs(ij, d)
-        s = mb.System(xyz, box=M)
-        s.set_option("lane_kernel", 1)
-        s.set_option("two_set_cells_min", 0)
-        pairs, dist = mb.distance_search(1.0, s(ids1), s(ids2), dims=[True] * 3)
-        gp, gd = orc.ordered_pairs(pairs, dist)
-        assert len(gp) == len(pairs)
-        assert_same_pairs(gp, gd, op, od)
-        inner = np.arange(100, 400, dtype=np.uint64)
-        ref_ids = orc.search_within(0.7, xyz, None, xyz, inner, box=b, pbc=7, nthreads=4)
-        assert np.array_equal(within(0.7, s(), s(inner), dims=7), np.unique(ref_ids))
-        s.close()
-        return
-    op, od, dims = oracle_single(1.2, xyz, box=M, pbc=7)
-    gp, gd = run_single(mb, xyz, 1.2, box=M, dims=[True] * 3, lane_kernel=1)
-    assert_same_pairs(gp, gd, op, od)
-    # pairs-only mode and the count-only mode of the same kernel
-    s = mb.System(xyz, box=M)
-    s.set_option("lane_kernel", 1)
-    s.set_option("with_dist", 0)
-    cnt = mb._capi.check(s._lib.mb_search_single(s._h, 1.2, None, len(xyz), 7))
-    pairs = np.empty((cnt, 2), np.uint64)
-    mb._capi.check(s._lib.mb_fill_pairs(s._h, pairs.ctypes.data, None))
-    assert np.array_equal(orc.canonical_pairs(pairs), op)
-    assert mb._capi.check(s._lib.mb_count_single(s._h, 1.2, None, len(xyz), 7)) == len(op)
     s.close()

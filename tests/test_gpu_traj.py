@@ -147,3 +147,46 @@ def test_errors(mb):
     bad[-4:] = b"\x01\x02\x03\x04"
     with pytest.raises(mb.MolarB200Error):
         mb.load_trajectory(bytes(bad), "dcd")
+
+
+def test_xtc_corrupt_streams_are_rejected_not_decoded_out_of_bounds(mb, golden_dir):
+    """Trajectory files are untrusted input.  A truncated compressed block, flipped bits in the block, a run code that
+    overruns the atom count or an invalid small-integer index must end in MolarB200Error (or decode to SOMETHING of the
+    right shape) — never in a crash or an out-of-frame write; the context stays usable afterwards."""
+    g = np.load(f"{golden_dir}/protein_xtc_trr.npz")
+    good = bytearray(g["xtc_bytes"].tobytes())
+    nf, na = mb.probe_trajectory(bytes(good), "xtc")
+    frame_len = len(good) // nf
+    rng = np.random.default_rng(5)
+    outcomes = {"error": 0, "decoded": 0}
+    cases = []
+    for trial in range(24):
+        b = bytearray(good)
+        kind = trial % 4
+        if kind == 0:      # flip bits inside the compressed block of the LAST frame (no slack behind the batch)
+            for _ in range(1 + trial):
+                pos = (nf - 1) * frame_len + 92 + int(rng.integers(0, frame_len - 100))
+                b[pos] ^= 1 << int(rng.integers(0, 8))
+        elif kind == 1:    # small-integer index out of range
+            b[(nf - 1) * frame_len + 84: (nf - 1) * frame_len + 88] = int(rng.integers(0, 200)).to_bytes(4, "big")
+        elif kind == 2:    # all-ones block: every flag set, maximal run codes
+            s = (nf - 1) * frame_len + 92
+            b[s: s + 4000] = b"\xff" * 4000
+        else:              # declared block length larger than what is there (truncated file)
+            b = b[: (nf - 1) * frame_len + 92 + int(rng.integers(10, frame_len - 200))]
+        cases.append(bytes(b))
+    for b in cases:
+        try:
+            n_ok = mb.probe_trajectory(b, "xtc")[0]
+            traj = mb.load_trajectory(b, "xtc")
+            xyz = traj.frames()
+            assert xyz.shape == (n_ok, na, 3)
+            traj.close()
+            outcomes["decoded"] += 1
+        except mb.MolarB200Error:
+            outcomes["error"] += 1
+    assert outcomes["error"] > 0
+    # the library is still healthy: the intact file decodes bit-exactly afterwards
+    traj = mb.load_trajectory(bytes(good), "xtc")
+    assert np.array_equal(traj.frames(), g["trr_xyz"])
+    traj.close()

@@ -27,13 +27,12 @@ t = mb.Trajectory(); t.synth(1, 0, 4, 8000, M, mass_seed=1)
 c = t.search(1.2); c2 = t.search(1.2, count_only=True); rows = t.pipeline(1.2); rr = t.fit(0)
 t.set_option("fused_fit", 1); rr2 = t.fit(0)
 print("ok", len(p), len(p2), len(w), len(p3), len(p4), c.tolist(), c2.tolist(), float(r))
-# ---- round 2 additions: lane kernel, periodic reductions, inertia, trajectory ingest, pair-list consumers ----
+# ---- round 2 additions: periodic reductions, inertia, trajectory ingest, pair-list consumers ----
 from oracle import traj_oracle as T
 s2 = mb.System(xyz, masses=m, box=M)
-s2.set_option("lane_kernel", 1)
-pl, dl = mb.distance_search(1.2, s2(), dims=[True] * 3)                   # lane kernel, pairs + dist
+pl, dl = mb.distance_search(1.2, s2(), dims=[True] * 3)                   # pairs + dist
 s2.set_option("with_dist", 0)
-npl2 = mb._capi.check(s2._lib.mb_search_single(s2._h, 1.2, None, n, 7))    # lane kernel, pairs only
+npl2 = mb._capi.check(s2._lib.mb_search_single(s2._h, 1.2, None, n, 7))    # pairs only
 pl2 = np.empty((npl2, 2), np.uint64); mb._capi.check(s2._lib.mb_fill_pairs(s2._h, pl2.ctypes.data, None))
 rp, cols = s2.connectivity()                                               # CSR adjacency
 cp = s2().com(dims=[True] * 3); cg = s2().cog(dims=[True, False, True]); gp = s2().gyration(pbc=True)
