@@ -29,21 +29,22 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
+def build(force=False, verbose=False, defines=(), out=None):
+    """defines / out: tuning builds of the same sources into another file (MOLAR_B200_PLUGIN selects it at run time)."""
+    if out is None and not force and not needs_build():
         return LIB
     os.makedirs(LIBDIR, exist_ok=True)
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    cmd = [nvcc] + NVCC_FLAGS + ["-D" + d for d in defines] + ["-o", out or LIB] + [os.path.join(CSRC, s) for s in SOURCES]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
-    log = os.path.join(LIBDIR, "build.log")
+    log = os.path.join(LIBDIR, "build.log" if out is None else os.path.basename(out) + ".log")
     with open(log, "w") as f:
         f.write(" ".join(cmd) + "\n" + r.stdout)
     if verbose or r.returncode != 0:
         sys.stderr.write(r.stdout)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed (see %s)" % log)
-    return LIB
+    return out or LIB
 
 
 if __name__ == "__main__":

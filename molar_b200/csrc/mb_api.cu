@@ -1,5 +1,6 @@
 // mb_api.cu — context, error plumbing, frame/mass residency (host side of the C ABI).
 #include <cmath>
+#include <algorithm>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -108,6 +109,19 @@ DevBox to_dev_box(const HostBox& b) {
     d.ncorr = b.ncorr;
     for (int i = 0; i < 26; ++i)
         for (int k = 0; k < 3; ++k) d.corr[3 * i + k] = i < b.ncorr ? b.corr[i][k] : 0.0f;
+    // Pruning data for the triclinic correction loop (mb_common.cuh, corrections_best): correction s can only give a
+    // shorter vector than `start` if 2 start.s + |s|^2 < 0.  corr_thr[i] = -0.4995 |s_i|^2: start.s above it means the
+    // real improvement is negative by more than 1e-3 |s|^2 — a thousand times the f32 rounding of the reference's
+    // own comparison — so the correction is skipped without evaluating it.  rin2 = (0.499 min |s|)^2: inside that
+    // sphere no correction at all can win.
+    double smin2 = 1e300;
+    for (int i = 0; i < 26; ++i) {
+        double s2 = 0;
+        for (int k = 0; k < 3; ++k) s2 += (double)d.corr[3 * i + k] * (double)d.corr[3 * i + k];
+        d.corr_thr[i] = i < b.ncorr ? (float)(-0.4995 * s2) : 0.0f;
+        if (i < b.ncorr) smin2 = std::min(smin2, s2);
+    }
+    d.rin2 = b.ncorr > 0 ? (float)(0.499 * 0.499 * smin2) : 0.0f;
     return d;
 }
 
@@ -275,6 +289,7 @@ int mb_set_option(MbCtx* h, const char* key, double value) {
     else if (!strcmp(key, "with_dist")) c.opt_with_dist = (int)value;
     else if (!strcmp(key, "exact_pbc")) c.opt_exact_pbc = (int)value;
     else if (!strcmp(key, "fused_fit")) c.opt_fused_fit = (int)value;
+    else if (!strcmp(key, "fit_lag")) c.opt_fit_lag = (int)value;
     else if (!strcmp(key, "batch_streams")) c.opt_batch_streams = (int)value;
     else if (!strcmp(key, "two_set_cells_min")) c.opt_two_set_cells_min = value;
     else if (!strcmp(key, "profile")) {

@@ -52,6 +52,8 @@ struct DevBox {
     float inv[9];  // row-major
     int ncorr;
     float corr[26 * 3];
+    float corr_thr[26];  // -0.4995 |s|^2 per correction: start.s above it => the correction cannot win (pruned)
+    float rin2;          // (0.499 min |s|)^2: |start|^2 below it => no correction can win
 };
 DevBox to_dev_box(const HostBox& b);
 
@@ -141,7 +143,8 @@ struct Ctx {
     int opt_with_dist = 1;
     double opt_two_set_cells_min = 5.0e7;  // two-set searches use the cell kernel when n1*n2 exceeds this
     int opt_batch_streams = 0;  // streams (slots) batch_search alternates frames over; 0 = automatic
-    int opt_fused_fit = 0;  // 1: batch_fit uses the persistent TMA-staged kernel (slower than the two-kernel path so far)
+    int opt_fused_fit = 0;  // batch_fit: 0 two kernels per frame group, 1/2 TMA-staged single-pass kernels, 3 persistent kernel with an L2-served lagging second pass
+    int opt_fit_lag = 0;    // fused_fit = 3: frames between pass 1 and pass 2 (0 = automatic)
     int opt_exact_pbc = 0;    // 1: wrapped cell pairs always use the exact PeriodicBox path (no filter)
     int opt_profile = 0;      // record CUDA events around every search-kernel launch
     std::vector<cudaEvent_t> prof_events;  // begin/end pairs not yet harvested
@@ -211,6 +214,8 @@ __device__ __forceinline__ float d2_pbc(const DevBox& bx, float ax, float ay, fl
     xmatvec(bx.m, f0, f1, f2, s0, s1, s2);
     float best2 = xnorm2(s0, s1, s2);
     if (bx.ncorr == 0 || w != 7u) return best2;
+    // (no pruning here: this copy is inlined into the pair kernel's rare wrapped path, where the extra live values
+    //  cost the hot loop registers; the pruned loop lives in shortest_vector_dev, used by the reductions)
     for (int c = 0; c < bx.ncorr; ++c) {
         float n2 = xnorm2(xadd(s0, bx.corr[3 * c]), xadd(s1, bx.corr[3 * c + 1]), xadd(s2, bx.corr[3 * c + 2]));
         if (n2 < best2) best2 = n2;
@@ -232,7 +237,14 @@ __device__ __forceinline__ void shortest_vector_dev(const DevBox& bx, float v0, 
     o2 = s2;
     if (bx.ncorr == 0 || w != 7u) return;
     float best2 = xnorm2(s0, s1, s2);
+    // The reference evaluates all (up to 26) triclinic corrections (periodic_box.rs:299-317).  A correction s can beat
+    // `start` only if 2 start.s + |s|^2 < 0; the two prunes below skip corrections whose real improvement is negative
+    // by a margin a thousand times the f32 rounding of the reference's comparison, so the surviving ones — evaluated
+    // with the reference's exact expression against the running best — give the reference's result.
+    if (best2 < bx.rin2) return;  // inside the inscribed sphere of the cell: no correction can win
     for (int c = 0; c < bx.ncorr; ++c) {
+        const float dot = fmaf(s0, bx.corr[3 * c], fmaf(s1, bx.corr[3 * c + 1], s2 * bx.corr[3 * c + 2]));
+        if (dot > bx.corr_thr[c]) continue;  // cannot beat `start` by a wide margin: pruned
         const float c0 = xadd(s0, bx.corr[3 * c]), c1 = xadd(s1, bx.corr[3 * c + 1]), c2 = xadd(s2, bx.corr[3 * c + 2]);
         const float n2 = xnorm2(c0, c1, c2);
         if (n2 < best2) {

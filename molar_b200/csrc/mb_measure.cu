@@ -548,6 +548,373 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) fit_fused_kernel(const Fused
     for (int f = max(0, P.nf - FUSED_DELAY); f < P.nf; ++f) pass2(f);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Single-pass Kabsch batch, second design (config 4; measure.rs:507-522,613-643 + modify.rs:32-36 + measure.rs:485-504
+// per frame): every byte of a frame crosses HBM once in each direction.
+//
+// The first fused kernel (above) is bound by its grid-wide dependency: the CTA that folds the partials and runs the
+// SVD of frame f also owns a slice, so it falls behind by the whole finish latency, frame f+1 cannot complete without
+// its partial, and the frames serialise on (finish latency + pass 1).  Here the roles are split:
+//   * WORKER CTAs (blockIdx < W) own a slice of every frame.  Slices arrive by 1-D TMA bulk copies into a ring of
+//     NBUF shared-memory buffers; pass 1 (16 f64 moments) publishes a partial and a ticket and never waits; pass 2
+//     (superpose in shared memory, sum |Rp+t-ref|^2, TMA bulk store) of frame f runs DELAY frames later, when the
+//     rotation has normally long been published.
+//   * FINISHER CTAs (blockIdx >= W) own no atoms: finisher k waits for the W tickets of frames f = k (mod NFIN), folds
+//     the partials with the whole CTA in a fixed order, runs the 3x3 Kabsch SVD and publishes (R, t) + a flag.
+// Workers therefore run at the speed of the TMA ring as long as the finish latency stays below DELAY frame times.
+constexpr int FS_NFIN = 4;
+
+template <int NBUF, int DELAY>
+__global__ void __launch_bounds__(FUSED_THREADS, 1) fit_stream_kernel(const FusedParams P, int W) {
+    static_assert(NBUF >= DELAY + 2, "one buffer must be free for the load in flight");
+    extern __shared__ __align__(128) unsigned char fsm[];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const unsigned lane = tid & 31u, wid = tid >> 5;
+    __shared__ double res[16];
+    const double o2x = P.ref[0], o2y = P.ref[1], o2z = P.ref[2];  // pivot of the reference frame: atom 0
+
+    if (b >= W) {
+        // ------------------------------ finisher ------------------------------
+        for (int f = b - W; f < P.nf; f += FS_NFIN) {
+            if (tid == 0) {
+                const volatile unsigned* tk = P.tick_fit + f;
+                while (*tk < (unsigned)W) { }
+                __threadfence();
+            }
+            __syncthreads();
+            // fold: output k by warp (k % 8), partials strided over the lanes, shuffle tree — a fixed order
+            const double* part = P.part_fit + (size_t)f * W * 16;
+            for (int k = (int)wid; k < 16; k += FUSED_THREADS / 32) {
+                double xsum = 0;
+                for (int bb = (int)lane; bb < W; bb += 32) xsum += __ldcg(&part[(size_t)bb * 16 + k]);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) xsum += __shfl_xor_sync(0xffffffffu, xsum, o);
+                if (lane == 0) res[k] = xsum;
+            }
+            __syncthreads();
+            if (tid == 0) {
+                const float* fr0 = P.frames + (size_t)f * P.n * 3;
+                const double o1[3] = {__ldcg(fr0), __ldcg(fr0 + 1), __ldcg(fr0 + 2)};
+                const double o2[3] = {o2x, o2y, o2z};
+                fit_finalize<false>(res, o1, o2, 0, P.fitres + (size_t)f * 16);
+                P.tick_fit[f] = 0;  // re-arm for the next launch
+                __threadfence();
+                atomicExch(P.flag + f, 1u);
+            }
+            __syncthreads();
+        }
+        return;
+    }
+
+    // ------------------------------ worker ------------------------------
+    const int slice = P.slice;
+    float* buf[NBUF];
+#pragma unroll
+    for (int i = 0; i < NBUF; ++i) buf[i] = reinterpret_cast<float*>(fsm) + (size_t)i * slice * 3;
+    float* sref = reinterpret_cast<float*>(fsm) + (size_t)NBUF * slice * 3;
+    __shared__ __align__(8) unsigned long long bar[NBUF];
+    __shared__ double sRt[12];
+    __shared__ double r2[1];
+    const int a0 = b * slice;
+    const int cnt = max(0, min(slice, P.n - a0));  // atoms of this CTA's slice
+    const unsigned bytes = (unsigned)cnt * 12u;
+    if (tid == 0) {
+        for (int i = 0; i < NBUF; ++i) mbar_init(&bar[i], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = tid; i < cnt * 3; i += FUSED_THREADS) sref[i] = P.ref[(size_t)a0 * 3 + i];  // resident for the kernel
+    __syncthreads();
+    const float* __restrict__ mass = P.masses + a0;  // 4 B/atom per frame from L2
+    auto prefetch = [&](int f) {
+        if (tid == 0 && cnt > 0 && f < P.nf) {
+            unsigned long long* br = &bar[f % NBUF];
+            mbar_expect_tx(br, bytes);
+            bulk_load(buf[f % NBUF], P.frames + ((size_t)f * P.n + a0) * 3, bytes, br);
+        }
+    };
+    for (int f = 0; f < NBUF - DELAY; ++f) prefetch(f);
+
+    auto pass2 = [&](int f) {
+        if (tid == 0) {
+            const volatile unsigned* fl = P.flag + f;
+            while (*fl == 0u) { }
+            __threadfence();
+        }
+        __syncthreads();
+        if (tid < 12) sRt[tid] = __ldcg(&P.fitres[(size_t)f * 16 + tid]);
+        __syncthreads();
+        double R[9], t[3];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) R[i] = sRt[i];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) t[i] = sRt[9 + i];
+        float* x = buf[f % NBUF];
+        double v[1] = {0.0};
+        for (int i = tid; i < cnt; i += FUSED_THREADS) {
+            const double px0 = x[3 * i], py0 = x[3 * i + 1], pz0 = x[3 * i + 2];
+            const double px = R[0] * px0 + R[1] * py0 + R[2] * pz0 + t[0];
+            const double py = R[3] * px0 + R[4] * py0 + R[5] * pz0 + t[1];
+            const double pz = R[6] * px0 + R[7] * py0 + R[8] * pz0 + t[2];
+            const double dx = px - (double)sref[3 * i], dy = py - (double)sref[3 * i + 1], dz = pz - (double)sref[3 * i + 2];
+            v[0] += dx * dx + dy * dy + dz * dz;
+            if (P.superpose) {
+                x[3 * i] = (float)px;
+                x[3 * i + 1] = (float)py;
+                x[3 * i + 2] = (float)pz;
+            }
+        }
+        if (P.superpose) fence_async_smem();  // generic-proxy writes -> visible to the bulk store
+        block_sum<1>(v, r2);                  // (contains the __syncthreads the store needs)
+        if (tid == 0) {
+            P.part_sup[(size_t)f * W + b] = r2[0];  // folded in block order by finish_rmsd_kernel
+            if (P.superpose && cnt > 0) {
+                bulk_store(P.frames + ((size_t)f * P.n + a0) * 3, x, bytes);
+                bulk_store_wait_read();  // the buffer may be refilled only after the store has read it
+            }
+        }
+        fence_async_smem();
+        __syncthreads();
+    };
+
+    for (int f = 0; f < P.nf; ++f) {
+        float* x = buf[f % NBUF];
+        if (cnt > 0) mbar_wait(&bar[f % NBUF], (unsigned)((f / NBUF) & 1));
+        const float* fr0 = P.frames + (size_t)f * P.n * 3;
+        // the frame's pivot (its atom 0) must be read BEFORE any worker superposes the frame in place: every CTA
+        // reads it here, and pass 2 of frame f starts only after all W tickets of frame f are in
+        const double o1x = __ldcg(fr0), o1y = __ldcg(fr0 + 1), o1z = __ldcg(fr0 + 2);
+        double v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = 0.0;
+        for (int i = tid; i < cnt; i += FUSED_THREADS) {
+            const double m = __ldg(mass + i);
+            const double q1x = (double)x[3 * i] - o1x, q1y = (double)x[3 * i + 1] - o1y, q1z = (double)x[3 * i + 2] - o1z;
+            const double q2x = (double)sref[3 * i] - o2x, q2y = (double)sref[3 * i + 1] - o2y, q2z = (double)sref[3 * i + 2] - o2z;
+            v[0] += m;
+            v[1] += m * q1x; v[2] += m * q1y; v[3] += m * q1z;
+            const double wx = m * q2x, wy = m * q2y, wz = m * q2z;
+            v[4] += wx; v[5] += wy; v[6] += wz;
+            v[7] += wx * q1x;  v[8] += wx * q1y;  v[9] += wx * q1z;
+            v[10] += wy * q1x; v[11] += wy * q1y; v[12] += wy * q1z;
+            v[13] += wz * q1x; v[14] += wz * q1y; v[15] += wz * q1z;
+        }
+        block_sum<16>(v, res);
+        if (tid < 16) P.part_fit[((size_t)f * W + b) * 16 + tid] = res[tid];
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) atomicAdd(P.tick_fit + f, 1u);  // never waits: the finisher CTAs do
+        if (f >= DELAY) pass2(f - DELAY);
+        prefetch(f + NBUF - DELAY);  // into the buffer released just now (or still unused)
+    }
+    for (int f = max(0, P.nf - DELAY); f < P.nf; ++f) pass2(f);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Single-pass Kabsch batch, third design (fused_fit = 3): ONE persistent kernel, second pass served by L2.
+//
+// Every CTA owns the same slice of every frame and alternates between pass 1 of frame f (16 f64 moments -> partial +
+// ticket; the CTA that takes the last ticket folds the partials and runs the SVD) and pass 2 of frame f - LAG
+// (superpose + sum |Rp+t-ref|^2).  LAG frames is long enough (tens of microseconds) for (R, t) of that frame to have
+// been published, so nobody ever waits, and short enough for the frame to be still resident in the 126 MB L2: HBM
+// sees each frame once in each direction (12 B/atom read by pass 1, 12 B/atom written by pass 2), the re-read is an
+// L2 hit.  No shared-memory staging, so any atom count works and several CTAs per SM hide the f64 latency.
+struct LagParams {
+    float* frames;        // [nf][n][3], superposed in place
+    const float* ref;     // [n][3]
+    const float* masses;  // [n]
+    int n, nf, superpose, lag;
+    int per;              // atoms per CTA slice (multiple of 4)
+    double* part_fit;     // [nf][grid][16]
+    double* part_sup;     // [nf][grid]
+    unsigned* tick_fit;   // [nf]
+    unsigned* flag;       // [nf]
+    double* fitres;       // [nf][16]
+};
+
+constexpr int LAG_THREADS = 256;
+
+// Warp total of 16 doubles per lane by a butterfly that halves the values kept per lane at every step (32 shuffles
+// instead of 160): afterwards lane l holds the warp total of value (l >> 1).  Fixed order => deterministic.
+__device__ __forceinline__ double warp_sum16(const double (&v)[16], unsigned lane) {
+    double a[8], b4[4], c2[2];
+    const bool h16 = lane & 16u, h8 = lane & 8u, h4 = lane & 4u, h2 = lane & 2u;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const double mine = h16 ? v[8 + k] : v[k], other = h16 ? v[k] : v[8 + k];
+        a[k] = mine + __shfl_xor_sync(0xffffffffu, other, 16);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const double mine = h8 ? a[4 + k] : a[k], other = h8 ? a[k] : a[4 + k];
+        b4[k] = mine + __shfl_xor_sync(0xffffffffu, other, 8);
+    }
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const double mine = h4 ? b4[2 + k] : b4[k], other = h4 ? b4[k] : b4[2 + k];
+        c2[k] = mine + __shfl_xor_sync(0xffffffffu, other, 4);
+    }
+    const double mine = h2 ? c2[1] : c2[0], other = h2 ? c2[0] : c2[1];
+    double d = mine + __shfl_xor_sync(0xffffffffu, other, 2);
+    d += __shfl_xor_sync(0xffffffffu, d, 1);
+    return d;
+}
+
+__global__ void __launch_bounds__(LAG_THREADS, 2) fit_lag_kernel(const LagParams P) {
+    __shared__ double wsum[LAG_THREADS / 32][16];
+    __shared__ double res[16];
+    __shared__ double sRt[12];
+    __shared__ unsigned s_last;
+    const int b = blockIdx.x, G = gridDim.x, tid = threadIdx.x;
+    const unsigned lane = tid & 31u, wid = tid >> 5;
+    const int a0 = min(P.n, b * P.per), a1 = min(P.n, a0 + P.per);
+    const bool vec = (P.n & 3) == 0 && ((reinterpret_cast<uintptr_t>(P.frames) | reinterpret_cast<uintptr_t>(P.ref) |
+                                         reinterpret_cast<uintptr_t>(P.masses)) & 15u) == 0;
+    const double o2x = P.ref[0], o2y = P.ref[1], o2z = P.ref[2];  // pivot of the reference frame: atom 0
+
+    for (int f = 0; f < P.nf + P.lag; ++f) {
+        if (f < P.nf) {
+            // ---------------- pass 1 of frame f ----------------
+            const float* fr = P.frames + (size_t)f * P.n * 3;
+            const double o1x = __ldcg(fr), o1y = __ldcg(fr + 1), o1z = __ldcg(fr + 2);
+            double v[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = 0.0;
+            auto acc = [&](float x1, float y1, float z1, float x2, float y2, float z2, float mf) {
+                const double m = mf;
+                const double q1x = (double)x1 - o1x, q1y = (double)y1 - o1y, q1z = (double)z1 - o1z;
+                const double q2x = (double)x2 - o2x, q2y = (double)y2 - o2y, q2z = (double)z2 - o2z;
+                v[0] += m;
+                v[1] += m * q1x; v[2] += m * q1y; v[3] += m * q1z;
+                const double wx = m * q2x, wy = m * q2y, wz = m * q2z;
+                v[4] += wx; v[5] += wy; v[6] += wz;
+                v[7] += wx * q1x;  v[8] += wx * q1y;  v[9] += wx * q1z;
+                v[10] += wy * q1x; v[11] += wy * q1y; v[12] += wy * q1z;
+                v[13] += wz * q1x; v[14] += wz * q1y; v[15] += wz * q1z;
+            };
+            if (vec) {
+                for (int a = a0 + 4 * tid; a < a1; a += 4 * LAG_THREADS) {
+                    float x1[4], y1[4], z1[4], x2[4], y2[4], z2[4];
+                    load4(fr, a, x1, y1, z1);
+                    load4(P.ref, a, x2, y2, z2);
+                    const float4 m4 = __ldg(reinterpret_cast<const float4*>(P.masses + a));
+                    acc(x1[0], y1[0], z1[0], x2[0], y2[0], z2[0], m4.x);
+                    acc(x1[1], y1[1], z1[1], x2[1], y2[1], z2[1], m4.y);
+                    acc(x1[2], y1[2], z1[2], x2[2], y2[2], z2[2], m4.z);
+                    acc(x1[3], y1[3], z1[3], x2[3], y2[3], z2[3], m4.w);
+                }
+            } else {
+                for (int a = a0 + tid; a < a1; a += LAG_THREADS)
+                    acc(fr[3 * (size_t)a], fr[3 * (size_t)a + 1], fr[3 * (size_t)a + 2], P.ref[3 * (size_t)a],
+                        P.ref[3 * (size_t)a + 1], P.ref[3 * (size_t)a + 2], P.masses[a]);
+            }
+            const double w = warp_sum16(v, lane);
+            if ((lane & 1u) == 0u) wsum[wid][lane >> 1] = w;
+            __syncthreads();
+            if (tid < 16) {
+                double x = 0.0;
+#pragma unroll
+                for (int k = 0; k < LAG_THREADS / 32; ++k) x += wsum[k][tid];
+                P.part_fit[((size_t)f * G + b) * 16 + tid] = x;
+            }
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) s_last = (atomicAdd(P.tick_fit + f, 1u) == (unsigned)(G - 1)) ? 1u : 0u;
+            __syncthreads();
+            if (s_last) {
+                // last ticket of the frame: fold the G partials in block order and finish the fit
+                __threadfence();
+                const double* part = P.part_fit + (size_t)f * G * 16;
+                for (int k = (int)wid; k < 16; k += LAG_THREADS / 32) {
+                    double xsum = 0;
+                    for (int bb = (int)lane; bb < G; bb += 32) xsum += __ldcg(&part[(size_t)bb * 16 + k]);
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) xsum += __shfl_xor_sync(0xffffffffu, xsum, o);
+                    if (lane == 0) res[k] = xsum;
+                }
+                __syncthreads();
+                if (tid == 0) {
+                    const double o1[3] = {o1x, o1y, o1z}, o2[3] = {o2x, o2y, o2z};
+                    fit_finalize<false>(res, o1, o2, 0, P.fitres + (size_t)f * 16);
+                    P.tick_fit[f] = 0;  // re-arm for the next launch
+                    __threadfence();
+                    atomicExch(P.flag + f, 1u);
+                }
+            }
+        }
+        const int g = f - P.lag;
+        if (g >= 0) {
+            // ---------------- pass 2 of frame g: (R, t) was published LAG frames ago ----------------
+            if (tid == 0) {
+                const volatile unsigned* fl = P.flag + g;
+                while (*fl == 0u) { }
+                __threadfence();
+            }
+            __syncthreads();
+            if (tid < 12) sRt[tid] = __ldcg(&P.fitres[(size_t)g * 16 + tid]);
+            __syncthreads();
+            double R[9], t[3];
+#pragma unroll
+            for (int i = 0; i < 9; ++i) R[i] = sRt[i];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) t[i] = sRt[9 + i];
+            float* fr = P.frames + (size_t)g * P.n * 3;
+            double r2 = 0.0;
+            auto sup = [&](float x0, float y0, float z0, float rx, float ry, float rz, float& ox, float& oy, float& oz) {
+                const double px0 = x0, py0 = y0, pz0 = z0;
+                const double px = R[0] * px0 + R[1] * py0 + R[2] * pz0 + t[0];
+                const double py = R[3] * px0 + R[4] * py0 + R[5] * pz0 + t[1];
+                const double pz = R[6] * px0 + R[7] * py0 + R[8] * pz0 + t[2];
+                const double dx = px - (double)rx, dy = py - (double)ry, dz = pz - (double)rz;
+                r2 += dx * dx + dy * dy + dz * dz;
+                ox = (float)px;
+                oy = (float)py;
+                oz = (float)pz;
+            };
+            if (vec) {
+                for (int a = a0 + 4 * tid; a < a1; a += 4 * LAG_THREADS) {
+                    float x1[4], y1[4], z1[4], x2[4], y2[4], z2[4], ox[4], oy[4], oz[4];
+                    const float4* p = reinterpret_cast<const float4*>(fr + 3 * (size_t)a);
+                    const float4 u = __ldcg(p), vv = __ldcg(p + 1), ww = __ldcg(p + 2);  // L2 hit (read LAG frames ago)
+                    x1[0] = u.x; y1[0] = u.y; z1[0] = u.z; x1[1] = u.w; y1[1] = vv.x; z1[1] = vv.y;
+                    x1[2] = vv.z; y1[2] = vv.w; z1[2] = ww.x; x1[3] = ww.y; y1[3] = ww.z; z1[3] = ww.w;
+                    load4(P.ref, a, x2, y2, z2);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) sup(x1[k], y1[k], z1[k], x2[k], y2[k], z2[k], ox[k], oy[k], oz[k]);
+                    if (P.superpose) {
+                        float4* q = reinterpret_cast<float4*>(fr + 3 * (size_t)a);
+                        __stcs(q, make_float4(ox[0], oy[0], oz[0], ox[1]));
+                        __stcs(q + 1, make_float4(oy[1], oz[1], ox[2], oy[2]));
+                        __stcs(q + 2, make_float4(oz[2], ox[3], oy[3], oz[3]));
+                    }
+                }
+            } else {
+                for (int a = a0 + tid; a < a1; a += LAG_THREADS) {
+                    float ox, oy, oz;
+                    sup(__ldcg(fr + 3 * (size_t)a), __ldcg(fr + 3 * (size_t)a + 1), __ldcg(fr + 3 * (size_t)a + 2),
+                        P.ref[3 * (size_t)a], P.ref[3 * (size_t)a + 1], P.ref[3 * (size_t)a + 2], ox, oy, oz);
+                    if (P.superpose) {
+                        fr[3 * (size_t)a] = ox;
+                        fr[3 * (size_t)a + 1] = oy;
+                        fr[3 * (size_t)a + 2] = oz;
+                    }
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) r2 += __shfl_xor_sync(0xffffffffu, r2, o);
+            __syncthreads();  // wsum is free again (pass 1 of this iteration has consumed it)
+            if (lane == 0) wsum[wid][0] = r2;
+            __syncthreads();
+            if (tid == 0) {
+                double x = 0.0;
+#pragma unroll
+                for (int k = 0; k < LAG_THREADS / 32; ++k) x += wsum[k][0];
+                P.part_sup[(size_t)g * G + b] = x;  // folded in block order by finish_rmsd_kernel
+            }
+            __syncthreads();
+        }
+    }
+}
+
 // rmsd[f] = sqrt(sum_b part[f][b] / n), partials folded in block order (deterministic)
 __global__ void __launch_bounds__(32) finish_rmsd_kernel(const double* __restrict__ part, int nblk, int n,
                                                          double* __restrict__ rmsd) {
@@ -645,12 +1012,116 @@ int batch_fit_impl(Ctx* c, size_t ref_frame, size_t f0, size_t f1, int superpose
                                 cudaMemcpyDeviceToDevice, c->stream));
     }
     const float* ref = c->batch_ref.as<float>();
-    // ---- fused persistent path (TMA-staged slices; 12 B/atom read + 12 B/atom written per frame) ----
+    // ---- single-pass path, third design (fused_fit = 3): one persistent kernel, pass 2 lags by LAG frames and reads L2
+    if (c->opt_fused_fit == 3) {
+        int occ = 0;
+        MB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fit_lag_kernel, LAG_THREADS, 0));
+        occ = std::max(1, std::min(occ, 2));
+        // grid: all resident CTAs, but never more CTAs than slices of 4 * LAG_THREADS atoms (one vector round)
+        const size_t tile = 4 * (size_t)LAG_THREADS;
+        int grid = (int)std::min<size_t>((size_t)c->sm_count * occ, std::max<size_t>(1, (n + tile - 1) / tile));
+        // slices of whole tiles, as even as the tile count allows
+        const size_t ntile = (n + tile - 1) / tile;
+        const size_t tiles_per = (ntile + grid - 1) / grid;
+        grid = (int)((ntile + tiles_per - 1) / tiles_per);
+        const int per = (int)(tiles_per * tile);
+        // LAG: long enough for the finish of a frame (fold + SVD, ~10 us) to be over, short enough for the frames
+        // in flight (read + written) to stay inside L2
+        const size_t fb = n * 12;
+        int lag = (int)std::max<size_t>(2, std::min<size_t>(64, ((size_t)40 << 20) / std::max<size_t>(fb, 1)));
+        if (c->opt_fit_lag > 0) lag = c->opt_fit_lag;
+        const size_t chunk = std::min<size_t>(nf, 4096);
+        RedScratch s{};
+        MB_TRY(red_scratch(c, 2 * chunk, chunk * (size_t)grid * 17, nf * 17, &s));
+        double* fitres = s.results;
+        double* d_rmsd = s.results + nf * 16;
+        for (size_t g0 = 0; g0 < nf; g0 += chunk) {
+            const size_t gn = std::min(chunk, nf - g0);
+            LagParams P;
+            P.frames = c->batch.as<float>() + (f0 + g0) * n * 3;
+            P.ref = ref;
+            P.masses = c->masses.as<float>();
+            P.n = (int)n;
+            P.nf = (int)gn;
+            P.superpose = superpose;
+            P.lag = (int)std::min<size_t>((size_t)lag, gn);
+            P.per = per;
+            P.part_fit = s.partials;
+            P.part_sup = s.partials + chunk * (size_t)grid * 16;
+            P.tick_fit = s.tickets;
+            P.flag = s.tickets + chunk;
+            P.fitres = fitres + g0 * 16;
+            MB_CUDA(cudaMemsetAsync(P.flag, 0, gn * sizeof(unsigned), c->stream));
+            void* args[] = {&P};
+            MB_CUDA(cudaLaunchCooperativeKernel((const void*)fit_lag_kernel, dim3(grid), dim3(LAG_THREADS), args, 0,
+                                                c->stream));
+            finish_rmsd_kernel<<<(unsigned)gn, 32, 0, c->stream>>>(P.part_sup, grid, (int)n, d_rmsd + g0);
+            c->launches += 2;
+        }
+        MB_CUDA(cudaGetLastError());
+        if (rmsd_out)
+            MB_CUDA(cudaMemcpyAsync(rmsd_out, d_rmsd, nf * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        MB_CUDA(cudaStreamSynchronize(c->stream));
+        return MB_OK;
+    }
+    // ---- single-pass path, second design (fused_fit = 2): worker CTAs stream slices through a TMA ring, dedicated
+    //      finisher CTAs fold + SVD; 12 B/atom read + 12 B/atom written per frame ----
+    if (c->opt_fused_fit == 2 && (n % 4) == 0 && !(reinterpret_cast<uintptr_t>(c->batch.p) & 15u) &&
+        c->sm_count > 2 * FS_NFIN) {
+        constexpr int NBUF = 4, DELAY = 2;
+        const int grid = c->sm_count, W = grid - FS_NFIN;
+        const int slice = (int)(((n + W - 1) / W + 3) / 4 * 4);
+        const size_t smem = (size_t)slice * (NBUF + 1) * 12;
+        int occ = 0;
+        if (smem <= (size_t)225 * 1024) {
+            auto kern = fit_stream_kernel<NBUF, DELAY>;
+            MB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            MB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, FUSED_THREADS, smem));
+        }
+        if (occ >= 1) {
+            const size_t chunk = std::min<size_t>(nf, 1024);
+            RedScratch s{};
+            MB_TRY(red_scratch(c, 3 * chunk, chunk * (size_t)W * 17, nf * 17, &s));
+            double* fitres = s.results;
+            double* d_rmsd = s.results + nf * 16;
+            for (size_t g0 = 0; g0 < nf; g0 += chunk) {
+                const size_t gn = std::min(chunk, nf - g0);
+                FusedParams P;
+                P.frames = c->batch.as<float>() + (f0 + g0) * n * 3;
+                P.ref = ref;
+                P.masses = c->masses.as<float>();
+                P.n = (int)n;
+                P.nf = (int)gn;
+                P.slice = slice;
+                P.superpose = superpose;
+                P.part_fit = s.partials;
+                P.part_sup = s.partials + chunk * (size_t)W * 16;
+                P.tick_fit = s.tickets;
+                P.tick_sup = s.tickets + chunk;
+                P.flag = s.tickets + 2 * chunk;
+                P.fitres = fitres + g0 * 16;
+                P.rmsd = d_rmsd + g0;
+                MB_CUDA(cudaMemsetAsync(P.flag, 0, gn * sizeof(unsigned), c->stream));
+                int Wv = W;
+                void* args[] = {&P, &Wv};
+                MB_CUDA(cudaLaunchCooperativeKernel((const void*)fit_stream_kernel<NBUF, DELAY>, dim3(grid),
+                                                    dim3(FUSED_THREADS), args, smem, c->stream));
+                finish_rmsd_kernel<<<(unsigned)gn, 32, 0, c->stream>>>(P.part_sup, W, (int)n, P.rmsd);
+                c->launches += 2;
+            }
+            MB_CUDA(cudaGetLastError());
+            if (rmsd_out)
+                MB_CUDA(cudaMemcpyAsync(rmsd_out, d_rmsd, nf * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+            MB_CUDA(cudaStreamSynchronize(c->stream));
+            return MB_OK;
+        }
+    }
+    // ---- fused persistent path, first design (fused_fit = 1) ----
     {
         int occ = 0;
         const int sm = c->sm_count;
         // try 2 CTAs/SM first, then 1
-        for (int want = 2; want >= 1 && c->opt_fused_fit; --want) {
+        for (int want = 2; want >= 1 && c->opt_fused_fit == 1; --want) {
             int grid = sm * want;
             int slice = (int)(((n + grid - 1) / grid + 3) / 4 * 4);
             size_t smem = (size_t)slice * (FUSED_NBUF + 1) * 12 + (size_t)slice * 4;

@@ -35,7 +35,16 @@ constexpr unsigned DROPPED = 0xFFFFFFFFu;
 constexpr int MAX_REACH = 7;
 constexpr int MAX_ROWS = (2 * MAX_REACH + 1) * (2 * MAX_REACH + 1);
 constexpr int STAGE_CAP = 512;  // pairs staged per warp before a flush (>= 16 lanes * 32 home atoms)
-constexpr int SEARCH_WARPS = 8;
+#ifndef MB_SEARCH_WARPS
+#define MB_SEARCH_WARPS 8
+#endif
+#ifndef MB_SEARCH_MIN_CTAS
+#define MB_SEARCH_MIN_CTAS 4
+#endif
+#ifndef MB_SEARCH_PIPELINE
+#define MB_SEARCH_PIPELINE 0
+#endif
+constexpr int SEARCH_WARPS = MB_SEARCH_WARPS;  // warps per CTA; MB_SEARCH_MIN_CTAS CTAs per SM bound the registers (tuning builds only)
 constexpr int CNT_STRIDE = 4;  // u64 words per search: [0] pairs, [1] tile work counter, [2] distance tests, [3] spare
 constexpr int PAD_CANDS = 64;  // finite far-away records behind each sorted array (read by idle lanes of the candidate stream)
 
@@ -363,7 +372,7 @@ template <int MODE>
 __device__ __forceinline__ void warp_flush(unsigned stage_sa, unsigned staged_sa, unsigned home_sa, int& stage_n,
                                            const SearchParams& P, unsigned lane) {
     constexpr bool DIST = MODE == 1;
-    static_assert(STAGE_CAP == 512, "the flush is written out for 16 chunks");
+    static_assert(STAGE_CAP % 128 == 0 && STAGE_CAP >= 512, "flush rounds of 128 entries; the 4-pass expansion needs 512");
     __syncwarp();
     if (stage_n == 0) return;
     const int n = stage_n;
@@ -773,7 +782,7 @@ __device__ __forceinline__ unsigned stage_hits4(unsigned e, unsigned id, unsigne
 // same iteration.
 // VDW: the cutoff of a pair is (vdw1[i] + vdw2[j]) + EPSILON instead of one number for all (two-set searches only).
 template <int MODE, bool VDW = false>
-__global__ void __launch_bounds__(SEARCH_WARPS * 32, 4) search_cells_kernel(const __grid_constant__ SearchParams P) {
+__global__ void __launch_bounds__(SEARCH_WARPS * 32, MB_SEARCH_MIN_CTAS) search_cells_kernel(const __grid_constant__ SearchParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const unsigned lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
     WarpShared& ws = reinterpret_cast<WarpShared*>(smem_raw)[wid];
@@ -823,7 +832,6 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32, 4) search_cells_kernel(cons
             unsigned nr, T;
             fill_run_table<MAX_RUNS>(P, ws.rec, fx, fy, fz, cx, cy, cz, hs, he, first, lane, row0, nr, T, ws.rbits);
             const bool use_bits = T < 32u * RUN_BITMAP_WORDS;  // every run start AND the sentinel are in the bitmap
-            const unsigned selfT = (first && !P.two_sets) ? he - hs : 0u;  // stream positions of the self run
 
             // ---------------- Phase B: consume the stream ----------------
 #pragma unroll 1
@@ -840,27 +848,42 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32, 4) search_cells_kernel(cons
                 unsigned cur0 = 0, cur1 = 0;
                 unsigned runs_before = 0;  // run starts at stream positions < c0 (bitmap path)
                 unsigned hit_any = 0;      // MODE 3: bit j = home atom j has a set-2 atom within the cutoff
+                // Candidates of stream positions [c, c + 64): run index of a position = (run starts at positions <= it)
+                // - 1: two broadcast words and a popcount instead of a per-lane search.  Positions >= T fall into the
+                // sentinel run, whose records are the far-away padding behind the sorted array: no bounds checks.
+                auto fetch = [&](unsigned c, float4& q0, float4& q1, unsigned& g0, unsigned& g1, unsigned& b0i, unsigned& b1i) {
+                    const uint2 bw = lds64(rbits_sa + (c >> 5) * 4u);
+                    const unsigned pw0 = __popc(bw.x);
+                    const unsigned k0 = runs_before + __popc(bw.x & le_mask) - 1u;
+                    const unsigned k1 = runs_before + pw0 + __popc(bw.y & le_mask) - 1u;
+                    runs_before += pw0 + __popc(bw.y);
+                    const uint2 r0 = lds64(rec_sa + k0 * 8u), r1 = lds64(rec_sa + k1 * 8u);
+                    b0i = r0.x + c + lane;
+                    b1i = r1.x + c + lane + 32u;
+                    q0 = __ldg(&P.sortedB[b0i]);
+                    q1 = __ldg(&P.sortedB[b1i]);
+                    g0 = r0.y;
+                    g1 = r1.y;
+                };
+#if MB_SEARCH_PIPELINE
+                // software pipeline: the loads of step s + 1 are issued before the tests of step s (needs the registers
+                // of a 3-CTA/SM build)
+                float4 n0n = make_float4(0.f, 0.f, 0.f, 0.f), n1n = n0n;
+                unsigned f0n = 0, f1n = 0, a0n = 0, a1n = 0;
+                if (use_bits && T > 0) fetch(0u, n0n, n1n, f0n, f1n, a0n, a1n);
+#endif
 #pragma unroll 1
                 for (unsigned c0 = 0; c0 < T; c0 += 64) {
                     const unsigned p0 = c0 + lane, p1 = p0 + 32;
                     float4 n0, n1;
                     unsigned f0, f1, a0i, a1i;
                     if (use_bits) {
-                        // run index of a stream position = (run starts at positions <= it) - 1: two broadcast words
-                        // and a popcount instead of a per-lane search.  Positions >= T fall into the sentinel run,
-                        // whose records are the far-away padding behind the sorted array: no bounds checks.
-                        const uint2 bw = lds64(rbits_sa + (c0 >> 5) * 4u);
-                        const unsigned pw0 = __popc(bw.x);
-                        cur0 = runs_before + __popc(bw.x & le_mask) - 1u;
-                        cur1 = runs_before + pw0 + __popc(bw.y & le_mask) - 1u;
-                        runs_before += pw0 + __popc(bw.y);
-                        const uint2 r0 = lds64(rec_sa + cur0 * 8u), r1 = lds64(rec_sa + cur1 * 8u);
-                        a0i = r0.x + p0;
-                        a1i = r1.x + p1;
-                        n0 = __ldg(&P.sortedB[a0i]);
-                        n1 = __ldg(&P.sortedB[a1i]);
-                        f0 = r0.y;
-                        f1 = r1.y;
+#if MB_SEARCH_PIPELINE
+                        n0 = n0n; n1 = n1n; f0 = f0n; f1 = f1n; a0i = a0n; a1i = a1n;
+                        if (c0 + 64 < T) fetch(c0 + 64, n0n, n1n, f0n, f1n, a0n, a1n);
+#else
+                        fetch(c0, n0, n1, f0, f1, a0i, a1i);
+#endif
                     } else {
                         // very long streams (dense systems): per-lane forward search over the run positions
                         n0 = make_float4(pad_cand, pad_cand, pad_cand, 0.f);
@@ -888,7 +911,17 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32, 4) search_cells_kernel(cons
                         vc0 = __ldg(&P.vdwB[__float_as_uint(n0.w)]);
                         vc1 = __ldg(&P.vdwB[__float_as_uint(n1.w)]);
                     }
-                    const bool any_wrapped = __any_sync(0xffffffffu, ((f0 | f1) & 7u) != 0u);
+                    // one warp-wide OR of the flags decides the path of the step: wrapped candidates (bits 0-2) need
+                    // the periodic distance, self-run candidates (RUN_SELF) the index-order filter
+                    const unsigned step_flags = __reduce_or_sync(0xffffffffu, (f0 | f1) & (7u | RUN_SELF));
+                    const bool any_wrapped = (step_flags & 7u) != 0u;
+                    // the next 64 stream positions usually continue the same runs: start pulling those lines into L1
+#if !MB_SEARCH_PIPELINE
+                    if (use_bits) {
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(P.sortedB + a0i + 64));
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(P.sortedB + a1i + 64));
+                    }
+#endif
                     if (VDW && any_wrapped) {
                         // vdW search, step with wrapped cell pairs: every test with the reference's own expression
                         // (direct difference or PeriodicBox::distance_squared) against the pair's own cutoff
@@ -942,7 +975,7 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32, 4) search_cells_kernel(cons
                         m0 = ~a0 & valid_slots;
                         m1 = ~a1 & valid_slots;
                         // home cell against itself (first stream positions): keep (home j, atom a) only for a > hb + j
-                        if (c0 < selfT) {
+                        if (step_flags & RUN_SELF) {
                             if (f0 & RUN_SELF) {
                                 const int lim = min(max((int)a0i - (int)hb, 0), 32);
                                 m0 &= lim >= 32 ? 0xffffffffu : ((1u << lim) - 1u);

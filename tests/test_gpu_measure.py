@@ -144,17 +144,19 @@ def test_batch_fit_config4_shape(mb):
     t.close()
 
 
-@pytest.mark.parametrize("n,nf", [(100_000, 9), (99_999, 4), (2048, 5)])
+@pytest.mark.parametrize("n,nf", [(100_000, 9), (99_999, 4), (2048, 5), (500_000, 13)])
 def test_batch_fit_fused_vs_two_kernel_path(mb, n, nf):
-    """The persistent TMA-staged kernel and the generic two-kernel path must agree with the oracle
-    (n % 4 != 0 takes the generic path by construction)."""
+    """The single-pass kernels (fused_fit=1: TMA ring, finisher role rotates over the slice CTAs; 2: TMA ring, worker CTAs
+    + dedicated finisher CTAs; 3: one persistent kernel whose second pass lags behind and is served by L2) and the
+    generic two-kernel path must agree with the oracle and with each other (n % 4 != 0: modes 1 and 2 fall back to the
+    generic path, mode 3 takes its scalar loop)."""
     m = orc.synth_masses(SEED, n)
     ref = orc.synth_frame(SEED, 0, n, TRIC)
     out = {}
-    for no_fused in (0, 1):
+    for mode in (0, 1, 2, 3):
         t = mb.Trajectory()
         t.synth(SEED, 0, nf, n, TRIC, mass_seed=SEED)
-        t.set_option("fused_fit", 1 - no_fused)
+        t.set_option("fused_fit", mode)
         before = t.frame(nf - 1)
         r = t.fit(ref_frame=0, superpose=True)
         rc, R, tt = orc.fit_transform(before, m, None, ref, m, None)
@@ -162,16 +164,20 @@ def test_batch_fit_fused_vs_two_kernel_path(mb, n, nf):
         exp_r = np.sqrt(((exp - ref) ** 2).sum(1).mean())
         assert abs(r[nf - 1] - exp_r) <= RTOL * exp_r + 1e-9
         assert np.allclose(t.frame(nf - 1), exp, rtol=RTOL, atol=2e-6)
-        out[no_fused] = (r, t.frame(1))
+        out[mode] = (r, t.frame(1))
         # fit only (no superposition) leaves the frames untouched
         t2 = mb.Trajectory()
         t2.synth(SEED, 0, 2, n, TRIC, mass_seed=SEED)
-        t2.set_option("fused_fit", 1 - no_fused)
+        t2.set_option("fused_fit", mode)
         r2 = t2.fit(ref_frame=0, superpose=False)
         assert np.array_equal(t2.frame(1), orc.synth_frame(SEED, 1, n, TRIC)) and abs(r2[1] - r[1]) <= 1e-9 * r[1]
+        # a second pass over the (now superposed) batch: RMSD unchanged up to f32 rounding of the stored frames
+        r3 = t.fit(ref_frame=0, superpose=True)
+        assert np.allclose(r3[1:], r[1:], rtol=1e-4)
         t.close()
         t2.close()
-    assert np.allclose(out[0][0], out[1][0], rtol=1e-10) and np.allclose(out[0][1], out[1][1], atol=1e-6)
+    for mode in (1, 2, 3):
+        assert np.allclose(out[0][0], out[mode][0], rtol=1e-10) and np.allclose(out[0][1], out[mode][1], atol=1e-6)
 
 
 def test_batch_pipeline_config5_shape(mb):

