@@ -731,7 +731,19 @@ struct LagParams {
     double* fitres;       // [nf][16]
 };
 
-constexpr int LAG_THREADS = 256;
+constexpr int LAG_THREADS = 256;            // streaming threads of a CTA
+constexpr int LAG_BLOCK = LAG_THREADS + 32;  // + one solver warp (fold + 3x3 SVD of the frames this CTA is responsible for)
+
+// barrier of the streaming warps only (the solver warp never joins it)
+__device__ __forceinline__ void bar_stream() { asm volatile("bar.sync 1, %0;" ::"n"(LAG_THREADS) : "memory"); }
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 
 // Warp total of 16 doubles per lane by a butterfly that halves the values kept per lane at every step (32 shuffles
 // instead of 160): afterwards lane l holds the warp total of value (l >> 1).  Fixed order => deterministic.
@@ -759,17 +771,50 @@ __device__ __forceinline__ double warp_sum16(const double (&v)[16], unsigned lan
     return d;
 }
 
-__global__ void __launch_bounds__(LAG_THREADS, 2) fit_lag_kernel(const LagParams P) {
+// One persistent kernel for the whole batch.  Every CTA owns one slice of atoms of EVERY frame: its 256 streaming
+// threads run pass 1 (moments) of frame f and pass 2 (superposition + RMSD sum) of frame f - lag in the same iteration,
+// so pass 2 re-reads its slice from L2 and a frame costs 12 B/atom of DRAM reads + 12 B/atom of writes.  The fold of
+// the per-CTA moments and the 3x3 SVD of frame f belong to the SOLVER WARP of CTA f mod G — a ninth warp that never
+// joins the streaming barriers.  (When the last CTA to arrive did the solve, the ~10 us of serial f64 Jacobi made that
+// CTA the last one of the next frame as well: every solve landed on the same CTA, one after the other, 19 us per frame.)
+__global__ void __launch_bounds__(LAG_BLOCK, 2) fit_lag_kernel(const LagParams P) {
     __shared__ double wsum[LAG_THREADS / 32][16];
-    __shared__ double res[16];
     __shared__ double sRt[12];
-    __shared__ unsigned s_last;
     const int b = blockIdx.x, G = gridDim.x, tid = threadIdx.x;
     const unsigned lane = tid & 31u, wid = tid >> 5;
+    const double o2x = P.ref[0], o2y = P.ref[1], o2z = P.ref[2];  // pivot of the reference frame: atom 0
+    if (wid == LAG_THREADS / 32) {
+        // ---------------- solver warp: frames b, b + G, ... ----------------
+        for (int f = b; f < P.nf; f += G) {
+            if (lane == 0)
+                while (ld_acquire_u32(P.tick_fit + f) != (unsigned)G) __nanosleep(200);
+            __syncwarp();
+            const double* part = P.part_fit + (size_t)f * G * 16;
+            double res[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                double xsum = 0;
+                for (int bb = (int)lane; bb < G; bb += 32) xsum += __ldcg(&part[(size_t)bb * 16 + k]);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) xsum += __shfl_xor_sync(0xffffffffu, xsum, o);
+                res[k] = xsum;
+            }
+            if (lane == 0) {
+                const float* fr = P.frames + (size_t)f * P.n * 3;
+                const double o1[3] = {(double)__ldcg(fr), (double)__ldcg(fr + 1), (double)__ldcg(fr + 2)};
+                const double o2[3] = {o2x, o2y, o2z};
+                fit_finalize<false>(res, o1, o2, 0, P.fitres + (size_t)f * 16);
+                P.tick_fit[f] = 0;  // re-arm for the next launch
+                __threadfence();
+                st_release_u32(P.flag + f, 1u);
+            }
+            __syncwarp();
+        }
+        return;
+    }
     const int a0 = min(P.n, b * P.per), a1 = min(P.n, a0 + P.per);
     const bool vec = (P.n & 3) == 0 && ((reinterpret_cast<uintptr_t>(P.frames) | reinterpret_cast<uintptr_t>(P.ref) |
                                          reinterpret_cast<uintptr_t>(P.masses)) & 15u) == 0;
-    const double o2x = P.ref[0], o2y = P.ref[1], o2z = P.ref[2];  // pivot of the reference frame: atom 0
 
     for (int f = 0; f < P.nf + P.lag; ++f) {
         if (f < P.nf) {
@@ -809,49 +854,25 @@ __global__ void __launch_bounds__(LAG_THREADS, 2) fit_lag_kernel(const LagParams
             }
             const double w = warp_sum16(v, lane);
             if ((lane & 1u) == 0u) wsum[wid][lane >> 1] = w;
-            __syncthreads();
+            bar_stream();
             if (tid < 16) {
                 double x = 0.0;
 #pragma unroll
                 for (int k = 0; k < LAG_THREADS / 32; ++k) x += wsum[k][tid];
                 P.part_fit[((size_t)f * G + b) * 16 + tid] = x;
-            }
-            __threadfence();
-            __syncthreads();
-            if (tid == 0) s_last = (atomicAdd(P.tick_fit + f, 1u) == (unsigned)(G - 1)) ? 1u : 0u;
-            __syncthreads();
-            if (s_last) {
-                // last ticket of the frame: fold the G partials in block order and finish the fit
                 __threadfence();
-                const double* part = P.part_fit + (size_t)f * G * 16;
-                for (int k = (int)wid; k < 16; k += LAG_THREADS / 32) {
-                    double xsum = 0;
-                    for (int bb = (int)lane; bb < G; bb += 32) xsum += __ldcg(&part[(size_t)bb * 16 + k]);
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) xsum += __shfl_xor_sync(0xffffffffu, xsum, o);
-                    if (lane == 0) res[k] = xsum;
-                }
-                __syncthreads();
-                if (tid == 0) {
-                    const double o1[3] = {o1x, o1y, o1z}, o2[3] = {o2x, o2y, o2z};
-                    fit_finalize<false>(res, o1, o2, 0, P.fitres + (size_t)f * 16);
-                    P.tick_fit[f] = 0;  // re-arm for the next launch
-                    __threadfence();
-                    atomicExch(P.flag + f, 1u);
-                }
             }
+            bar_stream();
+            if (tid == 0) atomicAdd(P.tick_fit + f, 1u);  // the G-th ticket releases the frame to its solver warp
         }
         const int g = f - P.lag;
         if (g >= 0) {
             // ---------------- pass 2 of frame g: (R, t) was published LAG frames ago ----------------
-            if (tid == 0) {
-                const volatile unsigned* fl = P.flag + g;
-                while (*fl == 0u) { }
-                __threadfence();
-            }
-            __syncthreads();
+            if (tid == 0)
+                while (ld_acquire_u32(P.flag + g) == 0u) __nanosleep(100);
+            bar_stream();
             if (tid < 12) sRt[tid] = __ldcg(&P.fitres[(size_t)g * 16 + tid]);
-            __syncthreads();
+            bar_stream();
             double R[9], t[3];
 #pragma unroll
             for (int i = 0; i < 9; ++i) R[i] = sRt[i];
@@ -901,16 +922,16 @@ __global__ void __launch_bounds__(LAG_THREADS, 2) fit_lag_kernel(const LagParams
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) r2 += __shfl_xor_sync(0xffffffffu, r2, o);
-            __syncthreads();  // wsum is free again (pass 1 of this iteration has consumed it)
+            bar_stream();  // wsum is free again (pass 1 of this iteration has consumed it)
             if (lane == 0) wsum[wid][0] = r2;
-            __syncthreads();
+            bar_stream();
             if (tid == 0) {
                 double x = 0.0;
 #pragma unroll
                 for (int k = 0; k < LAG_THREADS / 32; ++k) x += wsum[k][0];
                 P.part_sup[(size_t)g * G + b] = x;  // folded in block order by finish_rmsd_kernel
             }
-            __syncthreads();
+            bar_stream();
         }
     }
 }
@@ -1015,7 +1036,7 @@ int batch_fit_impl(Ctx* c, size_t ref_frame, size_t f0, size_t f1, int superpose
     // ---- single-pass path, third design (fused_fit = 3): one persistent kernel, pass 2 lags by LAG frames and reads L2
     if (c->opt_fused_fit == 3) {
         int occ = 0;
-        MB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fit_lag_kernel, LAG_THREADS, 0));
+        MB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fit_lag_kernel, LAG_BLOCK, 0));
         occ = std::max(1, std::min(occ, 2));
         // grid: all resident CTAs, but never more CTAs than slices of 4 * LAG_THREADS atoms (one vector round)
         const size_t tile = 4 * (size_t)LAG_THREADS;
@@ -1053,7 +1074,7 @@ int batch_fit_impl(Ctx* c, size_t ref_frame, size_t f0, size_t f1, int superpose
             P.fitres = fitres + g0 * 16;
             MB_CUDA(cudaMemsetAsync(P.flag, 0, gn * sizeof(unsigned), c->stream));
             void* args[] = {&P};
-            MB_CUDA(cudaLaunchCooperativeKernel((const void*)fit_lag_kernel, dim3(grid), dim3(LAG_THREADS), args, 0,
+            MB_CUDA(cudaLaunchCooperativeKernel((const void*)fit_lag_kernel, dim3(grid), dim3(LAG_BLOCK), args, 0,
                                                 c->stream));
             finish_rmsd_kernel<<<(unsigned)gn, 32, 0, c->stream>>>(P.part_sup, grid, (int)n, d_rmsd + g0);
             c->launches += 2;

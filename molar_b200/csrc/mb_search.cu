@@ -35,6 +35,7 @@ constexpr unsigned DROPPED = 0xFFFFFFFFu;
 constexpr int MAX_REACH = 7;
 constexpr int MAX_ROWS = (2 * MAX_REACH + 1) * (2 * MAX_REACH + 1);
 constexpr int STAGE_CAP = 512;  // pairs staged per warp before a flush (>= 16 lanes * 32 home atoms)
+constexpr int STAGE_ROOM = STAGE_CAP + 2;  // entries allocated per warp: a carried-over odd pair + a full pass of STAGE_CAP (keeps 16-byte alignment)
 #ifndef MB_SEARCH_WARPS
 #define MB_SEARCH_WARPS 8
 #endif
@@ -46,6 +47,7 @@ constexpr int STAGE_CAP = 512;  // pairs staged per warp before a flush (>= 16 l
 #endif
 constexpr int SEARCH_WARPS = MB_SEARCH_WARPS;  // warps per CTA; MB_SEARCH_MIN_CTAS CTAs per SM bound the registers (tuning builds only)
 constexpr int CNT_STRIDE = 4;  // u64 words per search: [0] pairs, [1] tile work counter, [2] distance tests, [3] spare
+constexpr int PAIR_TAIL = 8192;  // spare pair slots behind pair_cap: the odd last pair of each warp (bulk flushes move even counts)
 constexpr int PAD_CANDS = 64;  // finite far-away records behind each sorted array (read by idle lanes of the candidate stream)
 
 struct GridSpec {
@@ -342,29 +344,20 @@ __device__ __forceinline__ float lds32f(unsigned addr) {
 }
 
 // stage_sa / staged_sa: shared-window addresses of this warp's pair / distance staging buffers.
-// A staged entry is (j, candidate id) with j the slot of the home atom in ws.home: the home id is looked
-// up here, 32 pairs per instruction, instead of once per pair in the expansion loop — so the buffer must
-// be flushed before the home batch changes.  Fully unrolled, predicated on the entry count.
-// One 32-entry chunk of a MODE 0 flush, straight-line predicated code (a branch per chunk costs three more
-// instructions than the work it skips).  Entries hold the candidate's remaining hit bits — the home slot is the
-// lowest one (brev + bfind.shiftamt = count of trailing zeros) — and the candidate id; the home id is looked up in the
-// warp's home batch, 32 entries per instruction.
+// MODE 0: staged entries are final (home id, candidate id) pairs, so a flush is a plain copy (one LDS.64 + one STG.64
+// per 32 pairs, straight-line predicated chunks) and the buffer survives home batches and tiles.
+// MODE 1: a staged entry is (j, candidate id) with j the slot of the home atom in ws.home: the home id is looked up
+// here, 32 pairs per instruction — so the buffer must be flushed before the home batch changes.
 template <int Q>
-__device__ __forceinline__ void flush_chunk_bits(int r, unsigned sa, unsigned home_sa, uint2* d) {
+__device__ __forceinline__ void flush_chunk_copy(int r, unsigned sa, uint2* d) {
     asm volatile(
-        "{ .reg .pred p; .reg .b32 e, id, j;\n"
+        "{ .reg .pred p; .reg .b32 a, b;\n"
         "  setp.gt.s32 p, %0, %1;\n"
-        "  mov.b32 e, 1;\n"
-        "  @p ld.shared.v2.u32 {e, id}, [%2+%3];\n"
-        "  brev.b32 j, e;\n"
-        "  bfind.shiftamt.u32 j, j;\n"
-        "  shl.b32 j, j, 4;\n"
-        "  add.u32 j, j, %4;\n"
-        "  @p ld.shared.u32 e, [j+12];\n"
-        "  @p st.global.v2.u32 [%5+%3], {e, id};\n"
+        "  @p ld.shared.v2.u32 {a, b}, [%2+%3];\n"
+        "  @p st.global.v2.u32 [%4+%3], {a, b};\n"
         "}"
         :
-        : "r"(r), "n"(Q * 32), "r"(sa), "n"(Q * 256), "r"(home_sa), "l"(d)
+        : "r"(r), "n"(Q * 32), "r"(sa), "n"(Q * 256), "l"(d)
         : "memory");
 }
 
@@ -388,10 +381,10 @@ __device__ __forceinline__ void warp_flush(unsigned stage_sa, unsigned staged_sa
             asm volatile("" : "+r"(sa), "+r"(r));
 #pragma unroll 1
             for (int q = 0; q < n; q += 128) {
-                flush_chunk_bits<0>(r, sa, home_sa, d);
-                flush_chunk_bits<1>(r, sa, home_sa, d);
-                flush_chunk_bits<2>(r, sa, home_sa, d);
-                flush_chunk_bits<3>(r, sa, home_sa, d);
+                flush_chunk_copy<0>(r, sa, d);
+                flush_chunk_copy<1>(r, sa, d);
+                flush_chunk_copy<2>(r, sa, d);
+                flush_chunk_copy<3>(r, sa, d);
                 r -= 128;
                 sa += 1024u;
                 d += 128;
@@ -421,6 +414,49 @@ __device__ __forceinline__ void warp_flush(unsigned stage_sa, unsigned staged_sa
     }
     __syncwarp();
     stage_n = 0;
+}
+
+// MODE 0 flush through the async proxy: the staged pairs are final, so the whole buffer leaves with ONE bulk copy
+// (cp.async.bulk shared -> global, SASS UBLKCP) issued by lane 0 instead of an LDS.64 + STG.64 per 32 pairs.  Bulk
+// copies move multiples of 16 bytes between 16-byte aligned addresses, so every flush moves an EVEN number of pairs
+// (the global pair counter stays even) and an odd last entry is carried over to slot 0.  The entries written by the
+// other lanes reach the async proxy through fence.proxy.async + __syncwarp; the buffer is reused after
+// wait_group.read.  Returns the number of entries left in the buffer (0 or 1).
+__device__ __forceinline__ int warp_flush_bulk(unsigned stage_sa, int n, const SearchParams& P, unsigned lane) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    const int ne = n & ~1;
+    if (lane == 0) {
+        uint2 carry = make_uint2(0u, 0u);
+        if (n & 1) carry = lds64(stage_sa + 8u * (unsigned)(n - 1));
+        if (ne) {
+            const unsigned long long base = atomicAdd(P.counter, (unsigned long long)ne);
+            if (base + (unsigned long long)ne <= P.pair_cap) {
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(P.pairs + base),
+                             "r"(stage_sa), "r"(ne * 8)
+                             : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            }
+        }
+        if (n & 1) sts64(stage_sa, carry.x, carry.y);
+    }
+    __syncwarp();
+    return n & 1;
+}
+
+// The odd pairs the warps were left with at the end of a MODE 0 search sit behind pair_cap (slots [pair_cap,
+// pair_cap + counter[3])): append them to the list and fold their number into the pair count.
+__global__ void merge_pair_tail_kernel(uint2* __restrict__ pairs, unsigned long long pair_cap,
+                                       unsigned long long* __restrict__ counter) {
+    const unsigned long long m = counter[0], t = counter[3];
+    if (m + t <= pair_cap)
+        for (unsigned long long k = threadIdx.x; k < t; k += blockDim.x) pairs[m + k] = pairs[pair_cap + k];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        counter[0] = m + t;
+        counter[3] = 0;
+    }
 }
 
 // ---- packed f32x2 helpers (sm_100: FADD2 / FMUL2 process two neighbour atoms per lane) ----------
@@ -620,8 +656,9 @@ struct __align__(16) WarpShared {
     // low byte, the run's stream position above it.  Entry nr is the sentinel behind the last run: it maps stream
     // positions >= T onto the padding records behind the sorted array.
     uint2 rec[MAX_RUNS + 1];
-    unsigned rbits[RUN_BITMAP_WORDS + 2];
-    float hvdw[32];                      // vdW search: radii of the home batch  // bit p set <=> a run starts at stream position p (p < 32 * RUN_BITMAP_WORDS)
+    unsigned rbits[RUN_BITMAP_WORDS + 2];  // bit p set <=> a run starts at stream position p (p < 32 * RUN_BITMAP_WORDS)
+    unsigned hid[32];                    // ids of the home batch, compact: the emission loop reads them as broadcast words
+    float hvdw[32];                      // vdW search: radii of the home batch
 };
 
 // Phase A of the pair kernel: lanes work on different neighbour rows of the home tile and append their runs
@@ -739,32 +776,35 @@ __device__ __forceinline__ void scan_step(int& v, int o) {
         : "r"(o));
 }
 
-// Stage up to four entries (remaining hit bits, candidate id) of one candidate at [sp], [sp+8], ... and clear those
-// hits: entry k holds the mask with its k lowest hits removed, so the home slot of an entry is its lowest set bit.
-// lop3 with a predicate result clears the lowest bit and tells whether anything is left in one instruction.
-template <int OFF>
-__device__ __forceinline__ unsigned stage_hits4(unsigned e, unsigned id, unsigned sp) {
+// Emission of one group of four home slots (bits 0-3 of the masks): the candidates of this lane that hit them are staged
+// as final (home id, candidate id) pairs at the lane's running position.  Per (home, candidate half): LOP3 (bit -> value
+// and predicate), one predicated STS.64 and the position bump as (bit << (3 - J)) + position — no predicated add, no bit
+// search — plus the MOV that puts the home id next to the candidate id.  (Two STS.32 instead of MOV + STS.64 issue
+// fewer instructions but run into the shared-memory store rate: 1.41 ms against 1.29 ms, mio_throttle 1.6.)
+#define MB_EMIT_ONE(J, E, ID, H)                                                     \
+    "  and.b32 t, " E ", " #J ";\n  setp.ne.u32 p, t, 0;\n"                          \
+    "  @p st.shared.v2.u32 [%0], {" H ", " ID "};\n"
+__device__ __forceinline__ void emit_group(unsigned e0, unsigned e1, unsigned id0, unsigned id1, unsigned& sp, uint4 h) {
     asm volatile(
-        "{ .reg .pred p, q; .reg .b32 t;\n"
-        "  setp.ne.u32 p, %0, 0;\n"
-        "  setp.eq.u32 q, 0, 0;\n"
-        "  @p st.shared.v2.u32 [%1+%3], {%0, %2};\n"
-        "  add.u32 t, %0, -1;\n"
-        "  lop3.and.b32 %0|p, %0, t, 0, 0xc0, q;\n"
-        "  @p st.shared.v2.u32 [%1+%4], {%0, %2};\n"
-        "  add.u32 t, %0, -1;\n"
-        "  lop3.and.b32 %0|p, %0, t, 0, 0xc0, q;\n"
-        "  @p st.shared.v2.u32 [%1+%5], {%0, %2};\n"
-        "  add.u32 t, %0, -1;\n"
-        "  lop3.and.b32 %0|p, %0, t, 0, 0xc0, q;\n"
-        "  @p st.shared.v2.u32 [%1+%6], {%0, %2};\n"
-        "  add.u32 t, %0, -1;\n"
-        "  and.b32 %0, %0, t;\n"
+        "{ .reg .pred p; .reg .b32 t;\n"
+        MB_EMIT_ONE(1, "%1", "%3", "%5") "  shl.b32 t, t, 3;\n  add.u32 %0, %0, t;\n"
+        MB_EMIT_ONE(1, "%2", "%4", "%5") "  shl.b32 t, t, 3;\n  add.u32 %0, %0, t;\n"
+        MB_EMIT_ONE(2, "%1", "%3", "%6") "  shl.b32 t, t, 2;\n  add.u32 %0, %0, t;\n"
+        MB_EMIT_ONE(2, "%2", "%4", "%6") "  shl.b32 t, t, 2;\n  add.u32 %0, %0, t;\n"
+        MB_EMIT_ONE(4, "%1", "%3", "%7") "  shl.b32 t, t, 1;\n  add.u32 %0, %0, t;\n"
+        MB_EMIT_ONE(4, "%2", "%4", "%7") "  shl.b32 t, t, 1;\n  add.u32 %0, %0, t;\n"
+        MB_EMIT_ONE(8, "%1", "%3", "%8") "  add.u32 %0, %0, t;\n"
+        MB_EMIT_ONE(8, "%2", "%4", "%8") "  add.u32 %0, %0, t;\n"
         "}"
-        : "+r"(e)
-        : "r"(sp), "r"(id), "n"(OFF), "n"(OFF + 8), "n"(OFF + 16), "n"(OFF + 24)
+        : "+r"(sp)
+        : "r"(e0), "r"(e1), "r"(id0), "r"(id1), "r"(h.x), "r"(h.y), "r"(h.z), "r"(h.w)
         : "memory");
-    return e;
+}
+#undef MB_EMIT_ONE
+__device__ __forceinline__ uint4 lds128u(unsigned addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
 }
 
 // One warp per home tile = hx consecutive fine cells along x (dynamic work counter).
@@ -787,14 +827,14 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32, MB_SEARCH_MIN_CTAS) search_
     const unsigned lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
     WarpShared& ws = reinterpret_cast<WarpShared*>(smem_raw)[wid];
     uint2* stage = (MODE == 0 || MODE == 1)
-                       ? reinterpret_cast<uint2*>(smem_raw + SEARCH_WARPS * sizeof(WarpShared)) + wid * STAGE_CAP
+                       ? reinterpret_cast<uint2*>(smem_raw + SEARCH_WARPS * sizeof(WarpShared)) + wid * STAGE_ROOM
                        : nullptr;
     float* stage_d = MODE == 1 ? reinterpret_cast<float*>(smem_raw + SEARCH_WARPS * (sizeof(WarpShared) +
-                                                                                    STAGE_CAP * sizeof(uint2))) +
+                                                                                    STAGE_ROOM * sizeof(uint2))) +
                                      wid * STAGE_CAP
                                : nullptr;
     const float4* __restrict__ home = ws.home;
-    const unsigned home_sa = smem_addr(ws.home), rec_sa = smem_addr(ws.rec), rbits_sa = smem_addr(ws.rbits);
+    const unsigned home_sa = smem_addr(ws.home), rec_sa = smem_addr(ws.rec), rbits_sa = smem_addr(ws.rbits), hid_sa = smem_addr(ws.hid);
     const unsigned stage_sa = stage ? smem_addr(stage) : 0u, staged_sa = stage_d ? smem_addr(stage_d) : 0u;
     int stage_n = 0;
     unsigned long long count = 0;
@@ -841,6 +881,7 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32, MB_SEARCH_MIN_CTAS) search_
                 {
                     const float4 hrec = (lane < (unsigned)nh) ? __ldg(&P.sorted[hb + lane]) : make_float4(pad_home, pad_home, pad_home, 0.f);
                     ws.home[lane] = hrec;
+                    if (MODE == 0) ws.hid[lane] = __float_as_uint(hrec.w);
                     if (VDW) ws.hvdw[lane] = (lane < (unsigned)nh) ? __ldg(&P.vdwA[__float_as_uint(hrec.w)]) : 0.f;
                 }
                 __syncwarp();
@@ -1075,8 +1116,57 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32, MB_SEARCH_MIN_CTAS) search_
                     scan_step(inc, 16);
                     const int tot = __shfl_sync(0xffffffffu, inc, 31);
                     if (tot == 0) continue;
-                    // Expand the masks into the staging buffer.  Normally one pass; a step that found more pairs
-                    // than the buffer holds goes through four (one candidate per lane x one 16-lane group: <= 512).
+                    const unsigned id0 = __float_as_uint(n0.w), id1 = __float_as_uint(n1.w);
+                    if (MODE == 0) {
+                        // Stage the hits as final pairs, a lane's entries in home order.  Normally one pass over all
+                        // homes; a step that found more pairs than the buffer holds goes through passes of eight homes
+                        // (<= 8 x 64 entries), each with its own prefix sums.
+                        const bool single = tot <= STAGE_CAP;
+                        const int hstep = single ? 32 : 8;
+#pragma unroll 1
+                        for (int h0 = 0; h0 < nh; h0 += hstep) {
+                            unsigned e0 = m0, e1 = m1;
+                            int off = inc - cnt, need = tot;  // exclusive prefix of this lane, entries of this pass
+                            if (!single) {
+                                e0 = (m0 >> h0) & 0xffu;
+                                e1 = (m1 >> h0) & 0xffu;
+                                int v = __popc(e0) + __popc(e1), vi = v;
+                                scan_step(vi, 1);
+                                scan_step(vi, 2);
+                                scan_step(vi, 4);
+                                scan_step(vi, 8);
+                                scan_step(vi, 16);
+                                need = __shfl_sync(0xffffffffu, vi, 31);
+                                off = vi - v;
+                                if (need == 0) continue;
+                            }
+                            if (stage_n + need > STAGE_CAP + 1) stage_n = warp_flush_bulk(stage_sa, stage_n, P, lane);
+                            unsigned sp = stage_sa + 8u * (unsigned)(stage_n + off);
+                            unsigned ha = hid_sa + 4u * (unsigned)h0;
+                            const int hend = min(nh, h0 + hstep);
+                            // two groups per round, their ids loaded one round ahead into alternating registers (the
+                            // reads past the batch run into hvdw: harmless)
+                            uint4 hqa = lds128u(ha), hqb = lds128u(ha + 16u);
+#pragma unroll 1
+                            for (int gj = h0; gj < hend; gj += 8) {
+                                emit_group(e0, e1, id0, id1, sp, hqa);
+                                hqa = lds128u(ha + 32u);
+                                e0 >>= 4;
+                                e1 >>= 4;
+                                if (gj + 4 >= hend) break;
+                                emit_group(e0, e1, id0, id1, sp, hqb);
+                                hqb = lds128u(ha + 48u);
+                                e0 >>= 4;
+                                e1 >>= 4;
+                                ha += 32u;
+                            }
+                            stage_n += need;
+                        }
+                        continue;
+                    }
+                    // MODE 1: expand the masks into the staging buffer as (home slot, candidate id) + distance.  Normally
+                    // one pass; a step that found more pairs than the buffer holds goes through four (one candidate per
+                    // lane x one 16-lane group: <= 512).
                     const int npass = tot <= STAGE_CAP ? 1 : 4;
 #pragma unroll 1
                     for (int pass = 0; pass < npass; ++pass) {
@@ -1098,30 +1188,7 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32, MB_SEARCH_MIN_CTAS) search_
                         if (stage_n + need > STAGE_CAP) warp_flush<MODE>(stage_sa, staged_sa, home_sa, stage_n, P, lane);
                         unsigned sp0 = stage_sa + 8u * (unsigned)(stage_n + off);
                         unsigned sp1 = sp0 + 8u * (unsigned)__popc(e0);
-                        const unsigned id0 = __float_as_uint(n0.w), id1 = __float_as_uint(n1.w);
-                        if (MODE == 0) {
-                            // both candidates of the lane advance together, four entries each per round; the
-                            // number of rounds is warp-uniform (largest hit count of any candidate)
-                            const int kmax = __reduce_max_sync(0xffffffffu, max(__popc(e0), __popc(e1)));
-                            // straight-line for the first twelve hits per candidate (warp-uniform branches), a loop beyond
-                            e0 = stage_hits4<0>(e0, id0, sp0);
-                            e1 = stage_hits4<0>(e1, id1, sp1);
-                            if (kmax > 4) {
-                                e0 = stage_hits4<32>(e0, id0, sp0);
-                                e1 = stage_hits4<32>(e1, id1, sp1);
-                                if (kmax > 8) {
-                                    e0 = stage_hits4<64>(e0, id0, sp0);
-                                    e1 = stage_hits4<64>(e1, id1, sp1);
-#pragma unroll 1
-                                    for (int k = 12; k < kmax; k += 4) {
-                                        sp0 += 32u;
-                                        sp1 += 32u;
-                                        e0 = stage_hits4<64>(e0, id0, sp0);
-                                        e1 = stage_hits4<64>(e1, id1, sp1);
-                                    }
-                                }
-                            }
-                        } else {
+                        {
                             unsigned dp0 = staged_sa + 4u * (unsigned)(stage_n + off);
                             unsigned dp1 = dp0 + 4u * (unsigned)__popc(e0);
                             while (e0) {
@@ -1154,11 +1221,22 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32, MB_SEARCH_MIN_CTAS) search_
                     hit_any = __reduce_or_sync(0xffffffffu, hit_any);
                     if (lane < (unsigned)nh && ((hit_any >> lane) & 1u)) P.flags[__float_as_uint(home[lane].w)] = 1;
                 }
-                // staged entries name home atoms by their slot in ws.home: write them out before it changes
-                if (MODE == 0 || MODE == 1) warp_flush<MODE>(stage_sa, staged_sa, home_sa, stage_n, P, lane);
+                // MODE 1: staged entries name home atoms by their slot in ws.home: write them out before it changes
+                if (MODE == 1) warp_flush<MODE>(stage_sa, staged_sa, home_sa, stage_n, P, lane);
             }
             first = false;
         } while (row0 < P.nrows);
+    }
+    if (MODE == 0) {
+        // last flush: the even part as a bulk copy, an odd last pair into the tail behind pair_cap (merge_pair_tail_kernel)
+        stage_n = warp_flush_bulk(stage_sa, stage_n, P, lane);
+        if (lane == 0) {
+            if (stage_n) {
+                const unsigned long long k = atomicAdd(P.counter + 3, 1ull);
+                if (k < (unsigned long long)PAIR_TAIL) P.pairs[P.pair_cap + k] = lds64(stage_sa);
+            }
+            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        }
     }
     if (MODE == 2) {
 #pragma unroll
@@ -1816,8 +1894,8 @@ static void pad_bounds(float cutoff, float lo[3], float hi[3]) {
 static int ensure_pair_capacity(Ctx* c, size_t want, bool with_dist) {
     if (want < 1024) want = 1024;
     if (want > c->pair_cap || !c->pairs.p) {
-        MB_TRY(c->pairs.reserve(want * sizeof(uint2)));
-        c->pair_cap = c->pairs.cap / sizeof(uint2);
+        MB_TRY(c->pairs.reserve((want + PAIR_TAIL) * sizeof(uint2)));
+        c->pair_cap = c->pairs.cap / sizeof(uint2) - PAIR_TAIL;
     }
     if (with_dist) MB_TRY(c->dists.reserve(c->pair_cap * sizeof(float)));
     return MB_OK;
@@ -1842,7 +1920,7 @@ static int bin_set(Ctx* c, const float* xyz, const unsigned long long* d_ids, si
 template <int MODE>
 static int launch_search_cells(Ctx* c, const SearchParams& P) {
     size_t smem = SEARCH_WARPS * sizeof(WarpShared);
-    if (MODE == 0 || MODE == 1) smem += SEARCH_WARPS * STAGE_CAP * sizeof(uint2);
+    if (MODE == 0 || MODE == 1) smem += SEARCH_WARPS * STAGE_ROOM * sizeof(uint2);
     if (MODE == 1) smem += SEARCH_WARPS * STAGE_CAP * sizeof(float);
     int per_sm = 1;
     constexpr bool CAN_VDW = MODE == 0 || MODE == 1;
@@ -1858,12 +1936,17 @@ static int launch_search_cells(Ctx* c, const SearchParams& P) {
         MB_CUDA(cudaEventCreate(&e1));
         MB_CUDA(cudaEventRecord(e0, c->stream));
     }
+    if (blocks * SEARCH_WARPS > PAIR_TAIL) blocks = PAIR_TAIL / SEARCH_WARPS;  // one tail slot per warp
     kern<<<blocks, SEARCH_WARPS * 32, smem, c->stream>>>(P);
     c->launches++;
     if (c->opt_profile) {
         MB_CUDA(cudaEventRecord(e1, c->stream));
         c->prof_events.push_back(e0);
         c->prof_events.push_back(e1);
+    }
+    if (MODE == 0) {
+        merge_pair_tail_kernel<<<1, 256, 0, c->stream>>>(P.pairs, P.pair_cap, P.counter);
+        c->launches++;
     }
     MB_CUDA(cudaGetLastError());
     return MB_OK;
@@ -2428,6 +2511,16 @@ int mb_plan_describe(const float* box9_colmajor, float cutoff, uint8_t pbc_dims,
     Ctx c;  // plain host state: no CUDA call is made on this path
     MB_TRY(host_box_from_colmajor(box9_colmajor, &c.box));
     c.has_box = true;
+    // tuning studies (tools/model_steps.py): "subdiv_x=3,subdiv_y=4,subdiv_z=4,slice_x=3,atoms_per_cell=6"
+    if (const char* e = getenv("MOLAR_B200_PLAN_OPTS")) {
+        int v;
+        double dv;
+        if (const char* q = strstr(e, "subdiv_x=")) if (sscanf(q + 9, "%d", &v) == 1) c.opt_subdiv_xyz[0] = v;
+        if (const char* q = strstr(e, "subdiv_y=")) if (sscanf(q + 9, "%d", &v) == 1) c.opt_subdiv_xyz[1] = v;
+        if (const char* q = strstr(e, "subdiv_z=")) if (sscanf(q + 9, "%d", &v) == 1) c.opt_subdiv_xyz[2] = v;
+        if (const char* q = strstr(e, "slice_x=")) if (sscanf(q + 8, "%d", &v) == 1) c.opt_slice_x = v;
+        if (const char* q = strstr(e, "atoms_per_cell=")) if (sscanf(q + 15, "%lf", &dv) == 1) c.opt_atoms_per_cell = dv;
+    }
     Plan pl;
     memset(&pl, 0, sizeof(pl));
     pl.full_shell = full_shell != 0;
