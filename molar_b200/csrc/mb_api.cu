@@ -260,7 +260,7 @@ void mb_close(MbCtx* h) {
         if (e) cudaEventDestroy(e);
     if (c.copy_stream) cudaStreamDestroy(c.copy_stream);
     if (c.h_pinned) cudaFreeHost(c.h_pinned);
-    for (int i = 0; i < 2; ++i)
+    for (int i = 0; i < 4; ++i)
         if (c.aux_stream[i]) cudaStreamDestroy(c.aux_stream[i]);
     if (c.aux_event) cudaEventDestroy(c.aux_event);
     cudaStreamDestroy(c.stream);
@@ -290,6 +290,9 @@ int mb_set_option(MbCtx* h, const char* key, double value) {
     else if (!strcmp(key, "exact_pbc")) c.opt_exact_pbc = (int)value;
     else if (!strcmp(key, "fused_fit")) c.opt_fused_fit = (int)value;
     else if (!strcmp(key, "fit_lag")) c.opt_fit_lag = (int)value;
+    else if (!strcmp(key, "fit_teams")) c.opt_fit_teams = (int)value;
+    else if (!strcmp(key, "fit_group")) c.opt_fit_group = (int)value;
+    else if (!strcmp(key, "fit_streams")) c.opt_fit_streams = (int)value;
     else if (!strcmp(key, "batch_streams")) c.opt_batch_streams = (int)value;
     else if (!strcmp(key, "two_set_cells_min")) c.opt_two_set_cells_min = value;
     else if (!strcmp(key, "profile")) {

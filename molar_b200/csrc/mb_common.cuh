@@ -91,7 +91,7 @@ struct SearchSlot {
 struct Ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
-    cudaStream_t aux_stream[2] = {nullptr, nullptr};  // batch_fit alternates frame groups over these
+    cudaStream_t aux_stream[4] = {nullptr, nullptr, nullptr, nullptr};  // batch_fit alternates frame groups over these
     cudaEvent_t aux_event = nullptr;
     int sm_count = 148;
     uint64_t launches = 0;
@@ -144,7 +144,10 @@ struct Ctx {
     double opt_two_set_cells_min = 5.0e7;  // two-set searches use the cell kernel when n1*n2 exceeds this
     int opt_batch_streams = 0;  // streams (slots) batch_search alternates frames over; 0 = automatic
     int opt_fused_fit = 0;  // batch_fit: 0 two kernels per frame group, 1/2 TMA-staged single-pass kernels, 3 persistent kernel with an L2-served lagging second pass
-    int opt_fit_lag = 0;    // fused_fit = 3: frames between pass 1 and pass 2 (0 = automatic)
+    int opt_fit_lag = 0;    // fused_fit = 3: frames (of a team) between pass 1 and pass 2 (0 = automatic)
+    int opt_fit_group = 0;  // two-kernel batch_fit: frames per group (0 = automatic)
+    int opt_fit_streams = 0;  // two-kernel batch_fit: streams the groups alternate over (0 = automatic, <= 4)
+    int opt_fit_teams = 0;  // fused_fit = 3: teams of CTAs working on different frames at once (0 = automatic)
     int opt_exact_pbc = 0;    // 1: wrapped cell pairs always use the exact PeriodicBox path (no filter)
     int opt_profile = 0;      // record CUDA events around every search-kernel launch
     std::vector<cudaEvent_t> prof_events;  // begin/end pairs not yet harvested

@@ -724,14 +724,17 @@ struct LagParams {
     const float* masses;  // [n]
     int n, nf, superpose, lag;
     int per;              // atoms per CTA slice (multiple of 4)
-    double* part_fit;     // [nf][grid][16]
-    double* part_sup;     // [nf][grid]
+    int teams;            // T: the grid is T teams of gridDim.x / T CTAs; team t owns frames t, t + T, ...
+    int use_smem;         // the CTA's slice of the reference frame and of the masses lives in shared memory (16 B/atom)
+    double* part_fit;     // [nf][team size][16]
+    double* part_sup;     // [nf][team size]
     unsigned* tick_fit;   // [nf]
     unsigned* flag;       // [nf]
     double* fitres;       // [nf][16]
 };
 
-constexpr int LAG_THREADS = 256;            // streaming threads of a CTA
+constexpr int LAG_THREADS = 224;            // streaming threads of a CTA (7 warps: with the solver warp a CTA is 8 warps — warps are
+                                            // allocated in groups of four, a ninth would cost the registers of twelve)
 constexpr int LAG_BLOCK = LAG_THREADS + 32;  // + one solver warp (fold + 3x3 SVD of the frames this CTA is responsible for)
 
 // barrier of the streaming warps only (the solver warp never joins it)
@@ -780,12 +783,17 @@ __device__ __forceinline__ double warp_sum16(const double (&v)[16], unsigned lan
 __global__ void __launch_bounds__(LAG_BLOCK, 2) fit_lag_kernel(const LagParams P) {
     __shared__ double wsum[LAG_THREADS / 32][16];
     __shared__ double sRt[12];
-    const int b = blockIdx.x, G = gridDim.x, tid = threadIdx.x;
+    // teams: CTA blockIdx.x is member b of team `team`; a team works through its frames one after the other, the T
+    // teams run T frames concurrently (a frame's chain of dependent latencies — loads, block reduction, ticket, flag,
+    // L2 re-read — is several microseconds whatever the slice size, so one team alone cannot reach the HBM rate)
+    const int T = P.teams, team = blockIdx.x % T, b = blockIdx.x / T, G = gridDim.x / T, tid = threadIdx.x;
     const unsigned lane = tid & 31u, wid = tid >> 5;
     const double o2x = P.ref[0], o2y = P.ref[1], o2z = P.ref[2];  // pivot of the reference frame: atom 0
+    const int nft = P.nf > team ? (P.nf - team + T - 1) / T : 0;  // frames of this team
     if (wid == LAG_THREADS / 32) {
-        // ---------------- solver warp: frames b, b + G, ... ----------------
-        for (int f = b; f < P.nf; f += G) {
+        // ---------------- solver warp: every G-th frame of the team ----------------
+        for (int i = b; i < nft; i += G) {
+            const int f = team + i * T;
             if (lane == 0)
                 while (ld_acquire_u32(P.tick_fit + f) != (unsigned)G) __nanosleep(200);
             __syncwarp();
@@ -815,9 +823,35 @@ __global__ void __launch_bounds__(LAG_BLOCK, 2) fit_lag_kernel(const LagParams P
     const int a0 = min(P.n, b * P.per), a1 = min(P.n, a0 + P.per);
     const bool vec = (P.n & 3) == 0 && ((reinterpret_cast<uintptr_t>(P.frames) | reinterpret_cast<uintptr_t>(P.ref) |
                                          reinterpret_cast<uintptr_t>(P.masses)) & 15u) == 0;
+    // The slice of the reference frame and of the masses is the same for every frame: staged once in shared memory, so
+    // that the only global loads of the frame loop are the frame's own bytes (loads in flight are what bounds a
+    // latency-exposed streaming loop; L2 reads of the reference would take 4/7 of them)
+    extern __shared__ __align__(16) float lag_dyn[];
+    float* sref = lag_dyn;
+    float* smass = lag_dyn + 3 * (size_t)P.per;
+    if (P.use_smem) {
+        for (int k = tid; k < 3 * (a1 - a0); k += LAG_THREADS) sref[k] = P.ref[3 * (size_t)a0 + k];
+        for (int k = tid; k < a1 - a0; k += LAG_THREADS) smass[k] = P.masses[a0 + k];
+        bar_stream();
+    }
+    // reference coordinates + masses of the four atoms starting at atom a (a - a0 is a multiple of 4)
+    auto ref4 = [&](int a, float (&x)[4], float (&y)[4], float (&z)[4], float4& m4) {
+        if (P.use_smem) {
+            const float4* p = reinterpret_cast<const float4*>(sref + 3 * (a - a0));
+            const float4 u = p[0], v = p[1], w = p[2];
+            x[0] = u.x; y[0] = u.y; z[0] = u.z; x[1] = u.w; y[1] = v.x; z[1] = v.y;
+            x[2] = v.z; y[2] = v.w; z[2] = w.x; x[3] = w.y; y[3] = w.z; z[3] = w.w;
+            m4 = *reinterpret_cast<const float4*>(smass + (a - a0));
+        } else {
+            load4(P.ref, a, x, y, z);
+            m4 = __ldg(reinterpret_cast<const float4*>(P.masses + a));
+        }
+    };
+    constexpr int LAG_U = 3;  // four-atom groups whose loads a thread issues before it uses the first
 
-    for (int f = 0; f < P.nf + P.lag; ++f) {
-        if (f < P.nf) {
+    for (int i = 0; i < nft + P.lag; ++i) {
+        const int f = team + i * T;
+        if (i < nft) {
             // ---------------- pass 1 of frame f ----------------
             const float* fr = P.frames + (size_t)f * P.n * 3;
             const double o1x = __ldcg(fr), o1y = __ldcg(fr + 1), o1z = __ldcg(fr + 2);
@@ -837,15 +871,31 @@ __global__ void __launch_bounds__(LAG_BLOCK, 2) fit_lag_kernel(const LagParams P
                 v[13] += wz * q1x; v[14] += wz * q1y; v[15] += wz * q1z;
             };
             if (vec) {
-                for (int a = a0 + 4 * tid; a < a1; a += 4 * LAG_THREADS) {
-                    float x1[4], y1[4], z1[4], x2[4], y2[4], z2[4];
-                    load4(fr, a, x1, y1, z1);
-                    load4(P.ref, a, x2, y2, z2);
-                    const float4 m4 = __ldg(reinterpret_cast<const float4*>(P.masses + a));
-                    acc(x1[0], y1[0], z1[0], x2[0], y2[0], z2[0], m4.x);
-                    acc(x1[1], y1[1], z1[1], x2[1], y2[1], z2[1], m4.y);
-                    acc(x1[2], y1[2], z1[2], x2[2], y2[2], z2[2], m4.z);
-                    acc(x1[3], y1[3], z1[3], x2[3], y2[3], z2[3], m4.w);
+                for (int a = a0 + 4 * tid; a < a1; a += 4 * LAG_THREADS * LAG_U) {
+                    float4 q[LAG_U][3];
+#pragma unroll
+                    for (int u = 0; u < LAG_U; ++u) {
+                        const int au = a + u * 4 * LAG_THREADS;
+                        if (au < a1) {
+                            const float4* p = reinterpret_cast<const float4*>(fr + 3 * (size_t)au);
+                            q[u][0] = __ldcg(p);
+                            q[u][1] = __ldcg(p + 1);
+                            q[u][2] = __ldcg(p + 2);
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < LAG_U; ++u) {
+                        const int au = a + u * 4 * LAG_THREADS;
+                        if (au < a1) {
+                            float x2[4], y2[4], z2[4];
+                            float4 m4;
+                            ref4(au, x2, y2, z2, m4);
+                            acc(q[u][0].x, q[u][0].y, q[u][0].z, x2[0], y2[0], z2[0], m4.x);
+                            acc(q[u][0].w, q[u][1].x, q[u][1].y, x2[1], y2[1], z2[1], m4.y);
+                            acc(q[u][1].z, q[u][1].w, q[u][2].x, x2[2], y2[2], z2[2], m4.z);
+                            acc(q[u][2].y, q[u][2].z, q[u][2].w, x2[3], y2[3], z2[3], m4.w);
+                        }
+                    }
                 }
             } else {
                 for (int a = a0 + tid; a < a1; a += LAG_THREADS)
@@ -865,8 +915,8 @@ __global__ void __launch_bounds__(LAG_BLOCK, 2) fit_lag_kernel(const LagParams P
             bar_stream();
             if (tid == 0) atomicAdd(P.tick_fit + f, 1u);  // the G-th ticket releases the frame to its solver warp
         }
-        const int g = f - P.lag;
-        if (g >= 0) {
+        const int g = f - P.lag * T;
+        if (i >= P.lag) {
             // ---------------- pass 2 of frame g: (R, t) was published LAG frames ago ----------------
             if (tid == 0)
                 while (ld_acquire_u32(P.flag + g) == 0u) __nanosleep(100);
@@ -892,20 +942,36 @@ __global__ void __launch_bounds__(LAG_BLOCK, 2) fit_lag_kernel(const LagParams P
                 oz = (float)pz;
             };
             if (vec) {
-                for (int a = a0 + 4 * tid; a < a1; a += 4 * LAG_THREADS) {
-                    float x1[4], y1[4], z1[4], x2[4], y2[4], z2[4], ox[4], oy[4], oz[4];
-                    const float4* p = reinterpret_cast<const float4*>(fr + 3 * (size_t)a);
-                    const float4 u = __ldcg(p), vv = __ldcg(p + 1), ww = __ldcg(p + 2);  // L2 hit (read LAG frames ago)
-                    x1[0] = u.x; y1[0] = u.y; z1[0] = u.z; x1[1] = u.w; y1[1] = vv.x; z1[1] = vv.y;
-                    x1[2] = vv.z; y1[2] = vv.w; z1[2] = ww.x; x1[3] = ww.y; y1[3] = ww.z; z1[3] = ww.w;
-                    load4(P.ref, a, x2, y2, z2);
+                for (int a = a0 + 4 * tid; a < a1; a += 4 * LAG_THREADS * LAG_U) {
+                    float4 q[LAG_U][3];
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) sup(x1[k], y1[k], z1[k], x2[k], y2[k], z2[k], ox[k], oy[k], oz[k]);
-                    if (P.superpose) {
-                        float4* q = reinterpret_cast<float4*>(fr + 3 * (size_t)a);
-                        __stcs(q, make_float4(ox[0], oy[0], oz[0], ox[1]));
-                        __stcs(q + 1, make_float4(oy[1], oz[1], ox[2], oy[2]));
-                        __stcs(q + 2, make_float4(oz[2], ox[3], oy[3], oz[3]));
+                    for (int u = 0; u < LAG_U; ++u) {
+                        const int au = a + u * 4 * LAG_THREADS;
+                        if (au < a1) {
+                            const float4* p = reinterpret_cast<const float4*>(fr + 3 * (size_t)au);
+                            q[u][0] = __ldcg(p);  // L2 hits (the slice was read `lag` frames of this team ago)
+                            q[u][1] = __ldcg(p + 1);
+                            q[u][2] = __ldcg(p + 2);
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < LAG_U; ++u) {
+                        const int au = a + u * 4 * LAG_THREADS;
+                        if (au < a1) {
+                            float x2[4], y2[4], z2[4], ox[4], oy[4], oz[4];
+                            float4 m4;
+                            ref4(au, x2, y2, z2, m4);
+                            sup(q[u][0].x, q[u][0].y, q[u][0].z, x2[0], y2[0], z2[0], ox[0], oy[0], oz[0]);
+                            sup(q[u][0].w, q[u][1].x, q[u][1].y, x2[1], y2[1], z2[1], ox[1], oy[1], oz[1]);
+                            sup(q[u][1].z, q[u][1].w, q[u][2].x, x2[2], y2[2], z2[2], ox[2], oy[2], oz[2]);
+                            sup(q[u][2].y, q[u][2].z, q[u][2].w, x2[3], y2[3], z2[3], ox[3], oy[3], oz[3]);
+                            if (P.superpose) {
+                                float4* qo = reinterpret_cast<float4*>(fr + 3 * (size_t)au);
+                                __stcs(qo, make_float4(ox[0], oy[0], oz[0], ox[1]));
+                                __stcs(qo + 1, make_float4(oy[1], oz[1], ox[2], oy[2]));
+                                __stcs(qo + 2, make_float4(oz[2], ox[3], oy[3], oz[3]));
+                            }
+                        }
                     }
                 }
             } else {
@@ -1035,48 +1101,74 @@ int batch_fit_impl(Ctx* c, size_t ref_frame, size_t f0, size_t f1, int superpose
     const float* ref = c->batch_ref.as<float>();
     // ---- single-pass path, third design (fused_fit = 3): one persistent kernel, pass 2 lags by LAG frames and reads L2
     if (c->opt_fused_fit == 3) {
-        int occ = 0;
-        MB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fit_lag_kernel, LAG_BLOCK, 0));
-        occ = std::max(1, std::min(occ, 2));
+        const int occ = 2;  // CTAs per SM the kernel is sized for (<= 128 registers x 256 threads)
         // grid: all resident CTAs, but never more CTAs than slices of 4 * LAG_THREADS atoms (one vector round)
         const size_t tile = 4 * (size_t)LAG_THREADS;
-        int grid = (int)std::min<size_t>((size_t)c->sm_count * occ, std::max<size_t>(1, (n + tile - 1) / tile));
-        // slices of whole tiles, as even as the tile count allows
+        const int grid_max = (int)std::min<size_t>((size_t)c->sm_count * occ, std::max<size_t>(1, (n + tile - 1) / tile));
         const size_t ntile = (n + tile - 1) / tile;
-        const size_t tiles_per = (ntile + grid - 1) / grid;
-        grid = (int)((ntile + tiles_per - 1) / tiles_per);
-        const int per = (int)(tiles_per * tile);
+        // T teams of grid / T CTAs: each team processes its own frames (t, t + T, ...), T frames in flight.  Automatic:
+        // the largest T (<= 4) whose slices of the reference frame + masses (16 B/atom) still fit two CTAs per SM.
+        const size_t smem_budget = 100 * 1024;
+        auto shape = [&](int T, int& gt, int& per) {
+            gt = std::max(1, grid_max / T);
+            const size_t tiles_per = (ntile + gt - 1) / gt;
+            gt = (int)((ntile + tiles_per - 1) / tiles_per);  // slices of whole tiles, as even as the tile count allows
+            per = (int)(tiles_per * tile);
+        };
+        int T = c->opt_fit_teams, gt = 1, per = 0;
+        const int t_cap = std::max(1, std::min(grid_max, (int)std::min<size_t>(nf, 64)));
+        if (T > 0) {
+            T = std::min(T, t_cap);
+            shape(T, gt, per);
+        } else {
+            for (T = std::min(4, t_cap); T >= 1; --T) {
+                shape(T, gt, per);
+                if ((size_t)per * 16 <= smem_budget || T == 1) break;
+            }
+        }
+        const int grid = gt * T;
+        const int use_smem = (size_t)per * 16 <= smem_budget ? 1 : 0;
+        const size_t dyn_smem = use_smem ? (size_t)per * 16 : 0;
+        MB_CUDA(cudaFuncSetAttribute(fit_lag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_budget));
+        MB_CUDA(cudaFuncSetAttribute(fit_lag_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        int occ_real = 0;
+        MB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_real, fit_lag_kernel, LAG_BLOCK, dyn_smem));
+        if ((long long)occ_real * c->sm_count < grid)
+            return fail(MB_ERR_STATE, "batch_fit: persistent grid of %d CTAs (%zu B shared) does not fit the device (%d per SM)", grid,
+                        dyn_smem, occ_real);
         // LAG: long enough for the finish of a frame (fold + SVD, ~10 us) to be over, short enough for the frames
         // in flight (read + written) to stay inside L2
         const size_t fb = n * 12;
-        int lag = (int)std::max<size_t>(2, std::min<size_t>(64, ((size_t)40 << 20) / std::max<size_t>(fb, 1)));
+        int lag = (int)std::max<size_t>(1, std::min<size_t>(64, ((size_t)48 << 20) / std::max<size_t>(fb * T, 1)));
         if (c->opt_fit_lag > 0) lag = c->opt_fit_lag;
         const size_t chunk = std::min<size_t>(nf, 4096);
         RedScratch s{};
-        MB_TRY(red_scratch(c, 2 * chunk, chunk * (size_t)grid * 17, nf * 17, &s));
+        MB_TRY(red_scratch(c, 2 * chunk, chunk * (size_t)gt * 17, nf * 17, &s));
         double* fitres = s.results;
         double* d_rmsd = s.results + nf * 16;
         for (size_t g0 = 0; g0 < nf; g0 += chunk) {
             const size_t gn = std::min(chunk, nf - g0);
             LagParams P;
+            P.teams = T;
+            P.use_smem = use_smem;
             P.frames = c->batch.as<float>() + (f0 + g0) * n * 3;
             P.ref = ref;
             P.masses = c->masses.as<float>();
             P.n = (int)n;
             P.nf = (int)gn;
             P.superpose = superpose;
-            P.lag = (int)std::min<size_t>((size_t)lag, gn);
+            P.lag = (int)std::min<size_t>((size_t)lag, std::max<size_t>(1, gn / T));
             P.per = per;
             P.part_fit = s.partials;
-            P.part_sup = s.partials + chunk * (size_t)grid * 16;
+            P.part_sup = s.partials + chunk * (size_t)gt * 16;
             P.tick_fit = s.tickets;
             P.flag = s.tickets + chunk;
             P.fitres = fitres + g0 * 16;
             MB_CUDA(cudaMemsetAsync(P.flag, 0, gn * sizeof(unsigned), c->stream));
             void* args[] = {&P};
-            MB_CUDA(cudaLaunchCooperativeKernel((const void*)fit_lag_kernel, dim3(grid), dim3(LAG_BLOCK), args, 0,
+            MB_CUDA(cudaLaunchCooperativeKernel((const void*)fit_lag_kernel, dim3(grid), dim3(LAG_BLOCK), args, dyn_smem,
                                                 c->stream));
-            finish_rmsd_kernel<<<(unsigned)gn, 32, 0, c->stream>>>(P.part_sup, grid, (int)n, d_rmsd + g0);
+            finish_rmsd_kernel<<<(unsigned)gn, 32, 0, c->stream>>>(P.part_sup, gt, (int)n, d_rmsd + g0);
             c->launches += 2;
         }
         MB_CUDA(cudaGetLastError());
@@ -1196,10 +1288,10 @@ int batch_fit_impl(Ctx* c, size_t ref_frame, size_t f0, size_t f1, int superpose
     // superposition pass re-reads the group in reverse order, so its first ~90 MB still hit L2.
     size_t group = std::max<size_t>(1, std::min<size_t>(nf, (size_t)(768u << 20) / std::max<size_t>(frame_bytes, 1)));
     group = std::min<size_t>(group, 2048);
-    (void)frame_bytes;
+    if (c->opt_fit_group > 0) group = std::min<size_t>(nf, (size_t)c->opt_fit_group);
     int nb = (int)std::max<size_t>(1, std::min<size_t>((n + RED_THREADS * 8 - 1) / (RED_THREADS * 8),
                                                       std::max<size_t>(4, (size_t)c->sm_count * 8 / group)));
-    constexpr int NS = 2;
+    const int NS = c->opt_fit_streams > 0 ? std::min(c->opt_fit_streams, 4) : 2;
     for (int i = 0; i < NS; ++i)
         if (!c->aux_stream[i]) MB_CUDA(cudaStreamCreateWithFlags(&c->aux_stream[i], cudaStreamNonBlocking));
     if (!c->aux_event) MB_CUDA(cudaEventCreateWithFlags(&c->aux_event, cudaEventDisableTiming));

@@ -28,11 +28,21 @@ __host__ __device__ inline bool kabsch_rotation(const double A[9], double R[9]) 
                     beta += a[i][q] * a[i][q];
                     gamma += a[i][p] * a[i][q];
                 }
-                if (gamma == 0.0 || fabs(gamma) <= eps * sqrt(alpha * beta)) continue;
+                // |gamma| <= eps sqrt(alpha beta), without the square root
+                if (gamma == 0.0 || gamma * gamma <= (eps * eps) * (alpha * beta)) continue;
                 rotated = true;
-                double zeta = (beta - alpha) / (2.0 * gamma);
-                double t = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+                // t = sign(zeta) / (|zeta| + sqrt(1 + zeta^2)) with zeta = (beta - alpha) / (2 gamma), multiplied through
+                // by |2 gamma|: one square root, one division and one reciprocal square root per rotation instead of
+                // six such operations — on the device this chain of serial f64 div / sqrt sequences IS the latency of
+                // a frame's fit (three rotations per sweep, six to eight sweeps)
+                const double da = beta - alpha, dg = 2.0 * gamma;
+                const double hyp = sqrt(da * da + dg * dg);
+                double t = (da >= 0 ? dg : -dg) / (fabs(da) + hyp);
+#ifdef __CUDA_ARCH__
+                double c = rsqrt(1.0 + t * t), s = c * t;
+#else
                 double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
+#endif
                 for (int i = 0; i < 3; ++i) {
                     double x = a[i][p], y = a[i][q];
                     a[i][p] = c * x - s * y;
