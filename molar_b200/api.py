@@ -99,6 +99,8 @@ class System:
 
     def set_option(self, key, value):
         check(self._lib.mb_set_option(self._h, key.encode(), float(value)))
+        if key == "with_dist":
+            self._with_dist = bool(value)
 
     def coords(self):
         out = np.empty((self._n, 3), np.float32)
@@ -321,9 +323,10 @@ def distance_search(cutoff, data1, data2=None, dims=None):
         p2, n2 = data2._ids()
         cnt = check(s._lib.mb_search_double(s._h, cutoff, p1, n1, p2, n2, use2, pbc))
     pairs = np.empty((cnt, 2), np.uint64)
-    dist = np.empty(cnt, np.float32)
+    # option with_dist=0 (pairs-only kernel): the distances were not computed and None is returned in their place
+    dist = np.empty(cnt, np.float32) if getattr(s, "_with_dist", True) else None
     if cnt:
-        check(s._lib.mb_fill_pairs(s._h, pairs.ctypes.data, dist.ctypes.data))
+        check(s._lib.mb_fill_pairs(s._h, pairs.ctypes.data, dist.ctypes.data if dist is not None else None))
     return pairs, dist
 
 

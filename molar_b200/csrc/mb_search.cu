@@ -76,6 +76,7 @@ struct SearchParams {
     unsigned char* flags;        // MODE 3 (`within`): flags[global id of a set-1 atom] = 1 if it has a neighbour
     GridSpec g;
     float rc2;
+    float band;            // direct tests: |d2f - rc2| below this is re-evaluated with the reference's exact expression
     float rc2_lo, rc2_hi;  // band around cutoff^2 outside which the shifted-image filter is decisive
     int fast_pbc;          // 1: wrapped cell pairs may use the filter (see plan_cells)
     int nrows;
@@ -528,6 +529,25 @@ __device__ __forceinline__ unsigned long long rc2_minus_d2(unsigned long long nx
     const unsigned long long xx = mul2(dx, dx), yy = mul2(dy, dy), zz = mul2(dz, dz);
     const unsigned long long s = fma2(fma2(xx, one2, yy), one2, zz);
     return sub2(rc22, s);
+}
+
+// Filter form of the same test: d2f - rc2 with d2f accumulated by three fused multiply-adds that start from -rc2
+// (6 packed instructions instead of 9).  d2f is NOT the reference's number — the reference rounds every product and every
+// sum — but both approximate S = dx^2 + dy^2 + dz^2 of the SAME f32 differences: |d2_ref - S| <= 3.01 u S and
+// |t - (S - rc2)| <= 2 u max(S, rc2) + u |t| (u = 2^-24), so |t| > 10.1 u rc2 implies sign(t) = sign(d2_ref - rc2)
+// (S > 2 rc2 is a miss for both whatever t).  The caller keeps min |t| of a step and re-runs the step with
+// rc2_minus_d2 when it is below band = 16 u rc2 (SearchParams::band); a few thousand tests per 10^9 are.
+__device__ __forceinline__ unsigned long long d2f_minus_rc2(unsigned long long nx, unsigned long long ny,
+                                                            unsigned long long nz, const float4& h,
+                                                            unsigned long long nrc22) {
+    const unsigned long long dx = sub2(nx, pk2(h.x, h.x)), dy = sub2(ny, pk2(h.y, h.y)), dz = sub2(nz, pk2(h.z, h.z));
+    return fma2(dz, dz, fma2(dy, dy, fma2(dx, dx, nrc22)));
+}
+// running minimum of |t| over the tests of a step (one FMNMX3 with |.| operand modifiers)
+__device__ __forceinline__ float min3abs(float m, float a, float b) {
+    float r;
+    asm("{ .reg .f32 x, y;\n  abs.f32 x, %2;\n  abs.f32 y, %3;\n  min.f32 %0, %1, x, y; }" : "=f"(r) : "f"(m), "f"(a), "f"(b));
+    return r;
 }
 
 // vdW variant: c2 - ((dx*dx + dy*dy) + dz*dz) with c2 = the pair's own squared cutoff (already rounded).  The final
@@ -992,6 +1012,29 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32, MB_SEARCH_MIN_CTAS) search_
                                                  eps2 = pk2(FLT_EPSILON, FLT_EPSILON);
                         const int nh4 = (nh + 3) & ~3;
                         unsigned a0 = 0, a1 = 0;
+                        bool exact = VDW;
+                        if (!VDW) {
+                            // filter pass: fused d2f - rc2, sign SET = within; min |t| says whether any test of the
+                            // step is too close to the cutoff for the filter to be trusted
+                            const unsigned long long nrc22 = pk2_once(-rc2, -rc2);
+                            float tmin = 3.0e38f;
+#pragma unroll 1
+                            for (int gj = nh4 - 4; gj >= 0; gj -= 4) {
+#pragma unroll
+                                for (int jj = 3; jj >= 0; --jj) {
+                                    float t0, t1;
+                                    upk2(d2f_minus_rc2(nx, ny, nz, home[gj + jj], nrc22), t0, t1);
+                                    a0 = __funnelshift_l(__float_as_uint(t0), a0, 1);
+                                    a1 = __funnelshift_l(__float_as_uint(t1), a1, 1);
+                                    tmin = min3abs(tmin, t0, t1);
+                                }
+                            }
+                            exact = __any_sync(0xffffffffu, tmin <= P.band);
+                            a0 = ~a0;  // the exact loop below produces "not within" bits
+                            a1 = ~a1;
+                        }
+                        if (exact) {
+                        a0 = a1 = 0;
 #pragma unroll 1
                         for (int gj = nh4 - 4; gj >= 0; gj -= 4) {
 #pragma unroll
@@ -1012,6 +1055,7 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32, MB_SEARCH_MIN_CTAS) search_
                                 a0 = __funnelshift_l(__float_as_uint(t0), a0, 1);
                                 a1 = __funnelshift_l(__float_as_uint(t1), a1, 1);
                             }
+                        }
                         }
                         m0 = ~a0 & valid_slots;
                         m1 = ~a1 & valid_slots;
@@ -1978,6 +2022,7 @@ int enqueue_cells_search(Ctx* c, const float* xyz, const unsigned long long* d_i
     P.vdwA = P.vdwB = nullptr;
     P.g = g;
     P.rc2 = cutoff * cutoff;
+    P.band = 16.0f * 5.9604645e-8f * P.rc2;
     P.one = 1.0f;
     P.rc2_lo = pl.rc2_lo;
     P.rc2_hi = pl.rc2_hi;
@@ -2040,6 +2085,7 @@ static int enqueue_cells_search2(Ctx* c, const float* xyz1, const unsigned long 
     P.vdwB = d_vdw2;
     P.g = g;
     P.rc2 = cutoff * cutoff;
+    P.band = 16.0f * 5.9604645e-8f * P.rc2;
     P.one = 1.0f;
     P.rc2_lo = pl.rc2_lo;
     P.rc2_hi = pl.rc2_hi;

@@ -24,7 +24,20 @@ def run_single(mb, xyz, cutoff, box=None, dims=None, ids=None, **opts):
     sel = s(ids) if ids is not None else s()
     pairs, dist = mb.distance_search(cutoff, sel, dims=dims)
     s.close()
+    if dist is None:  # with_dist=0: the pairs-only kernel
+        p = orc.canonical_pairs(pairs)
+        assert len(p) == len(pairs), "GPU pair list contains duplicates"
+        return p, None
     return gpu_canonical(pairs, dist)
+
+
+def run_single_both(mb, xyz, cutoff, op, od, **kw):
+    """The same search through the pairs + distances kernel (MODE 1) and the pairs-only kernel (MODE 0: fused filter
+    + exact re-evaluation, per-home emission, bulk flush): both must give the oracle's pair set."""
+    gp, gd = run_single(mb, xyz, cutoff, **kw)
+    assert_same_pairs(gp, gd, op, od)
+    gp0, _ = run_single(mb, xyz, cutoff, with_dist=0, **kw)
+    assert gp0.shape == op.shape and np.array_equal(gp0, op), "pairs-only kernel: pair sets differ"
 
 
 ORTHO_SMALL = np.diag([4.0, 4.4, 5.1]).astype(np.float32)
@@ -56,8 +69,28 @@ def test_single_pbc_cells_orthorhombic(mb, subdiv):
     xyz = orc.synth_frame(SEED + 2, 0, 30000, M, stray_permille=10)
     op, od, dims = oracle_single(1.2, xyz, box=M, pbc=7)
     assert list(dims) == [5, 5, 6]
-    gp, gd = run_single(mb, xyz, 1.2, box=M, dims=[True] * 3, subdiv=subdiv)
-    assert_same_pairs(gp, gd, op, od)
+    run_single_both(mb, xyz, 1.2, op, od, box=M, dims=[True] * 3, subdiv=subdiv)
+
+
+@pytest.mark.parametrize("with_dist", [0, 1])
+def test_single_pbc_lattice_ties_at_cutoff(mb, with_dist):
+    """Atoms on a 0.3 nm lattice, cutoff 1.5 nm = 5 lattice steps: thousands of pairs sit within a few ulps of the
+    cutoff ((5,0,0), (3,4,0), ... in lattice units, each coordinate an f32 rounding of k * 0.3).  The fused-multiply-add
+    filter of the pair kernel cannot decide those; they must come out as the reference's unfused expression decides
+    them (with_dist=0: filter + exact re-evaluation of the step; with_dist=1: the MODE 1 kernel)."""
+    k = 30
+    g = (np.arange(k, dtype=np.float64) * 0.3).astype(np.float32)
+    xyz = np.stack(np.meshgrid(g, g, g, indexing="ij"), -1).reshape(-1, 3).astype(np.float32)
+    M = np.diag([k * 0.3] * 3).astype(np.float32)
+    op, od, dims = oracle_single(1.5, xyz, box=M, pbc=7)
+    d2 = od.astype(np.float64) ** 2
+    assert (np.abs(d2 - 2.25) < 1e-5).sum() > 1000  # the case really has ties at the cutoff
+    if with_dist:
+        gp, gd = run_single(mb, xyz, 1.5, box=M, dims=[True] * 3)
+        assert_same_pairs(gp, gd, op, od)
+    else:
+        gp, _ = run_single(mb, xyz, 1.5, box=M, dims=[True] * 3, with_dist=0)
+        assert gp.shape == op.shape and np.array_equal(gp, op)
 
 
 @pytest.mark.parametrize("subdiv", [0, 1, 2])
@@ -65,8 +98,7 @@ def test_single_pbc_cells_triclinic_config3_shape(mb, subdiv):
     M = (TRIC * np.float32(0.3)).astype(np.float32)
     xyz = orc.synth_frame(SEED + 3, 0, 27000, M, stray_permille=10)
     op, od, dims = oracle_single(1.2, xyz, box=M, pbc=7)
-    gp, gd = run_single(mb, xyz, 1.2, box=M, dims=[True] * 3, subdiv=subdiv)
-    assert_same_pairs(gp, gd, op, od)
+    run_single_both(mb, xyz, 1.2, op, od, box=M, dims=[True] * 3, subdiv=subdiv)
 
 
 def test_single_pbc_cells_triclinic_adversarial_positive_shear(mb):
@@ -100,8 +132,7 @@ def test_single_partial_pbc(mb, dims):
     xyz = orc.synth_frame(SEED + 5, 0, 12000, M, stray_permille=40)
     pbc = sum(1 << i for i in range(3) if dims[i])
     op, od, gd_ = oracle_single(1.2, xyz, box=M, pbc=pbc)
-    gp, gd = run_single(mb, xyz, 1.2, box=M, dims=dims)
-    assert_same_pairs(gp, gd, op, od)
+    run_single_both(mb, xyz, 1.2, op, od, box=M, dims=dims)
 
 
 def test_single_nonperiodic_config1_2lao(mb, golden_dir):
@@ -119,8 +150,7 @@ def test_single_nonperiodic_cells(mb):
     M = np.diag([6.0, 7.0, 8.0]).astype(np.float32)
     xyz = orc.synth_frame(SEED + 6, 0, 25000, M) - np.float32(2.5)  # negative coordinates too
     op, od, dims = oracle_single(0.9, xyz)
-    gp, gd = run_single(mb, xyz, 0.9)
-    assert_same_pairs(gp, gd, op, od)
+    run_single_both(mb, xyz, 0.9, op, od)
 
 
 def test_single_with_selection_ids(mb):
@@ -170,6 +200,14 @@ def test_double_and_within_cell_path_vs_oracle(mb, pbc, tric):
     gp, gd = orc.ordered_pairs(pairs, dist)
     assert len(gp) == len(pairs)
     assert_same_pairs(gp, gd, op, od)
+    # the same search through the pairs-only kernel (MODE 0)
+    s.set_option("with_dist", 0)
+    pairs0, none = mb.distance_search(1.0, s(ids1), s(ids2), dims=[bool(pbc & 1), bool(pbc & 2), bool(pbc & 4)])
+    s.set_option("with_dist", 1)
+    assert none is None and len(pairs0) == len(op)
+    k0 = np.sort((pairs0[:, 0].astype(np.uint64) << np.uint64(32)) | pairs0[:, 1].astype(np.uint64))
+    ko = np.sort((op[:, 0].astype(np.uint64) << np.uint64(32)) | op[:, 1].astype(np.uint64))
+    assert np.array_equal(k0, ko)
     # within: small inner set, periodic and non-periodic
     inner = np.arange(100, 400, dtype=np.uint64)
     if pbc:
