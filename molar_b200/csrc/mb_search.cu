@@ -34,7 +34,10 @@ namespace mb {
 constexpr unsigned DROPPED = 0xFFFFFFFFu;
 constexpr int MAX_REACH = 7;
 constexpr int MAX_ROWS = (2 * MAX_REACH + 1) * (2 * MAX_REACH + 1);
-constexpr int STAGE_CAP = 512;  // pairs staged per warp before a flush (>= 16 lanes * 32 home atoms)
+#ifndef MB_STAGE_CAP
+#define MB_STAGE_CAP 512
+#endif
+constexpr int STAGE_CAP = MB_STAGE_CAP;  // pairs staged per warp before a flush (>= 8 homes x 64 candidates of a dense pass)
 constexpr int STAGE_ROOM = STAGE_CAP + 2;  // entries allocated per warp: a carried-over odd pair + a full pass of STAGE_CAP (keeps 16-byte alignment)
 #ifndef MB_SEARCH_WARPS
 #define MB_SEARCH_WARPS 8

@@ -26,6 +26,7 @@ tr = mb.fit_transform(s(), ref()); s().apply_transform(tr); r = mb.rmsd(s(), ref
 t = mb.Trajectory(); t.synth(1, 0, 4, 8000, M, mass_seed=1)
 c = t.search(1.2); c2 = t.search(1.2, count_only=True); rows = t.pipeline(1.2); rr = t.fit(0)
 t.set_option("fused_fit", 1); rr2 = t.fit(0)
+t.set_option("fused_fit", 3); rr3 = t.fit(0); t.set_option("fused_fit", 0)  # persistent kernel: solver warps, teams, L2-served lag
 print("ok", len(p), len(p2), len(w), len(p3), len(p4), c.tolist(), c2.tolist(), float(r))
 # ---- round 2 additions: periodic reductions, inertia, trajectory ingest, pair-list consumers ----
 from oracle import traj_oracle as T
