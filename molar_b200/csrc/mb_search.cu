@@ -35,7 +35,7 @@ constexpr unsigned DROPPED = 0xFFFFFFFFu;
 constexpr int MAX_REACH = 7;
 constexpr int MAX_ROWS = (2 * MAX_REACH + 1) * (2 * MAX_REACH + 1);
 #ifndef MB_STAGE_CAP
-#define MB_STAGE_CAP 512
+#define MB_STAGE_CAP 768
 #endif
 constexpr int STAGE_CAP = MB_STAGE_CAP;  // pairs staged per warp before a flush (>= 8 homes x 64 candidates of a dense pass)
 constexpr int STAGE_ROOM = STAGE_CAP + 2;  // entries allocated per warp: a carried-over odd pair + a full pass of STAGE_CAP (keeps 16-byte alignment)
@@ -43,7 +43,7 @@ constexpr int STAGE_ROOM = STAGE_CAP + 2;  // entries allocated per warp: a carr
 #define MB_SEARCH_WARPS 8
 #endif
 #ifndef MB_SEARCH_MIN_CTAS
-#define MB_SEARCH_MIN_CTAS 4
+#define MB_SEARCH_MIN_CTAS 3
 #endif
 #ifndef MB_SEARCH_PIPELINE
 #define MB_SEARCH_PIPELINE 0
@@ -369,7 +369,7 @@ template <int MODE>
 __device__ __forceinline__ void warp_flush(unsigned stage_sa, unsigned staged_sa, unsigned home_sa, int& stage_n,
                                            const SearchParams& P, unsigned lane) {
     constexpr bool DIST = MODE == 1;
-    static_assert(STAGE_CAP % 128 == 0 && STAGE_CAP >= 512, "flush rounds of 128 entries; the 4-pass expansion needs 512");
+    static_assert(STAGE_CAP % 128 == 0 && STAGE_CAP >= 512, "a pass of 8 homes x 64 (or 4 x 128) candidates must fit; MODE 1 flushes rounds of 128");
     __syncwarp();
     if (stage_n == 0) return;
     const int n = stage_n;
@@ -823,6 +823,24 @@ __device__ __forceinline__ void emit_group(unsigned e0, unsigned e1, unsigned id
         : "r"(e0), "r"(e1), "r"(id0), "r"(id1), "r"(h.x), "r"(h.y), "r"(h.z), "r"(h.w)
         : "memory");
 }
+// Same for a fused double step (four candidates per lane): a lane's entries are home-major, candidates 0..3 within a home.
+#define MB_EMIT_Q(J, SH, H)                                                                        \
+    MB_EMIT_ONE(J, "%1", "%5", H) SH MB_EMIT_ONE(J, "%2", "%6", H) SH MB_EMIT_ONE(J, "%3", "%7", H) SH \
+        MB_EMIT_ONE(J, "%4", "%8", H) SH
+__device__ __forceinline__ void emit_group4(unsigned e0, unsigned e1, unsigned e2, unsigned e3, unsigned id0, unsigned id1,
+                                            unsigned id2, unsigned id3, unsigned& sp, uint4 h) {
+    asm volatile(
+        "{ .reg .pred p; .reg .b32 t;\n"
+        MB_EMIT_Q(1, "  shl.b32 t, t, 3;\n  add.u32 %0, %0, t;\n", "%9")
+        MB_EMIT_Q(2, "  shl.b32 t, t, 2;\n  add.u32 %0, %0, t;\n", "%10")
+        MB_EMIT_Q(4, "  shl.b32 t, t, 1;\n  add.u32 %0, %0, t;\n", "%11")
+        MB_EMIT_Q(8, "  add.u32 %0, %0, t;\n", "%12")
+        "}"
+        : "+r"(sp)
+        : "r"(e0), "r"(e1), "r"(e2), "r"(e3), "r"(id0), "r"(id1), "r"(id2), "r"(id3), "r"(h.x), "r"(h.y), "r"(h.z), "r"(h.w)
+        : "memory");
+}
+#undef MB_EMIT_Q
 #undef MB_EMIT_ONE
 __device__ __forceinline__ uint4 lds128u(unsigned addr) {
     uint4 v;
@@ -938,6 +956,128 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32, MB_SEARCH_MIN_CTAS) search_
 #endif
 #pragma unroll 1
                 for (unsigned c0 = 0; c0 < T; c0 += 64) {
+                    // ---- fused double step (pairs-only and count-only kernels): 128 candidates, four per lane, when
+                    // neither half has a wrapped candidate.  One LDS.128 per home atom serves 128 tests, and the cursor,
+                    // the step flags, the prefix scan and the emission loop's own overhead are paid once per 128
+                    // candidates.  Mixed steps, steps with a test inside the band and the last odd step of a stream take
+                    // the single-step path below.
+                    if ((MODE == 0 || MODE == 2) && !VDW && use_bits && c0 + 64 < T) {
+                        const unsigned rb_save = runs_before;
+                        float4 q0, q1, q2, q3;
+                        unsigned g0, g1, g2, g3, i0, i1, i2, i3;
+                        fetch(c0, q0, q1, g0, g1, i0, i1);
+                        fetch(c0 + 64, q2, q3, g2, g3, i2, i3);
+                        const unsigned fl = __reduce_or_sync(0xffffffffu, (g0 | g1 | g2 | g3) & (7u | RUN_SELF));
+                        bool fused = (fl & 7u) == 0u;
+                        unsigned m0 = 0, m1 = 0, m2 = 0, m3 = 0;
+                        if (fused) {
+                            asm volatile("prefetch.global.L1 [%0];" ::"l"(P.sortedB + i0 + 128));
+                            asm volatile("prefetch.global.L1 [%0];" ::"l"(P.sortedB + i1 + 128));
+                            asm volatile("prefetch.global.L1 [%0];" ::"l"(P.sortedB + i2 + 128));
+                            asm volatile("prefetch.global.L1 [%0];" ::"l"(P.sortedB + i3 + 128));
+                            const unsigned long long zz2 = pk2(0.f, 0.f);
+                            const unsigned long long nxa = add2(pk2(q0.x, q1.x), zz2), nya = add2(pk2(q0.y, q1.y), zz2),
+                                                     nza = add2(pk2(q0.z, q1.z), zz2);
+                            const unsigned long long nxb = add2(pk2(q2.x, q3.x), zz2), nyb = add2(pk2(q2.y, q3.y), zz2),
+                                                     nzb = add2(pk2(q2.z, q3.z), zz2);
+                            const unsigned long long nrc22 = pk2_once(-rc2, -rc2);
+                            float tmin = 3.0e38f;
+                            const int nh4 = (nh + 3) & ~3;
+#pragma unroll 1
+                            for (int gj = nh4 - 4; gj >= 0; gj -= 4) {
+#pragma unroll
+                                for (int jj = 3; jj >= 0; --jj) {
+                                    const float4 h = home[gj + jj];
+                                    float t0, t1, t2, t3;
+                                    upk2(d2f_minus_rc2(nxa, nya, nza, h, nrc22), t0, t1);
+                                    upk2(d2f_minus_rc2(nxb, nyb, nzb, h, nrc22), t2, t3);
+                                    m0 = __funnelshift_l(__float_as_uint(t0), m0, 1);
+                                    m1 = __funnelshift_l(__float_as_uint(t1), m1, 1);
+                                    m2 = __funnelshift_l(__float_as_uint(t2), m2, 1);
+                                    m3 = __funnelshift_l(__float_as_uint(t3), m3, 1);
+                                    tmin = min3abs(min3abs(tmin, t0, t1), t2, t3);
+                                }
+                            }
+                            fused = !__any_sync(0xffffffffu, tmin <= P.band);
+                        }
+                        if (fused) {
+                            m0 &= valid_slots;  // sign set = within
+                            m1 &= valid_slots;
+                            m2 &= valid_slots;
+                            m3 &= valid_slots;
+                            if (fl & RUN_SELF) {
+                                // home cell against itself: keep (home j, atom a) only for a > hb + j
+                                auto self_mask = [&](unsigned g, unsigned ai) {
+                                    if (!(g & RUN_SELF)) return 0xffffffffu;
+                                    const int lim = min(max((int)ai - (int)hb, 0), 32);
+                                    return lim >= 32 ? 0xffffffffu : ((1u << lim) - 1u);
+                                };
+                                m0 &= self_mask(g0, i0);
+                                m1 &= self_mask(g1, i1);
+                                m2 &= self_mask(g2, i2);
+                                m3 &= self_mask(g3, i3);
+                            }
+                            const int cnt = __popc(m0) + __popc(m1) + __popc(m2) + __popc(m3);
+                            c0 += 64;  // the loop's own increment adds the other half
+                            if (MODE == 2) {
+                                count += cnt;
+                                ntests += 4u * (unsigned)((nh + 3) & ~3);
+                                continue;
+                            }
+                            int inc = cnt;
+                            scan_step(inc, 1);
+                            scan_step(inc, 2);
+                            scan_step(inc, 4);
+                            scan_step(inc, 8);
+                            scan_step(inc, 16);
+                            const int tot = __shfl_sync(0xffffffffu, inc, 31);
+                            if (tot == 0) continue;
+                            const unsigned id0 = __float_as_uint(q0.w), id1 = __float_as_uint(q1.w),
+                                           id2 = __float_as_uint(q2.w), id3 = __float_as_uint(q3.w);
+                            // one pass over all homes, or passes of four homes (<= 4 x 128 entries) for a dense step
+                            const bool single = tot <= STAGE_CAP;
+                            const int hstep = single ? 32 : 4;
+#pragma unroll 1
+                            for (int h0 = 0; h0 < nh; h0 += hstep) {
+                                unsigned e0 = m0, e1 = m1, e2 = m2, e3 = m3;
+                                int off = inc - cnt, need = tot;
+                                if (!single) {
+                                    e0 = (m0 >> h0) & 0xfu;
+                                    e1 = (m1 >> h0) & 0xfu;
+                                    e2 = (m2 >> h0) & 0xfu;
+                                    e3 = (m3 >> h0) & 0xfu;
+                                    int v = __popc(e0) + __popc(e1) + __popc(e2) + __popc(e3), vi = v;
+                                    scan_step(vi, 1);
+                                    scan_step(vi, 2);
+                                    scan_step(vi, 4);
+                                    scan_step(vi, 8);
+                                    scan_step(vi, 16);
+                                    need = __shfl_sync(0xffffffffu, vi, 31);
+                                    off = vi - v;
+                                    if (need == 0) continue;
+                                }
+                                if (stage_n + need > STAGE_CAP + 1) stage_n = warp_flush_bulk(stage_sa, stage_n, P, lane);
+                                unsigned sp = stage_sa + 8u * (unsigned)(stage_n + off);
+                                unsigned ha = hid_sa + 4u * (unsigned)h0;
+                                const int hend = min(nh, h0 + hstep);
+                                uint4 hqa = lds128u(ha), hqb = lds128u(ha + 16u);
+#pragma unroll 1
+                                for (int gj = h0; gj < hend; gj += 8) {
+                                    emit_group4(e0, e1, e2, e3, id0, id1, id2, id3, sp, hqa);
+                                    hqa = lds128u(ha + 32u);
+                                    e0 >>= 4; e1 >>= 4; e2 >>= 4; e3 >>= 4;
+                                    if (gj + 4 >= hend) break;
+                                    emit_group4(e0, e1, e2, e3, id0, id1, id2, id3, sp, hqb);
+                                    hqb = lds128u(ha + 48u);
+                                    e0 >>= 4; e1 >>= 4; e2 >>= 4; e3 >>= 4;
+                                    ha += 32u;
+                                }
+                                stage_n += need;
+                            }
+                            continue;
+                        }
+                        runs_before = rb_save;  // not fused: the single-step path fetches its 64 candidates again
+                    }
                     const unsigned p0 = c0 + lane, p1 = p0 + 32;
                     float4 n0, n1;
                     unsigned f0, f1, a0i, a1i;

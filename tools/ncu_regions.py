@@ -20,11 +20,16 @@ marks = [
     ('kernel prologue / tile', line_of('search_cells_kernel(const __grid_constant__ SearchParams P)')),
     ('home batch load', line_of('for (unsigned hb = hs; hb < he; hb += 32)')),
     ('cursor / fetch', line_of('auto fetch = [&]')),
-    ('step flags / pack', line_of('unsigned m0 = 0, m1 = 0;')),
+    ('fused: fetch + flags', line_of('// ---- fused double step')),
+    ('fused: tests', line_of('const unsigned long long nrc22 = pk2_once(-rc2, -rc2);', line_of('// ---- fused double step'))),
+    ('fused: masks / scan / setup', line_of('fused = !__any_sync(0xffffffffu, tmin <= P.band);')),
+    ('fused: emission loop', line_of('uint4 hqa = lds128u(ha), hqb = lds128u(ha + 16u);', line_of('// ---- fused double step'))),
+    ('single step: fetch', line_of('runs_before = rb_save;')),
+    ('step flags / pack', line_of('unsigned m0 = 0, m1 = 0;', line_of('runs_before = rb_save;'))),
     ('direct tests', line_of('} else if (!any_wrapped) {')),
     ('mixed tests', line_of('// ---- mixed step: wrapped cell pairs')),
-    ('count / scan / pass setup', line_of('if (MODE == 3) {\n'.split('\n')[0], line_of('// ---- mixed step'))),
-    ('emission loop', line_of('if (MODE == 0) {', line_of('const int npass'))),
+    ('count / scan (single step)', line_of('if (MODE == 3) {', line_of('// ---- mixed step'))),
+    ('emission (single step)', line_of('const bool single = tot <= STAGE_CAP;', line_of('// inclusive scan of the hits per lane'))),
     ('after emission', line_of('stage_n += need;')),
     ('end', line_of('// general all-pairs kernel')),
 ]
