@@ -25,6 +25,7 @@
  *   mb_principal_transform  Measure::principal_transform[_pbc]            measure.rs:100-108,240-252,645-649
  *   mb_batch_*            the per-frame loop AnalysisTask::run drives     analysis_task.rs:113-280
  *   mb_connectivity       SearchConnectivity::from_iter                   connectivity.rs:8-38
+ *   mb_search_connectivity  the same, rows written by the search kernel    connectivity.rs:8-38, distance_search.rs:892-954
  *   mb_unwrap_connectivity  Modify::unwrap_connectivity[_dim]             modify.rs:64-131
  *   mb_batch_load_traj    DcdFileHandler::read_state / XtcFileHandler::read_state (+ molly's XTC codec)
  *                                                                         io/dcd_handler.rs:204-300,389-464; io/xtc_handler.rs:64-110
@@ -180,6 +181,14 @@ int mb_principal_transform(MbCtx* ctx, const uint64_t* ids, size_t n, int pbc, d
  * space [0, n_index): returns the number of entries (2 x pairs); row_ptr_out (n_index + 1 entries) may be NULL;
  * the neighbour lists follow with mb_fill_connectivity.  Order inside a row is unspecified (as in the reference). */
 int64_t mb_connectivity(MbCtx* ctx, size_t n_index, uint64_t* row_ptr_out);
+/* The same adjacency WITHOUT a pair list in between: SearchConnectivity::from_iter(distance_search_single[_pbc](cutoff,
+ * sel)) (connectivity.rs:8-38 over distance_search.rs:892-954) as CSR over [0, n_atoms).  The search kernel walks the full
+ * neighbour shell twice (count per atom, then every atom's row written at its own cursor), so no per-pair atomics and no
+ * 8-byte pair ever reaches memory; small or degenerate grids fall back to pair list -> CSR.  Returns the number of
+ * entries (2 x pairs); row_ptr_out (n_atoms + 1 entries) may be NULL; rows follow with mb_fill_connectivity.  The
+ * context holds no pair list afterwards (mb_fill_pairs fails with MB_ERR_STATE). */
+int64_t mb_search_connectivity(MbCtx* ctx, float cutoff, const uint64_t* ids, size_t n, uint8_t pbc_dims,
+                               uint64_t* row_ptr_out);
 int mb_fill_connectivity(MbCtx* ctx, uint64_t* cols_out);
 /* unwrap_connectivity_dim: contact graph of the selection at `cutoff` (periodic in all dims), every atom moved to
  * its closest image (image_dims) next to the atom it is reached from, walking from the lowest-index atom of each

@@ -228,6 +228,19 @@ class Sel:
                                        ax.ctypes.data_as(f64p)))
         return mom, ax.reshape(3, 3).T.copy()
 
+    def search_connectivity(self, cutoff, dims=None):
+        """SearchConnectivity of distance_search_single[_pbc](cutoff, self) (connectivity.rs:8-38 over
+        distance_search.rs:892-954) as CSR (row_ptr[n_atoms + 1], cols), the rows written by the search kernel itself:
+        no pair list in between.  dims=None: non-periodic."""
+        bits = 0 if dims is None else _pbc_bits(dims)
+        p, n = self._ids()
+        row_ptr = np.zeros(self.sys._n + 1, np.uint64)
+        nnz = check(self.sys._lib.mb_search_connectivity(self.sys._h, cutoff, p, n, bits, row_ptr.ctypes.data_as(u64p)))
+        cols = np.zeros(nnz, np.uint64)
+        if nnz:
+            check(self.sys._lib.mb_fill_connectivity(self.sys._h, cols.ctypes.data_as(u64p)))
+        return row_ptr, cols
+
     def inertia_pbc(self):
         return self.inertia(pbc=True)
 

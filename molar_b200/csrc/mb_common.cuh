@@ -272,6 +272,9 @@ int batch_search_impl(Ctx* c, float cutoff, uint8_t pbc, size_t f0, size_t f1, i
                       uint64_t* checksums2);
 int enqueue_count_frame(Ctx* c, const float* xyz, size_t n, float cutoff, uint8_t pbc,
                         unsigned long long* d_counter2);
+// neighbour list of one selection as CSR rows written by the search kernel itself (mb_search.cu)
+int neighbor_rows_cells(Ctx* c, float cutoff, const uint64_t* ids, size_t n, uint8_t pbc, size_t n_index,
+                        size_t extra_bytes, bool* done);
 void free_plan_cache(Ctx* c);
 void comm_destroy(Ctx* c);  // mb_comm.cu
 // exclusive scan of n u32 on the context stream, out[n] = total (mb_search.cu)

@@ -86,6 +86,31 @@ __global__ void __launch_bounds__(256) uf_unite_kernel(const uint2* __restrict__
         }
     }
 }
+// same over CSR rows (one warp per row; every edge is stored in both rows: the higher end unites)
+__global__ void __launch_bounds__(256) uf_unite_rows_kernel(const unsigned* __restrict__ row_ptr,
+                                                            const unsigned* __restrict__ cols, unsigned n, unsigned* parent) {
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned nw = (gridDim.x * blockDim.x) >> 5;
+    for (unsigned i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += nw) {
+        const unsigned e1 = row_ptr[i + 1];
+        for (unsigned e = row_ptr[i] + lane; e < e1; e += 32) {
+            const unsigned j = cols[e];
+            if (j >= i) continue;
+            unsigned a = uf_find(parent, i), b = uf_find(parent, j);
+            while (a != b) {
+                if (a < b) {
+                    const unsigned t = a;
+                    a = b;
+                    b = t;
+                }
+                const unsigned old = atomicCAS(&parent[a], a, b);
+                if (old == a) break;
+                a = uf_find(parent, old);
+                b = uf_find(parent, b);
+            }
+        }
+    }
+}
 __global__ void uf_flatten_kernel(unsigned* parent, unsigned n) {
     unsigned k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k < n) {
@@ -248,6 +273,38 @@ int64_t mb_connectivity(MbCtx* h, size_t n_index, uint64_t* row_ptr_out) {
     return (int64_t)nnz;
 }
 
+int64_t mb_search_connectivity(MbCtx* h, float cutoff, const uint64_t* ids, size_t n, uint8_t pbc_dims,
+                               uint64_t* row_ptr_out) {
+    if (!h) return fail(MB_ERR_ARG, "null context");
+    Ctx* c = &h->c;
+    const size_t N = c->n_atoms;
+    bool rows_done = false;
+    MB_TRY(neighbor_rows_cells(c, cutoff, ids, n, pbc_dims & 7u, N, 0, &rows_done));
+    unsigned *rp = nullptr, *cols = nullptr;
+    size_t nnz = 0;
+    if (rows_done) {
+        rp = c->conn_tmp.as<unsigned>() + (N + 2);
+        nnz = c->conn_nnz;
+    } else {
+        // small or degenerate grids: pair list of the general path -> CSR
+        const int keep_dist = c->opt_with_dist;
+        c->opt_with_dist = 0;
+        int64_t np = 0;
+        int rc = search_single_impl(c, cutoff, ids, n, pbc_dims & 7u, 0, &np);
+        c->opt_with_dist = keep_dist;
+        if (rc < 0) return rc;
+        MB_TRY(build_csr(c, N, &rp, &cols, &nnz));
+    }
+    if (row_ptr_out) {
+        MB_TRY(c->out_ids.reserve((N + 1) * sizeof(unsigned long long)));
+        widen_u32_kernel<<<(unsigned)((N + 1 + 255) / 256), 256, 0, c->stream>>>(rp, N + 1, c->out_ids.as<unsigned long long>());
+        c->launches++;
+        MB_CUDA(cudaMemcpyAsync(row_ptr_out, c->out_ids.p, (N + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+    }
+    MB_CUDA(cudaStreamSynchronize(c->stream));
+    return (int64_t)nnz;
+}
+
 int mb_fill_connectivity(MbCtx* h, uint64_t* cols_out) {
     if (!h || !cols_out) return fail(MB_ERR_ARG, "null argument");
     Ctx* c = &h->c;
@@ -270,20 +327,30 @@ int64_t mb_unwrap_connectivity(MbCtx* h, float cutoff, const uint64_t* ids, size
     if (!c->d_xyz) return fail(MB_ERR_STATE, "no frame set");
     if (!c->has_box) return fail(MB_ERR_NO_PBC, "unwrap_connectivity: the frame has no periodic box");
     MB_CUDA(cudaSetDevice(c->device));
-    // contact graph: distance_search_single_pbc(cutoff, ..., PBC_FULL)   (modify.rs:79-80)
-    const int keep_dist = c->opt_with_dist;
-    c->opt_with_dist = 0;
-    int64_t np = 0;
-    int rc = search_single_impl(c, cutoff, ids, n, 7, 0, &np);
-    c->opt_with_dist = keep_dist;
-    if (rc < 0) return rc;
+    // contact graph: distance_search_single_pbc(cutoff, ..., PBC_FULL)   (modify.rs:79-80), as neighbour rows written
+    // by the search itself when the grid allows it, else pair list -> CSR
     const size_t N = c->n_atoms;
     // scratch after the CSR words: label[N] cand[N] frontier0[N] frontier1[N] count[8] visited[N] member[N]
     const size_t csr_words = 2 * (N + 2);
-    MB_TRY(c->conn_tmp.reserve((csr_words + 4 * N + 8) * sizeof(unsigned) + 2 * N + 64));
+    const size_t extra_bytes = (4 * N + 8) * sizeof(unsigned) + 2 * N + 64;
+    bool rows_done = false;
+    MB_TRY(neighbor_rows_cells(c, cutoff, ids, n, 7, N, extra_bytes, &rows_done));
     unsigned *rp = nullptr, *cols = nullptr;
     size_t nnz = 0;
-    MB_TRY(build_csr(c, N, &rp, &cols, &nnz));
+    int64_t np = 0;
+    if (rows_done) {
+        rp = c->conn_tmp.as<unsigned>() + (N + 2);
+        cols = c->conn_cols.as<unsigned>();
+        nnz = c->conn_nnz;
+    } else {
+        const int keep_dist = c->opt_with_dist;
+        c->opt_with_dist = 0;
+        int rc = search_single_impl(c, cutoff, ids, n, 7, 0, &np);
+        c->opt_with_dist = keep_dist;
+        if (rc < 0) return rc;
+        MB_TRY(c->conn_tmp.reserve(csr_words * sizeof(unsigned) + extra_bytes));
+        MB_TRY(build_csr(c, N, &rp, &cols, &nnz));
+    }
     unsigned* base = c->conn_tmp.as<unsigned>() + csr_words;
     unsigned* label = base;
     unsigned* cand = base + N;
@@ -294,9 +361,13 @@ int64_t mb_unwrap_connectivity(MbCtx* h, float cutoff, const uint64_t* ids, size
     unsigned char* member = visited + N;
     const unsigned nb = (unsigned)((N + 255) / 256);
     uf_init_kernel<<<nb, 256, 0, c->stream>>>(label, (unsigned)N);
-    const unsigned long long P = (unsigned long long)np;
-    const int pblocks = (int)std::max<unsigned long long>(1, std::min<unsigned long long>((P + 255) / 256, (unsigned long long)c->sm_count * 16));
-    if (P) uf_unite_kernel<<<pblocks, 256, 0, c->stream>>>(c->pairs.as<uint2>(), P, label);
+    if (rows_done) {
+        if (nnz) uf_unite_rows_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(rp, cols, (unsigned)N, label);
+    } else {
+        const unsigned long long P = (unsigned long long)np;
+        const int pblocks = (int)std::max<unsigned long long>(1, std::min<unsigned long long>((P + 255) / 256, (unsigned long long)c->sm_count * 16));
+        if (P) uf_unite_kernel<<<pblocks, 256, 0, c->stream>>>(c->pairs.as<uint2>(), P, label);
+    }
     uf_flatten_kernel<<<nb, 256, 0, c->stream>>>(label, (unsigned)N);
     MB_CUDA(cudaMemsetAsync(cand, 0xff, N * sizeof(unsigned), c->stream));
     MB_CUDA(cudaMemsetAsync(count, 0, 8 * sizeof(unsigned), c->stream));

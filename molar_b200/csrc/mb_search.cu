@@ -95,6 +95,10 @@ struct SearchParams {
     // id stored in .w of the records; NULL for a plain cutoff search
     const float* vdwA;
     const float* vdwB;
+    // neighbour-list modes (4: degrees, 5: rows): nl_deg[global id] = number of neighbours (MODE 4) / next free slot of
+    // the atom's row (MODE 5); nl_cols = the rows, back to back in id order
+    unsigned* nl_deg;
+    unsigned* nl_cols;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -848,6 +852,77 @@ __device__ __forceinline__ uint4 lds128u(unsigned addr) {
     return v;
 }
 
+// ---- neighbour-list modes: per-home-atom hit counters kept BIT-SLICED in every lane ---------------------------------
+// Lane l looks at its own candidates; bit j of plane k is bit k of "how many of my candidates hit home slot j".  Adding
+// the (up to four) hit masks of a step is a carry-save compression to a 3-bit sliced number and one ripple through the
+// seven planes — about 18 LOP3 for 128 tests x 32 homes, independent of the number of home atoms.  Seven planes hold
+// 127: the planes are folded into the per-home totals (lane j keeps home j's) every 31 steps.
+constexpr int VC_PLANES = 7;
+constexpr unsigned VC_MAX_STEPS = 31;  // 31 steps x <= 4 hits per step and lane <= 127
+__device__ __forceinline__ void vcount_add(unsigned (&p)[VC_PLANES], unsigned b1, unsigned b2, unsigned b4) {
+    unsigned cy = p[0] & b1;
+    p[0] ^= b1;
+    unsigned t = p[1] ^ b2 ^ cy;
+    cy = (p[1] & b2) | (p[1] & cy) | (b2 & cy);
+    p[1] = t;
+    t = p[2] ^ b4 ^ cy;
+    cy = (p[2] & b4) | (p[2] & cy) | (b4 & cy);
+    p[2] = t;
+#pragma unroll
+    for (int k = 3; k < VC_PLANES; ++k) {
+        t = p[k] & cy;
+        p[k] ^= cy;
+        cy = t;
+    }
+}
+__device__ __forceinline__ void vcount_add4(unsigned (&p)[VC_PLANES], unsigned m0, unsigned m1, unsigned m2, unsigned m3) {
+    const unsigned s = m0 ^ m1 ^ m2, c = (m0 & m1) | (m0 & m2) | (m1 & m2);
+    const unsigned s2 = s ^ m3, c2 = s & m3;
+    vcount_add(p, s2, c ^ c2, c & c2);
+}
+__device__ __forceinline__ void vcount_fold(unsigned (&p)[VC_PLANES], unsigned& deg, int nh, unsigned lane) {
+#pragma unroll 1
+    for (int j = 0; j < nh; ++j) {
+        unsigned v = 0;
+#pragma unroll
+        for (int k = 0; k < VC_PLANES; ++k) v |= ((p[k] >> j) & 1u) << k;
+        v = __reduce_add_sync(0xffffffffu, v);
+        if (lane == (unsigned)j) deg += v;
+    }
+#pragma unroll
+    for (int k = 0; k < VC_PLANES; ++k) p[k] = 0u;
+}
+// the bit of home slot (candidate index - first home index) when the candidate IS one of the home atoms
+__device__ __forceinline__ unsigned self_slot_bit(unsigned cand_index, unsigned hb) {
+    const unsigned d = cand_index - hb;
+    return d < 32u ? (1u << d) : 0u;
+}
+// MODE 5: the hits of home slot j (one ballot per candidate quarter) go to the atom's row at the running cursor, in
+// lane order; lane j owns the cursor of home slot j
+template <int NQ>
+__device__ __forceinline__ void rows_emit(const unsigned (&m)[NQ], const unsigned (&id)[NQ], unsigned& cur, unsigned lane,
+                                          unsigned* __restrict__ cols) {
+    unsigned any = m[0];
+#pragma unroll
+    for (int q = 1; q < NQ; ++q) any |= m[q];
+    any = __reduce_or_sync(0xffffffffu, any);
+    const unsigned lt = (1u << lane) - 1u;
+#pragma unroll 1
+    while (any) {
+        const int j = __ffs(any) - 1;
+        any &= any - 1u;
+        unsigned base = __shfl_sync(0xffffffffu, cur, j);
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            const bool hit = (m[q] >> j) & 1u;
+            const unsigned b = __ballot_sync(0xffffffffu, hit);
+            if (hit) cols[base + __popc(b & lt)] = id[q];
+            base += __popc(b);
+        }
+        if (lane == (unsigned)j) cur = base;
+    }
+}
+
 // One warp per home tile = hx consecutive fine cells along x (dynamic work counter).
 //  Phase A  lanes work on different neighbour rows in parallel and build a table of runs: contiguous
 //           ranges of the sorted atom array (self cell, then direct runs, then wrapped runs).
@@ -855,7 +930,8 @@ __device__ __forceinline__ uint4 lds128u(unsigned addr) {
 //           per step (two per lane, two coalesced float4 loads), tested against the home atoms that
 //           are broadcast from shared memory (one LDS.128 per home atom), hits are kept as per-lane
 //           bit masks and expanded into the staging buffer afterwards.
-// MODE: 0 pairs, 1 pairs + distances, 2 count only, 3 `within` flags (two sets)
+// MODE: 0 pairs, 1 pairs + distances, 2 count only, 3 `within` flags (two sets), 4 / 5 neighbour list of ONE set over the
+// full shell (two_sets = 1 with sortedB == sorted): 4 counts the neighbours of every atom, 5 writes the rows
 //
 // Staging entries.  MODE 1: (home slot j, candidate id).  MODE 0: (remaining hit bits of the candidate, candidate id):
 // the home slot is the LOWEST set bit, decoded in the flush 32 entries per instruction — the expansion loop then
@@ -880,6 +956,8 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32, MB_SEARCH_MIN_CTAS) search_
     int stage_n = 0;
     unsigned long long count = 0;
     unsigned ntests = 0;  // MODE 2: distance tests this lane evaluated (FP32-pipe roofline of the count-only search)
+    unsigned vplane[VC_PLANES] = {0u, 0u, 0u, 0u, 0u, 0u, 0u};  // MODE 4: bit-sliced hit counters of the home batch
+    unsigned vsteps = 0;
     const GridSpec& g = P.g;
     const int fdx = g.fd[0], fdy = g.fd[1], fdz = g.fd[2];
     const int hx = g.hx, tdx = fdx / hx;  // tiles per x-row
@@ -930,6 +1008,12 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32, MB_SEARCH_MIN_CTAS) search_
                 unsigned cur0 = 0, cur1 = 0;
                 unsigned runs_before = 0;  // run starts at stream positions < c0 (bitmap path)
                 unsigned hit_any = 0;      // MODE 3: bit j = home atom j has a set-2 atom within the cutoff
+                // MODE 4: neighbours of home atom `lane` found in this visit; MODE 5: next free slot of its row (a batch
+                // can be visited again when the run table overflowed: the cursor lives in global memory in between;
+                // only this lane ever touches it)
+                unsigned nl_val = 0;
+                const unsigned nl_gid = __float_as_uint(ws.home[lane].w);
+                if (MODE == 5 && lane < (unsigned)nh) nl_val = __ldcg(P.nl_deg + nl_gid);
                 // Candidates of stream positions [c, c + 64): run index of a position = (run starts at positions <= it)
                 // - 1: two broadcast words and a popcount instead of a per-lane search.  Positions >= T fall into the
                 // sentinel run, whose records are the far-away padding behind the sorted array: no bounds checks.
@@ -961,7 +1045,7 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32, MB_SEARCH_MIN_CTAS) search_
                     // the step flags, the prefix scan and the emission loop's own overhead are paid once per 128
                     // candidates.  Mixed steps, steps with a test inside the band and the last odd step of a stream take
                     // the single-step path below.
-                    if ((MODE == 0 || MODE == 2) && !VDW && use_bits && c0 + 64 < T) {
+                    if ((MODE == 0 || MODE == 2 || MODE >= 4) && !VDW && use_bits && c0 + 64 < T) {
                         const unsigned rb_save = runs_before;
                         float4 q0, q1, q2, q3;
                         unsigned g0, g1, g2, g3, i0, i1, i2, i3;
@@ -1016,6 +1100,28 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32, MB_SEARCH_MIN_CTAS) search_
                                 m1 &= self_mask(g1, i1);
                                 m2 &= self_mask(g2, i2);
                                 m3 &= self_mask(g3, i3);
+                            }
+                            if (MODE >= 4) {
+                                // the candidate stream of the full shell contains the home atoms themselves
+                                m0 &= ~self_slot_bit(i0, hb);
+                                m1 &= ~self_slot_bit(i1, hb);
+                                m2 &= ~self_slot_bit(i2, hb);
+                                m3 &= ~self_slot_bit(i3, hb);
+                                c0 += 64;
+                                if (MODE == 4) {
+                                    if (vsteps == VC_MAX_STEPS) {
+                                        vcount_fold(vplane, nl_val, nh, lane);
+                                        vsteps = 0;
+                                    }
+                                    vcount_add4(vplane, m0, m1, m2, m3);
+                                    ++vsteps;
+                                } else {
+                                    const unsigned mm[4] = {m0, m1, m2, m3};
+                                    const unsigned ii[4] = {__float_as_uint(q0.w), __float_as_uint(q1.w),
+                                                            __float_as_uint(q2.w), __float_as_uint(q3.w)};
+                                    rows_emit<4>(mm, ii, nl_val, lane, P.nl_cols);
+                                }
+                                continue;
                             }
                             const int cnt = __popc(m0) + __popc(m1) + __popc(m2) + __popc(m3);
                             c0 += 64;  // the loop's own increment adds the other half
@@ -1286,6 +1392,23 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32, MB_SEARCH_MIN_CTAS) search_
                         hit_any |= m0 | m1;
                         continue;
                     }
+                    if (MODE >= 4) {
+                        m0 &= ~self_slot_bit(a0i, hb);
+                        m1 &= ~self_slot_bit(a1i, hb);
+                        if (MODE == 4) {
+                            if (vsteps == VC_MAX_STEPS) {
+                                vcount_fold(vplane, nl_val, nh, lane);
+                                vsteps = 0;
+                            }
+                            vcount_add(vplane, m0 ^ m1, m0 & m1, 0u);
+                            ++vsteps;
+                        } else {
+                            const unsigned mm[2] = {m0, m1};
+                            const unsigned ii[2] = {__float_as_uint(n0.w), __float_as_uint(n1.w)};
+                            rows_emit<2>(mm, ii, nl_val, lane, P.nl_cols);
+                        }
+                        continue;
+                    }
                     const int c0n = __popc(m0), c1n = __popc(m1);
                     if (MODE == 2) {
                         count += c0n + c1n;
@@ -1408,6 +1531,13 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32, MB_SEARCH_MIN_CTAS) search_
                     hit_any = __reduce_or_sync(0xffffffffu, hit_any);
                     if (lane < (unsigned)nh && ((hit_any >> lane) & 1u)) P.flags[__float_as_uint(home[lane].w)] = 1;
                 }
+                if (MODE == 4) {
+                    vcount_fold(vplane, nl_val, nh, lane);
+                    vsteps = 0;
+                    if (lane < (unsigned)nh && nl_val) atomicAdd(P.nl_deg + nl_gid, nl_val);
+                    count += nl_val;  // u64 total: the host checks it against the 32-bit row offsets
+                }
+                if (MODE == 5 && lane < (unsigned)nh) __stcg(P.nl_deg + nl_gid, nl_val);
                 // MODE 1: staged entries name home atoms by their slot in ws.home: write them out before it changes
                 if (MODE == 1) warp_flush<MODE>(stage_sa, staged_sa, home_sa, stage_n, P, lane);
             }
@@ -1425,7 +1555,7 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32, MB_SEARCH_MIN_CTAS) search_
             asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
         }
     }
-    if (MODE == 2) {
+    if (MODE == 2 || MODE == 4) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) count += __shfl_xor_sync(0xffffffffu, count, o);
         if (lane == 0 && count) atomicAdd(P.counter, count);
@@ -2360,6 +2490,105 @@ int search_single_impl(Ctx* c, float cutoff, const uint64_t* ids, size_t n, uint
     c->last.has_dist = with_dist;
     for (int d = 0; d < 3; ++d) c->last.grid_dims[d] = pl.g.dims[d];
     *count_out = (int64_t)found;
+    return MB_OK;
+}
+
+// Neighbour list of ONE selection written by the search itself (SearchConnectivity, connectivity.rs:8-38, without a
+// pair list in between): the cell kernel runs over the full neighbour shell twice — MODE 4 counts the neighbours of
+// every atom (bit-sliced per-lane counters, one atomic per home atom and visit), an exclusive scan turns the counts into
+// row starts, MODE 5 writes every atom's row at its own cursor (the rows of a home tile belong to one warp: no atomics).
+// Layout in c->conn_tmp: deg / cursors [n_index + 2] | row_ptr [n_index + 2] | extra_bytes of caller scratch; rows in
+// c->conn_cols.  *done = false (nothing computed) when the grid is not one the cell kernel handles.
+int neighbor_rows_cells(Ctx* c, float cutoff, const uint64_t* ids, size_t n, uint8_t pbc, size_t n_index,
+                        size_t extra_bytes, bool* done) {
+    *done = false;
+    if (!c->d_xyz) return fail(MB_ERR_STATE, "no frame set");
+    if (!(cutoff > 0.0f)) return fail(MB_ERR_ARG, "cutoff must be positive");
+    if (n_index < c->n_atoms || n_index > 0x7fffffffull) return fail(MB_ERR_ARG, "connectivity: bad index space");
+    MB_CUDA(cudaSetDevice(c->device));
+    MB_TRY(check_sel(c, ids, n, c->n_atoms, "search_connectivity"));
+    if (n > 0x7fffffffull) return fail(MB_ERR_ARG, "selection too large");
+    const unsigned long long* d_ids;
+    MB_TRY(upload_ids(c, c->ids1, ids, n, &d_ids));
+    MB_TRY(c->counters.reserve(256));
+    unsigned long long* d_counter = c->counters.as<unsigned long long>();
+    Plan pl;
+    memset(&pl, 0, sizeof(pl));
+    if (pbc) {
+        MB_TRY(get_plan_pbc(c, cutoff, pbc, n, pl, true));
+    } else {
+        float lo[3], hi[3];
+        MB_TRY(device_minmax(c, c->d_xyz, d_ids, n, 0.0f, 0.0f, lo, hi));  // compute_min_max starts at 0 (:603-604)
+        pad_bounds(cutoff, lo, hi);
+        make_grid_bounds(cutoff, lo, hi, pl.g);
+        pl.full_shell = true;
+        plan_cells(c, pl, cutoff, n);
+    }
+    if (!pl.use_cells) return MB_OK;
+    const GridSpec& g = pl.g;
+    MB_TRY(c->cell_count.reserve((pl.ncells + 1) * sizeof(unsigned)));
+    MB_TRY(c->cell_start.reserve((pl.ncells + 2) * sizeof(unsigned)));
+    MB_TRY(c->sorted4.reserve((n + PAD_CANDS) * sizeof(float4)));
+    const size_t words = 2 * (n_index + 2);
+    MB_TRY(c->conn_tmp.reserve(words * sizeof(unsigned) + extra_bytes));
+    unsigned* deg = c->conn_tmp.as<unsigned>();
+    unsigned* rp = deg + (n_index + 2);
+    MB_CUDA(cudaMemsetAsync(c->cell_count.p, 0, (pl.ncells + 1) * sizeof(unsigned), c->stream));
+    MB_CUDA(cudaMemsetAsync(d_counter, 0, CNT_STRIDE * sizeof(unsigned long long), c->stream));
+    MB_CUDA(cudaMemsetAsync(deg, 0, (n_index + 2) * sizeof(unsigned), c->stream));
+    MB_TRY(bin_set(c, c->d_xyz, d_ids, n, g, c->tmp4a, c->cellid_a, &c->rank_a, c->cell_count.as<unsigned>(), nullptr));
+    MB_TRY(exclusive_scan_u32(c, c->cell_count.as<unsigned>(), (int)pl.ncells, c->cell_start.as<unsigned>()));
+    scatter_kernel<<<(int)((n + 255) / 256), 256, 0, c->stream>>>(c->tmp4a.as<float4>(), c->cellid_a.as<unsigned>(),
+                                                                 c->rank_a.as<unsigned>(), c->cell_start.as<unsigned>(),
+                                                                 (int)n, c->sorted4.as<float4>());
+    c->launches++;
+    SearchParams P;
+    memset(&P, 0, sizeof(P));
+    P.sorted = c->sorted4.as<float4>();
+    P.cell_start = c->cell_start.as<unsigned>();
+    P.sortedB = P.sorted;
+    P.cell_startB = P.cell_start;
+    P.two_sets = 1;  // full shell, no self run: the home atoms meet themselves in the stream and are masked out there
+    P.g = g;
+    P.rc2 = cutoff * cutoff;
+    P.band = 16.0f * 5.9604645e-8f * P.rc2;
+    P.one = 1.0f;
+    P.rc2_lo = pl.rc2_lo;
+    P.rc2_hi = pl.rc2_hi;
+    P.fast_pbc = pl.fast_pbc;
+    P.nrows = pl.nrows;
+    memcpy(P.rows, pl.rows, sizeof(NbrRow) * pl.nrows);
+    P.dx_min = 127;
+    P.dx_max = -128;
+    for (int r = 0; r < pl.nrows; ++r) {
+        P.dx_min = std::min(P.dx_min, (int)pl.rows[r].dxlo);
+        P.dx_max = std::max(P.dx_max, (int)pl.rows[r].dxhi);
+    }
+    P.counter = d_counter;
+    P.n_sortedB = n;
+    P.nl_deg = deg;
+    MB_TRY(launch_search_cells<4>(c, P));
+    MB_TRY(exclusive_scan_u32(c, deg, (int)n_index, rp));
+    MB_CUDA(cudaMemcpyAsync(deg, rp, n_index * sizeof(unsigned), cudaMemcpyDeviceToDevice, c->stream));  // row cursors
+    unsigned total = 0;
+    unsigned long long total64 = 0;
+    MB_CUDA(cudaMemcpyAsync(&total, rp + n_index, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
+    MB_CUDA(cudaMemcpyAsync(&total64, d_counter, sizeof(total64), cudaMemcpyDeviceToHost, c->stream));
+    MB_CUDA(cudaMemsetAsync(d_counter, 0, CNT_STRIDE * sizeof(unsigned long long), c->stream));  // tile work counter
+    MB_CUDA(cudaStreamSynchronize(c->stream));
+    if (total64 > 0xfffffff0ull) return fail(MB_ERR_ARG, "connectivity: more than 2^32 entries");
+    if (total64 != total) return fail(MB_ERR_STATE, "connectivity: degree count and row offsets disagree");
+    MB_TRY(c->conn_cols.reserve(((size_t)total + 1) * sizeof(unsigned)));
+    P.nl_cols = c->conn_cols.as<unsigned>();
+    if (total) MB_TRY(launch_search_cells<5>(c, P));
+    c->harvest_profile();
+    c->conn_n = n_index;
+    c->conn_nnz = total;
+    c->last.kind = 4;  // no pair list on the context
+    c->last.count = (int64_t)(total / 2);
+    c->last.has_dist = false;
+    for (int d = 0; d < 3; ++d) c->last.grid_dims[d] = pl.g.dims[d];
+    *done = true;
     return MB_OK;
 }
 

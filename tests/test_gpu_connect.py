@@ -49,6 +49,54 @@ def test_connectivity_csr_vs_pair_list(mb):
     s.close()
 
 
+def _rows_from_pairs(pairs, n):
+    """SearchConnectivity::from_iter (connectivity.rs:19-35) of an (i, j) list: sorted (atom * n + neighbour) keys."""
+    p = np.asarray(pairs, dtype=np.int64).reshape(-1, 2)
+    return np.sort(np.concatenate([p[:, 0] * n + p[:, 1], p[:, 1] * n + p[:, 0]]))
+
+
+def _rows_from_csr(row_ptr, cols, n):
+    deg = np.diff(row_ptr.astype(np.int64))
+    assert deg.min() >= 0 and row_ptr[0] == 0 and row_ptr[-1] == len(cols)
+    return np.sort(np.repeat(np.arange(n), deg) * n + cols.astype(np.int64))
+
+
+TRIC_SMALL = np.array([[6.5, -0.8, -0.8], [0.0, 6.5, -0.8], [0.0, 0.0, 6.5]], np.float32)
+
+
+@pytest.mark.parametrize("case", ["ortho_pbc", "tric_pbc_strays", "partial_pbc", "nonperiodic", "selection", "small_fallback",
+                                  "dense_tiles"])
+def test_search_connectivity_vs_oracle_pairs(mb, case):
+    """Neighbour rows written by the search kernel (full shell, count pass + fill pass) == the adjacency the reference
+    builds from ITS pair list (connectivity.rs:8-38 over distance_search.rs:892-954), compared with the oracle's pairs."""
+    box, pbc, dims, n, cutoff, ids, stray = np.diag([6.0, 7.0, 8.0]).astype(np.float32), 7, [True] * 3, 30_000, 0.5, None, 0
+    if case == "tric_pbc_strays":
+        box, stray, cutoff = TRIC_SMALL, 10, 0.6
+    elif case == "partial_pbc":
+        pbc, dims, stray = 5, [True, False, True], 10
+    elif case == "nonperiodic":
+        pbc, dims = 0, None
+    elif case == "selection":
+        ids = np.sort(np.random.default_rng(5).choice(n, 20_000, replace=False)).astype(np.uint64)
+    elif case == "small_fallback":
+        n = 2_000
+    elif case == "dense_tiles":
+        # 60 atoms per home tile and long candidate streams: several home batches per tile, counter folds, batches
+        # visited again after a full run table
+        box, n, cutoff = np.diag([3.0, 3.0, 3.0]).astype(np.float32), 60_000, 0.45
+    xyz = orc.synth_frame(20260, 3, n, box, stray_permille=stray)
+    want, _, _ = orc.search_single(cutoff, xyz, ids, orc.Box(matrix=box) if pbc else None, pbc, 4)
+    s = mb.System(xyz, box=box)
+    sel = s() if ids is None else s(ids)
+    row_ptr, cols = sel.search_connectivity(cutoff, dims=dims)
+    assert len(cols) == 2 * len(want)
+    assert np.array_equal(_rows_from_csr(row_ptr, cols, n), _rows_from_pairs(want, n))
+    if case != "small_fallback":  # (small grids go through pair list -> CSR)
+        with pytest.raises(mb._capi.MolarB200Error):
+            mb._capi.check(s._lib.mb_fill_pairs(s._h, None, None))  # no pair list on the context
+    s.close()
+
+
 @pytest.mark.parametrize("n_mol,n_per,L", [(40, 60, 5.0), (3, 2000, 24.0), (500, 3, 5.0)])
 def test_unwrap_connectivity_vs_oracle(mb, n_mol, n_per, L):
     # (3, 2000): long chains, deep walk (hundreds of levels); the box is large enough that a chain never touches

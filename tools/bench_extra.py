@@ -145,6 +145,18 @@ def bench_connect(mb, orc, n):
                 "roofline": roof(8.0 * npairs * 2 + 8.0 * npairs, ms, "csr_count_kernel + scan + csr_fill_kernel "
                                  "(pairs read twice, 2P neighbour ids written; wall clock of the synchronous call)"),
                 "cpu_baseline": None})
+    import ctypes as C
+    lib.mb_search_connectivity(h, C.c_float(1.2), None, n, 7, None)  # warm-up: plan, allocations
+    t0 = time.perf_counter()
+    nnz2 = mb._capi.check(lib.mb_search_connectivity(h, C.c_float(1.2), None, n, 7, None))
+    ms2 = (time.perf_counter() - t0) * 1e3
+    out.append({"workload": f"SearchConnectivity as neighbour rows written by the search kernel (full shell: count pass, "
+                            f"scan, fill pass), {n} atoms, {nnz2} entries",
+                "metric": "calls/sec", "value": 1e3 / ms2, "unit": "calls/s", "ms_per_call": ms2,
+                "same_entries_as_pair_list_csr": bool(nnz2 == nnz),
+                "roofline": roof(12.0 * n + 4.0 * nnz2, ms2, "search_cells_kernel<4> + scan + search_cells_kernel<5> "
+                                 "(frame read, 4-byte neighbour ids written; wall clock of the synchronous call)"),
+                "cpu_baseline": None})
     s.close()
     rng = np.random.default_rng(2)
     L = (n / 100.0) ** (1.0 / 3.0)
