@@ -1002,6 +1002,359 @@ __global__ void __launch_bounds__(LAG_BLOCK, 2) fit_lag_kernel(const LagParams P
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Single-pass Kabsch batch, fourth design (fused_fit = 4): the persistent kernel of design 3 with WARP-SPECIALISED
+// roles, so that no computing warp ever waits on a global load, on a fence or on another warp.  One CTA per SM owns a
+// slice of every frame; the slice moves in chunks through two shared-memory rings filled by cp.async.bulk (TMA, SASS
+// UBLKCP); every hand-over is an mbarrier full / empty pair — there is no CTA or group barrier in the frame loop:
+//   warp 0  (one lane)  producer of ring 1: the frame's chunks from DRAM, never more than `max_lead` frames ahead of
+//                       pass 2 (keeps the frames in flight inside L2)
+//   warp 1  (one lane)  producer of ring 2: waits for (R, t) of frame g to be published, copies it to shared memory and
+//                       re-loads the frame's chunks — L2 hits, pass 1 read them a few frames ago
+//   warp 2              publisher of pass 1: adds the warps' moment sums of a frame, stores the CTA's partial, fence, ticket
+//   warp 3  (one lane)  storer of pass 2: one bulk store per finished chunk, frees the slot once the store has read it,
+//                       adds the warps' RMSD sums of a frame
+//   warps 4-9           pass 1: 16 f64 moments of the slice (reference slice + masses resident in shared memory)
+//   warps 10-15         pass 2: p <- R p + t in place in the ring slot, sum |p - ref|^2
+//   warp 16             solver: fold of the per-CTA partials + 3x3 SVD of the frames f = blockIdx.x (mod grid)
+// HBM sees each frame once in each direction (12 B/atom read + 12 B/atom written).
+struct WsParams {
+    float* frames;        // [nf][n][3], superposed in place (n % 4 == 0, 16-byte aligned)
+    const float* ref;     // [n][3]
+    const float* masses;  // [n]
+    int n, nf, superpose;
+    int per;              // atoms per CTA slice (multiple of 4); every CTA of the grid owns at least one atom
+    int chunk;            // atoms per ring slot (multiple of 4)
+    int use_smem;         // the CTA's slice of the reference frame and of the masses lives in shared memory (16 B/atom)
+    int max_lead;         // frames pass 1 may run ahead of pass 2
+    double* part_fit;     // [nf][grid][16]
+    double* part_sup;     // [nf][grid]
+    unsigned* tick_fit;   // [nf]
+    unsigned* flag;       // [nf]
+    double* fitres;       // [nf][16]
+};
+constexpr int WS_S1 = 6;   // slots of ring 1 (DRAM latency)
+constexpr int WS_S = 4;    // slots of ring 2 (L2 latency)
+constexpr int WS_NW = 6;   // warps of a computing group
+constexpr int WS_NT = WS_NW * 32;
+constexpr int WS_UB = 3;   // atoms a thread has in flight
+constexpr int WS_BLOCK = 32 * (4 + 2 * WS_NW + 1);
+constexpr int WS_RT = 4;   // (R, t) of the frames pass 2 has in flight
+
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__global__ void __launch_bounds__(WS_BLOCK, 1) fit_ws_kernel(const WsParams P) {
+    extern __shared__ __align__(128) unsigned char ws_dyn[];
+    __shared__ __align__(8) unsigned long long full1[WS_S1], empty1[WS_S1], full2[WS_S], empty2[WS_S], done2[WS_S];
+    __shared__ __align__(8) unsigned long long red1_full[2], red1_empty[2], red2_full[2], red2_empty[2];
+    __shared__ __align__(16) float piv[WS_S1][4];  // first 16 bytes of the frame whose chunk 0 sits in the slot (pivot = atom 0)
+    __shared__ double sRt[WS_RT][12];
+    __shared__ double wsum1[2][WS_NW][16];
+    __shared__ double wsum2[2][WS_NW];
+    __shared__ volatile int p2_done;  // frames pass 2 of this CTA has finished
+
+    const int tid = threadIdx.x, wid = tid >> 5;
+    const unsigned lane = tid & 31u;
+    const int b = blockIdx.x, G = gridDim.x;
+    const int a0 = b * P.per, cnt = min(P.per, P.n - a0);
+    const int K = (cnt + P.chunk - 1) / P.chunk;  // chunks of this CTA's slice
+    float* ring1 = reinterpret_cast<float*>(ws_dyn);
+    float* ring2 = ring1 + (size_t)WS_S1 * P.chunk * 3;
+    float* sref = ring2 + (size_t)WS_S * P.chunk * 3;
+    float* smass = sref + 3 * (size_t)P.per;
+    if (tid == 0) {
+        for (int i = 0; i < WS_S1; ++i) {
+            mbar_init(&full1[i], 1);
+            mbar_init(&empty1[i], WS_NT);
+        }
+        for (int i = 0; i < WS_S; ++i) {
+            mbar_init(&full2[i], 1);
+            mbar_init(&empty2[i], 1);
+            mbar_init(&done2[i], WS_NT);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&red1_full[i], WS_NW * 16);
+            mbar_init(&red1_empty[i], 16);
+            mbar_init(&red2_full[i], WS_NW);
+            mbar_init(&red2_empty[i], 1);
+        }
+        p2_done = 0;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (P.use_smem) {
+        for (int k = tid; k < 3 * cnt; k += WS_BLOCK) sref[k] = P.ref[3 * (size_t)a0 + k];
+        for (int k = tid; k < cnt; k += WS_BLOCK) smass[k] = P.masses[a0 + k];
+    }
+    __syncthreads();
+    const size_t fstride = (size_t)P.n * 3;
+    auto chunk_atoms = [&](int c) { return min(P.chunk, cnt - c * P.chunk); };
+
+    if (wid == 0) {
+        // ---------------- producer of ring 1 ----------------
+        if (lane != 0) return;
+        int i = 0;
+        for (int f = 0; f < P.nf; ++f) {
+            while (f - p2_done > P.max_lead) __nanosleep(200);
+            const float* fr = P.frames + (size_t)f * fstride;
+            for (int c = 0; c < K; ++c, ++i) {
+                const int s = i % WS_S1, u = i / WS_S1;
+                if (u >= 1) mbar_wait(&empty1[s], (unsigned)(u - 1) & 1u);
+                const unsigned bytes = (unsigned)chunk_atoms(c) * 12u;
+                mbar_expect_tx(&full1[s], bytes + (c == 0 ? 16u : 0u));
+                if (c == 0) bulk_load(piv[s], fr, 16u, &full1[s]);
+                bulk_load(ring1 + (size_t)s * P.chunk * 3, fr + 3 * (size_t)(a0 + c * P.chunk), bytes, &full1[s]);
+            }
+        }
+        return;
+    }
+    if (wid == 1) {
+        // ---------------- producer of ring 2 ----------------
+        if (lane != 0) return;
+        int j = 0;
+        for (int g = 0; g < P.nf; ++g) {
+            while (ld_acquire_u32(P.flag + g) == 0u) __nanosleep(100);
+            const float* fr = P.frames + (size_t)g * fstride;
+            for (int c = 0; c < K; ++c, ++j) {
+                const int s = j % WS_S, u = j / WS_S;
+                if (u >= 1) mbar_wait(&empty2[s], (unsigned)(u - 1) & 1u);
+                if (c == 0) {
+                    double rt[12];
+#pragma unroll
+                    for (int k = 0; k < 12; ++k) rt[k] = __ldcg(&P.fitres[(size_t)g * 16 + k]);
+#pragma unroll
+                    for (int k = 0; k < 12; ++k) sRt[g % WS_RT][k] = rt[k];
+                }
+                const unsigned bytes = (unsigned)chunk_atoms(c) * 12u;
+                mbar_expect_tx(&full2[s], bytes);
+                bulk_load(ring2 + (size_t)s * P.chunk * 3, fr + 3 * (size_t)(a0 + c * P.chunk), bytes, &full2[s]);
+            }
+        }
+        return;
+    }
+    if (wid == 2) {
+        // ---------------- publisher of pass 1 ----------------
+        for (int f = 0; f < P.nf; ++f) {
+            mbar_wait(&red1_full[f & 1], (unsigned)(f >> 1) & 1u);
+            if (lane < 16) {
+                double x = 0.0;
+#pragma unroll
+                for (int k = 0; k < WS_NW; ++k) x += wsum1[f & 1][k][lane];
+                mbar_arrive(&red1_empty[f & 1]);
+                P.part_fit[((size_t)f * G + b) * 16 + lane] = x;
+                __threadfence();
+            }
+            __syncwarp();
+            if (lane == 0) atomicAdd(P.tick_fit + f, 1u);  // the G-th ticket releases the frame to its solver warp
+        }
+        return;
+    }
+    if (wid == 3) {
+        // ---------------- storer of pass 2 ----------------
+        if (lane != 0) return;
+        int j = 0;
+        for (int g = 0; g < P.nf; ++g) {
+            float* fr = P.frames + (size_t)g * fstride;
+            for (int c = 0; c < K; ++c, ++j) {
+                const int s = j % WS_S, u = j / WS_S;
+                mbar_wait(&done2[s], (unsigned)u & 1u);
+                if (P.superpose) {
+                    bulk_store(fr + 3 * (size_t)(a0 + c * P.chunk), ring2 + (size_t)s * P.chunk * 3, (unsigned)chunk_atoms(c) * 12u);
+                    // the slot of the PREVIOUS chunk is free once its store has read it out
+                    asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                    if (j >= 1) mbar_arrive(&empty2[(j - 1) % WS_S]);
+                } else {
+                    mbar_arrive(&empty2[s]);
+                }
+            }
+            mbar_wait(&red2_full[g & 1], (unsigned)(g >> 1) & 1u);
+            double x = 0.0;
+#pragma unroll
+            for (int k = 0; k < WS_NW; ++k) x += wsum2[g & 1][k];
+            mbar_arrive(&red2_empty[g & 1]);
+            P.part_sup[(size_t)g * G + b] = x;  // folded in block order by finish_rmsd_kernel
+            p2_done = g + 1;
+        }
+        if (P.superpose) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        return;
+    }
+    if (wid == 4 + 2 * WS_NW) {
+        // ---------------- solver warp: frames b, b + G, ... ----------------
+        const double o2[3] = {(double)P.ref[0], (double)P.ref[1], (double)P.ref[2]};
+        for (int f = b; f < P.nf; f += G) {
+            // the pivot (atom 0 of the frame) does not change before pass 2 of this frame: fetched ahead of the wait
+            const float* fr = P.frames + (size_t)f * fstride;
+            const double o1[3] = {(double)__ldcg(fr), (double)__ldcg(fr + 1), (double)__ldcg(fr + 2)};
+            if (lane == 0)
+                while (ld_acquire_u32(P.tick_fit + f) != (unsigned)G) __nanosleep(100);
+            __syncwarp();
+            // fold: lane l sums the partials of CTAs l, l + 32, ... (all loads of a lane independent, 16 bytes each),
+            // then one butterfly over the 16 values
+            const double2* part = reinterpret_cast<const double2*>(P.part_fit + (size_t)f * G * 16);
+            double acc[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) acc[k] = 0.0;
+            for (int bb = (int)lane; bb < G; bb += 32) {
+                double2 q[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) q[k] = __ldcg(&part[(size_t)bb * 8 + k]);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    acc[2 * k] += q[k].x;
+                    acc[2 * k + 1] += q[k].y;
+                }
+            }
+            const double tot = warp_sum16(acc, lane);  // lane l holds the total of value l >> 1
+            double res[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) res[k] = __shfl_sync(0xffffffffu, tot, 2 * k);
+            if (lane == 0) {
+                fit_finalize<false>(res, o1, o2, 0, P.fitres + (size_t)f * 16);
+                P.tick_fit[f] = 0;  // re-arm for the next launch
+                __threadfence();
+                st_release_u32(P.flag + f, 1u);
+            }
+            __syncwarp();
+        }
+        return;
+    }
+    if (wid < 4 + WS_NW) {
+        // ---------------- pass 1: moments ----------------
+        const int t = tid - 4 * 32, w = wid - 4;
+        const double o2x = P.ref[0], o2y = P.ref[1], o2z = P.ref[2];
+        int i = 0;
+        for (int f = 0; f < P.nf; ++f) {
+            double v[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) v[k] = 0.0;
+            double o1x = 0, o1y = 0, o1z = 0;
+            for (int c = 0; c < K; ++c, ++i) {
+                const int s = i % WS_S1, u = i / WS_S1;
+                mbar_wait(&full1[s], (unsigned)u & 1u);
+                if (c == 0) {
+                    o1x = piv[s][0];
+                    o1y = piv[s][1];
+                    o1z = piv[s][2];
+                }
+                const float* sb = ring1 + (size_t)s * P.chunk * 3;
+                const int cc = chunk_atoms(c), roff = c * P.chunk;
+                for (int ab = t; ab < cc; ab += WS_NT * WS_UB) {
+                    float x1[WS_UB], y1[WS_UB], z1[WS_UB], x2[WS_UB], y2[WS_UB], z2[WS_UB], mf[WS_UB];
+#pragma unroll
+                    for (int q = 0; q < WS_UB; ++q) {
+                        const int a = ab + q * WS_NT;
+                        const bool ok = a < cc;
+                        const int as = ok ? a : t;  // in range: t < cc here
+                        x1[q] = sb[3 * as]; y1[q] = sb[3 * as + 1]; z1[q] = sb[3 * as + 2];
+                        if (P.use_smem) {
+                            x2[q] = sref[3 * (roff + as)];
+                            y2[q] = sref[3 * (roff + as) + 1];
+                            z2[q] = sref[3 * (roff + as) + 2];
+                            mf[q] = smass[roff + as];
+                        } else {
+                            const size_t ga = (size_t)a0 + roff + as;
+                            x2[q] = __ldg(P.ref + 3 * ga);
+                            y2[q] = __ldg(P.ref + 3 * ga + 1);
+                            z2[q] = __ldg(P.ref + 3 * ga + 2);
+                            mf[q] = __ldg(P.masses + ga);
+                        }
+                        if (!ok) mf[q] = 0.0f;  // a zero mass adds exact zeros to every moment
+                    }
+#pragma unroll
+                    for (int q = 0; q < WS_UB; ++q) {
+                        const double m = mf[q];
+                        const double q1x = (double)x1[q] - o1x, q1y = (double)y1[q] - o1y, q1z = (double)z1[q] - o1z;
+                        const double q2x = (double)x2[q] - o2x, q2y = (double)y2[q] - o2y, q2z = (double)z2[q] - o2z;
+                        v[0] += m;
+                        v[1] += m * q1x; v[2] += m * q1y; v[3] += m * q1z;
+                        const double wx = m * q2x, wy = m * q2y, wz = m * q2z;
+                        v[4] += wx; v[5] += wy; v[6] += wz;
+                        v[7] += wx * q1x;  v[8] += wx * q1y;  v[9] += wx * q1z;
+                        v[10] += wy * q1x; v[11] += wy * q1y; v[12] += wy * q1z;
+                        v[13] += wz * q1x; v[14] += wz * q1y; v[15] += wz * q1z;
+                    }
+                }
+                mbar_arrive(&empty1[s]);
+            }
+            const double ws = warp_sum16(v, lane);
+            if (f >= 2) mbar_wait(&red1_empty[f & 1], (unsigned)((f >> 1) - 1) & 1u);
+            if ((lane & 1u) == 0u) {
+                wsum1[f & 1][w][lane >> 1] = ws;
+                mbar_arrive(&red1_full[f & 1]);
+            }
+        }
+        return;
+    }
+    // ---------------- pass 2: superposition + RMSD sum ----------------
+    {
+        const int t = tid - (4 + WS_NW) * 32, w = wid - 4 - WS_NW;
+        int j = 0;
+        for (int g = 0; g < P.nf; ++g) {
+            double R[9], tr[3];
+            double r2 = 0.0;
+            for (int c = 0; c < K; ++c, ++j) {
+                const int s = j % WS_S, u = j / WS_S;
+                mbar_wait(&full2[s], (unsigned)u & 1u);
+                if (c == 0) {
+#pragma unroll
+                    for (int k = 0; k < 9; ++k) R[k] = sRt[g % WS_RT][k];
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) tr[k] = sRt[g % WS_RT][9 + k];
+                }
+                float* sb = ring2 + (size_t)s * P.chunk * 3;
+                const int cc = chunk_atoms(c), roff = c * P.chunk;
+                for (int ab = t; ab < cc; ab += WS_NT * WS_UB) {
+                    float x0[WS_UB], y0[WS_UB], z0[WS_UB], rx[WS_UB], ry[WS_UB], rz[WS_UB];
+#pragma unroll
+                    for (int q = 0; q < WS_UB; ++q) {
+                        const int a = ab + q * WS_NT;
+                        const int as = a < cc ? a : t;
+                        x0[q] = sb[3 * as]; y0[q] = sb[3 * as + 1]; z0[q] = sb[3 * as + 2];
+                        if (P.use_smem) {
+                            rx[q] = sref[3 * (roff + as)];
+                            ry[q] = sref[3 * (roff + as) + 1];
+                            rz[q] = sref[3 * (roff + as) + 2];
+                        } else {
+                            const size_t ga = (size_t)a0 + roff + as;
+                            rx[q] = __ldg(P.ref + 3 * ga);
+                            ry[q] = __ldg(P.ref + 3 * ga + 1);
+                            rz[q] = __ldg(P.ref + 3 * ga + 2);
+                        }
+                    }
+#pragma unroll
+                    for (int q = 0; q < WS_UB; ++q) {
+                        const int a = ab + q * WS_NT;
+                        if (a < cc) {
+                            const double px0 = x0[q], py0 = y0[q], pz0 = z0[q];
+                            const double px = R[0] * px0 + R[1] * py0 + R[2] * pz0 + tr[0];
+                            const double py = R[3] * px0 + R[4] * py0 + R[5] * pz0 + tr[1];
+                            const double pz = R[6] * px0 + R[7] * py0 + R[8] * pz0 + tr[2];
+                            const double dx = px - (double)rx[q], dy = py - (double)ry[q], dz = pz - (double)rz[q];
+                            r2 += dx * dx + dy * dy + dz * dz;
+                            if (P.superpose) {
+                                sb[3 * a] = (float)px;
+                                sb[3 * a + 1] = (float)py;
+                                sb[3 * a + 2] = (float)pz;
+                            }
+                        }
+                    }
+                }
+                if (P.superpose) fence_async_smem();  // the slot's new contents become visible to the bulk store
+                mbar_arrive(&done2[s]);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) r2 += __shfl_xor_sync(0xffffffffu, r2, o);
+            if (lane == 0) {
+                if (g >= 2) mbar_wait(&red2_empty[g & 1], (unsigned)((g >> 1) - 1) & 1u);
+                wsum2[g & 1][w] = r2;
+                mbar_arrive(&red2_full[g & 1]);
+            }
+            __syncwarp();
+        }
+    }
+}
+
 // rmsd[f] = sqrt(sum_b part[f][b] / n), partials folded in block order (deterministic)
 __global__ void __launch_bounds__(32) finish_rmsd_kernel(const double* __restrict__ part, int nblk, int n,
                                                          double* __restrict__ rmsd) {
@@ -1099,6 +1452,57 @@ int batch_fit_impl(Ctx* c, size_t ref_frame, size_t f0, size_t f1, int superpose
                                 cudaMemcpyDeviceToDevice, c->stream));
     }
     const float* ref = c->batch_ref.as<float>();
+    // ---- single-pass path, fourth design (fused_fit = 4): warp-specialised persistent kernel, TMA rings ----
+    if (c->opt_fused_fit == 4 && (n % 4) == 0 && !(reinterpret_cast<uintptr_t>(c->batch.p) & 15u)) {
+        int per = (int)((((n + c->sm_count - 1) / c->sm_count) + 3) / 4 * 4);
+        const int grid = (int)((n + per - 1) / per);  // every CTA owns at least one atom
+        int chunk = std::min(per, c->opt_fit_group > 0 ? (c->opt_fit_group + 3) / 4 * 4 : WS_NT * 2 * WS_UB);
+        const size_t ring_bytes = (size_t)(WS_S1 + WS_S) * chunk * 12;
+        const int use_smem = ring_bytes + (size_t)per * 16 <= (size_t)200 * 1024 ? 1 : 0;
+        const size_t dyn_smem = ring_bytes + (use_smem ? (size_t)per * 16 : 0);
+        MB_CUDA(cudaFuncSetAttribute(fit_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
+        int occ_real = 0;
+        MB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_real, fit_ws_kernel, WS_BLOCK, dyn_smem));
+        if ((long long)occ_real * c->sm_count < grid)
+            return fail(MB_ERR_STATE, "batch_fit: persistent grid of %d CTAs (%zu B shared) does not fit the device", grid, dyn_smem);
+        const size_t fb = n * 12;
+        int lead = (int)std::max<size_t>(2, std::min<size_t>(64, ((size_t)40 << 20) / std::max<size_t>(fb, 1)));
+        if (c->opt_fit_lag > 0) lead = c->opt_fit_lag;
+        const size_t fchunk = std::min<size_t>(nf, 4096);
+        RedScratch s{};
+        MB_TRY(red_scratch(c, 2 * fchunk, fchunk * (size_t)grid * 17, nf * 17, &s));
+        double* fitres = s.results;
+        double* d_rmsd = s.results + nf * 16;
+        for (size_t g0 = 0; g0 < nf; g0 += fchunk) {
+            const size_t gn = std::min(fchunk, nf - g0);
+            WsParams P;
+            P.frames = c->batch.as<float>() + (f0 + g0) * n * 3;
+            P.ref = ref;
+            P.masses = c->masses.as<float>();
+            P.n = (int)n;
+            P.nf = (int)gn;
+            P.superpose = superpose;
+            P.per = per;
+            P.chunk = chunk;
+            P.use_smem = use_smem;
+            P.max_lead = lead;
+            P.part_fit = s.partials;
+            P.part_sup = s.partials + fchunk * (size_t)grid * 16;
+            P.tick_fit = s.tickets;
+            P.flag = s.tickets + fchunk;
+            P.fitres = fitres + g0 * 16;
+            MB_CUDA(cudaMemsetAsync(P.flag, 0, gn * sizeof(unsigned), c->stream));
+            void* args[] = {&P};
+            MB_CUDA(cudaLaunchCooperativeKernel((const void*)fit_ws_kernel, dim3(grid), dim3(WS_BLOCK), args, dyn_smem, c->stream));
+            finish_rmsd_kernel<<<(unsigned)gn, 32, 0, c->stream>>>(P.part_sup, grid, (int)n, d_rmsd + g0);
+            c->launches += 2;
+        }
+        MB_CUDA(cudaGetLastError());
+        if (rmsd_out)
+            MB_CUDA(cudaMemcpyAsync(rmsd_out, d_rmsd, nf * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        MB_CUDA(cudaStreamSynchronize(c->stream));
+        return MB_OK;
+    }
     // ---- single-pass path, third design (fused_fit = 3): one persistent kernel, pass 2 lags by LAG frames and reads L2
     if (c->opt_fused_fit == 3) {
         const int occ = 2;  // CTAs per SM the kernel is sized for (<= 128 registers x 256 threads)

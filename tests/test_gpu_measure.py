@@ -149,11 +149,12 @@ def test_batch_fit_fused_vs_two_kernel_path(mb, n, nf):
     """The single-pass kernels (fused_fit=1: TMA ring, finisher role rotates over the slice CTAs; 2: TMA ring, worker CTAs
     + dedicated finisher CTAs; 3: one persistent kernel whose second pass lags behind and is served by L2) and the
     generic two-kernel path must agree with the oracle and with each other (n % 4 != 0: modes 1 and 2 fall back to the
-    generic path, mode 3 takes its scalar loop)."""
+    generic path, mode 3 takes its scalar loop; 4: the warp-specialised persistent kernel — TMA producers, pass-1 and
+    pass-2 warp groups, solver warp)."""
     m = orc.synth_masses(SEED, n)
     ref = orc.synth_frame(SEED, 0, n, TRIC)
     out = {}
-    for mode in (0, 1, 2, 3):
+    for mode in (0, 1, 2, 3, 4):
         t = mb.Trajectory()
         t.synth(SEED, 0, nf, n, TRIC, mass_seed=SEED)
         t.set_option("fused_fit", mode)
@@ -176,7 +177,7 @@ def test_batch_fit_fused_vs_two_kernel_path(mb, n, nf):
         assert np.allclose(r3[1:], r[1:], rtol=1e-4)
         t.close()
         t2.close()
-    for mode in (1, 2, 3):
+    for mode in (1, 2, 3, 4):
         assert np.allclose(out[0][0], out[mode][0], rtol=1e-10) and np.allclose(out[0][1], out[mode][1], atol=1e-6)
 
 
