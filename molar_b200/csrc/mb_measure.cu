@@ -347,12 +347,28 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
     do {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)  // suspend-time hint (ns): a waiting warp should not spin on issue slots
+            : "memory");
+    } while (!ok);
+}
+// the same for a role that has nothing else to do (producers, storer, publisher): back off between polls so that the
+// spinning does not take issue slots from the computing warps of the same scheduler
+__device__ __forceinline__ void mbar_wait_idle(unsigned long long* bar, unsigned parity) {
+    for (;;) {
+        unsigned ok;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(ok)
             : "r"(smem_u32(bar)), "r"(parity)
             : "memory");
-    } while (!ok);
+        if (ok) break;
+        __nanosleep(40);
+    }
 }
 __device__ __forceinline__ void bulk_load(void* dst_smem, const void* src_gmem, unsigned bytes, unsigned long long* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
@@ -1035,9 +1051,15 @@ struct WsParams {
 };
 constexpr int WS_S1 = 6;   // slots of ring 1 (DRAM latency)
 constexpr int WS_S = 4;    // slots of ring 2 (L2 latency)
-constexpr int WS_NW = 6;   // warps of a computing group
+#ifndef MB_WS_NW
+#define MB_WS_NW 6
+#endif
+constexpr int WS_NW = MB_WS_NW;   // warps of a computing group
 constexpr int WS_NT = WS_NW * 32;
-constexpr int WS_UB = 3;   // atoms a thread has in flight
+#ifndef MB_WS_UB
+#define MB_WS_UB 3
+#endif
+constexpr int WS_UB = MB_WS_UB;   // atoms a thread has in flight
 constexpr int WS_BLOCK = 32 * (4 + 2 * WS_NW + 1);
 constexpr int WS_RT = 4;   // (R, t) of the frames pass 2 has in flight
 
@@ -1045,6 +1067,7 @@ __device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+template <bool REF_SMEM>
 __global__ void __launch_bounds__(WS_BLOCK, 1) fit_ws_kernel(const WsParams P) {
     extern __shared__ __align__(128) unsigned char ws_dyn[];
     __shared__ __align__(8) unsigned long long full1[WS_S1], empty1[WS_S1], full2[WS_S], empty2[WS_S], done2[WS_S];
@@ -1083,7 +1106,7 @@ __global__ void __launch_bounds__(WS_BLOCK, 1) fit_ws_kernel(const WsParams P) {
         p2_done = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (P.use_smem) {
+    if (REF_SMEM) {
         for (int k = tid; k < 3 * cnt; k += WS_BLOCK) sref[k] = P.ref[3 * (size_t)a0 + k];
         for (int k = tid; k < cnt; k += WS_BLOCK) smass[k] = P.masses[a0 + k];
     }
@@ -1100,7 +1123,7 @@ __global__ void __launch_bounds__(WS_BLOCK, 1) fit_ws_kernel(const WsParams P) {
             const float* fr = P.frames + (size_t)f * fstride;
             for (int c = 0; c < K; ++c, ++i) {
                 const int s = i % WS_S1, u = i / WS_S1;
-                if (u >= 1) mbar_wait(&empty1[s], (unsigned)(u - 1) & 1u);
+                if (u >= 1) mbar_wait_idle(&empty1[s], (unsigned)(u - 1) & 1u);
                 const unsigned bytes = (unsigned)chunk_atoms(c) * 12u;
                 mbar_expect_tx(&full1[s], bytes + (c == 0 ? 16u : 0u));
                 if (c == 0) bulk_load(piv[s], fr, 16u, &full1[s]);
@@ -1118,7 +1141,7 @@ __global__ void __launch_bounds__(WS_BLOCK, 1) fit_ws_kernel(const WsParams P) {
             const float* fr = P.frames + (size_t)g * fstride;
             for (int c = 0; c < K; ++c, ++j) {
                 const int s = j % WS_S, u = j / WS_S;
-                if (u >= 1) mbar_wait(&empty2[s], (unsigned)(u - 1) & 1u);
+                if (u >= 1) mbar_wait_idle(&empty2[s], (unsigned)(u - 1) & 1u);
                 if (c == 0) {
                     double rt[12];
 #pragma unroll
@@ -1136,7 +1159,8 @@ __global__ void __launch_bounds__(WS_BLOCK, 1) fit_ws_kernel(const WsParams P) {
     if (wid == 2) {
         // ---------------- publisher of pass 1 ----------------
         for (int f = 0; f < P.nf; ++f) {
-            mbar_wait(&red1_full[f & 1], (unsigned)(f >> 1) & 1u);
+            if (lane == 0) mbar_wait_idle(&red1_full[f & 1], (unsigned)(f >> 1) & 1u);
+            __syncwarp();
             if (lane < 16) {
                 double x = 0.0;
 #pragma unroll
@@ -1158,7 +1182,7 @@ __global__ void __launch_bounds__(WS_BLOCK, 1) fit_ws_kernel(const WsParams P) {
             float* fr = P.frames + (size_t)g * fstride;
             for (int c = 0; c < K; ++c, ++j) {
                 const int s = j % WS_S, u = j / WS_S;
-                mbar_wait(&done2[s], (unsigned)u & 1u);
+                mbar_wait_idle(&done2[s], (unsigned)u & 1u);
                 if (P.superpose) {
                     bulk_store(fr + 3 * (size_t)(a0 + c * P.chunk), ring2 + (size_t)s * P.chunk * 3, (unsigned)chunk_atoms(c) * 12u);
                     // the slot of the PREVIOUS chunk is free once its store has read it out
@@ -1168,7 +1192,7 @@ __global__ void __launch_bounds__(WS_BLOCK, 1) fit_ws_kernel(const WsParams P) {
                     mbar_arrive(&empty2[s]);
                 }
             }
-            mbar_wait(&red2_full[g & 1], (unsigned)(g >> 1) & 1u);
+            mbar_wait_idle(&red2_full[g & 1], (unsigned)(g >> 1) & 1u);
             double x = 0.0;
 #pragma unroll
             for (int k = 0; k < WS_NW; ++k) x += wsum2[g & 1][k];
@@ -1247,7 +1271,7 @@ __global__ void __launch_bounds__(WS_BLOCK, 1) fit_ws_kernel(const WsParams P) {
                         const bool ok = a < cc;
                         const int as = ok ? a : t;  // in range: t < cc here
                         x1[q] = sb[3 * as]; y1[q] = sb[3 * as + 1]; z1[q] = sb[3 * as + 2];
-                        if (P.use_smem) {
+                        if (REF_SMEM) {
                             x2[q] = sref[3 * (roff + as)];
                             y2[q] = sref[3 * (roff + as) + 1];
                             z2[q] = sref[3 * (roff + as) + 2];
@@ -1311,7 +1335,7 @@ __global__ void __launch_bounds__(WS_BLOCK, 1) fit_ws_kernel(const WsParams P) {
                         const int a = ab + q * WS_NT;
                         const int as = a < cc ? a : t;
                         x0[q] = sb[3 * as]; y0[q] = sb[3 * as + 1]; z0[q] = sb[3 * as + 2];
-                        if (P.use_smem) {
+                        if (REF_SMEM) {
                             rx[q] = sref[3 * (roff + as)];
                             ry[q] = sref[3 * (roff + as) + 1];
                             rz[q] = sref[3 * (roff + as) + 2];
@@ -1456,13 +1480,24 @@ int batch_fit_impl(Ctx* c, size_t ref_frame, size_t f0, size_t f1, int superpose
     if (c->opt_fused_fit == 4 && (n % 4) == 0 && !(reinterpret_cast<uintptr_t>(c->batch.p) & 15u)) {
         int per = (int)((((n + c->sm_count - 1) / c->sm_count) + 3) / 4 * 4);
         const int grid = (int)((n + per - 1) / per);  // every CTA owns at least one atom
-        int chunk = std::min(per, c->opt_fit_group > 0 ? (c->opt_fit_group + 3) / 4 * 4 : WS_NT * 2 * WS_UB);
+        // ring slot: a multiple of one batched round of a group (WS_NT x WS_UB atoms), as large as the shared memory
+        // left next to the resident reference slice allows, at most half a slice (>= 2 chunks in flight per frame)
+        const size_t smem_budget = (size_t)200 * 1024;
+        const int round = WS_NT * WS_UB;
+        int use_smem = (size_t)per * 16 + (size_t)(WS_S1 + WS_S) * round * 12 <= smem_budget ? 1 : 0;
+        const size_t ring_budget = smem_budget - (use_smem ? (size_t)per * 16 : 0);
+        int mult = (int)std::max<size_t>(1, std::min<size_t>(ring_budget / ((size_t)(WS_S1 + WS_S) * round * 12),
+                                                              std::max<size_t>(1, ((size_t)per / 2 + round - 1) / round)));
+        int chunk = c->opt_fit_group > 0 ? (c->opt_fit_group + 3) / 4 * 4 : mult * round;
+        chunk = std::min(chunk, per);
         const size_t ring_bytes = (size_t)(WS_S1 + WS_S) * chunk * 12;
-        const int use_smem = ring_bytes + (size_t)per * 16 <= (size_t)200 * 1024 ? 1 : 0;
+        if (ring_bytes + (use_smem ? (size_t)per * 16 : 0) > smem_budget) use_smem = 0;
+        if (ring_bytes > smem_budget) return fail(MB_ERR_ARG, "batch_fit: fit_group too large for the shared-memory rings");
         const size_t dyn_smem = ring_bytes + (use_smem ? (size_t)per * 16 : 0);
-        MB_CUDA(cudaFuncSetAttribute(fit_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
+        auto ws_kern = use_smem ? fit_ws_kernel<true> : fit_ws_kernel<false>;
+        MB_CUDA(cudaFuncSetAttribute(ws_kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
         int occ_real = 0;
-        MB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_real, fit_ws_kernel, WS_BLOCK, dyn_smem));
+        MB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_real, ws_kern, WS_BLOCK, dyn_smem));
         if ((long long)occ_real * c->sm_count < grid)
             return fail(MB_ERR_STATE, "batch_fit: persistent grid of %d CTAs (%zu B shared) does not fit the device", grid, dyn_smem);
         const size_t fb = n * 12;
@@ -1493,7 +1528,7 @@ int batch_fit_impl(Ctx* c, size_t ref_frame, size_t f0, size_t f1, int superpose
             P.fitres = fitres + g0 * 16;
             MB_CUDA(cudaMemsetAsync(P.flag, 0, gn * sizeof(unsigned), c->stream));
             void* args[] = {&P};
-            MB_CUDA(cudaLaunchCooperativeKernel((const void*)fit_ws_kernel, dim3(grid), dim3(WS_BLOCK), args, dyn_smem, c->stream));
+            MB_CUDA(cudaLaunchCooperativeKernel((const void*)ws_kern, dim3(grid), dim3(WS_BLOCK), args, dyn_smem, c->stream));
             finish_rmsd_kernel<<<(unsigned)gn, 32, 0, c->stream>>>(P.part_sup, grid, (int)n, d_rmsd + g0);
             c->launches += 2;
         }
