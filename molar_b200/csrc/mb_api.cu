@@ -122,6 +122,41 @@ DevBox to_dev_box(const HostBox& b) {
         if (i < b.ncorr) smin2 = std::min(smin2, s2);
     }
     d.rin2 = b.ncorr > 0 ? (float)(0.499 * 0.499 * smin2) : 0.0f;
+    // the same corrections as 13 (+v, -v) pairs over the lattice coefficients (shortest_vector_dev): the reference's
+    // list is generated for i, j, k = -1..1 in that nesting, minus (0,0,0), minus the ones beyond the diagonal bound —
+    // replay the generation to find the index of every combination
+    static const int PAIR_IJK[13][3] = {{0, 0, 1}, {0, 1, -1}, {0, 1, 0}, {0, 1, 1}, {1, -1, -1}, {1, -1, 0}, {1, -1, 1},
+                                        {1, 0, -1}, {1, 0, 0}, {1, 0, 1}, {1, 1, -1}, {1, 1, 0}, {1, 1, 1}};
+    for (int p = 0; p < 13; ++p) {
+        d.pair_thr[p] = 0.0f;
+        d.pair_bit[2 * p] = d.pair_bit[2 * p + 1] = 0u;
+    }
+    if (b.ncorr > 0) {
+        const float a[3] = {b.m[0][0], b.m[1][0], b.m[2][0]}, bb[3] = {b.m[0][1], b.m[1][1], b.m[2][1]},
+                    cc[3] = {b.m[0][2], b.m[1][2], b.m[2][2]};
+        for (int i = -1; i <= 1; ++i)
+            for (int j = -1; j <= 1; ++j)
+                for (int k = -1; k <= 1; ++k) {
+                    if (i == 0 && j == 0 && k == 0) continue;
+                    float s[3];
+                    for (int q = 0; q < 3; ++q) s[q] = ((float)i * a[q] + (float)j * bb[q]) + (float)k * cc[q];
+                    int idx = -1;
+                    for (int t = 0; t < b.ncorr; ++t)
+                        if (b.corr[t][0] == s[0] && b.corr[t][1] == s[1] && b.corr[t][2] == s[2]) {
+                            idx = t;
+                            break;
+                        }
+                    if (idx < 0) continue;
+                    for (int p = 0; p < 13; ++p) {
+                        const int sg = (PAIR_IJK[p][0] == i && PAIR_IJK[p][1] == j && PAIR_IJK[p][2] == k)      ? 0
+                                       : (PAIR_IJK[p][0] == -i && PAIR_IJK[p][1] == -j && PAIR_IJK[p][2] == -k) ? 1
+                                                                                                                : -1;
+                        if (sg < 0) continue;
+                        d.pair_bit[2 * p + sg] = 1u << idx;
+                        d.pair_thr[p] = d.corr_thr[idx];
+                    }
+                }
+    }
     return d;
 }
 

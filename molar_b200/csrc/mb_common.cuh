@@ -54,6 +54,11 @@ struct DevBox {
     float corr[26 * 3];
     float corr_thr[26];  // -0.4995 |s|^2 per correction: start.s above it => the correction cannot win (pruned)
     float rin2;          // (0.499 min |s|)^2: |start|^2 below it => no correction can win
+    // The 26 lattice combinations as 13 pairs (+v, -v), v = i a + j b + k c in the order of PAIR_IJK (mb_common.cuh):
+    // start.v is a sum of the three basis products, start.(-v) its negative, and both share one threshold.
+    // pair_bit[2p] / [2p + 1]: bit (1 << index in corr[]) of +v / -v, 0 when the reference's list does not hold it.
+    float pair_thr[13];
+    unsigned pair_bit[26];
 };
 DevBox to_dev_box(const HostBox& b);
 
@@ -240,14 +245,39 @@ __device__ __forceinline__ void shortest_vector_dev(const DevBox& bx, float v0, 
     o2 = s2;
     if (bx.ncorr == 0 || w != 7u) return;
     float best2 = xnorm2(s0, s1, s2);
-    // The reference evaluates all (up to 26) triclinic corrections (periodic_box.rs:299-317).  A correction s can beat
-    // `start` only if 2 start.s + |s|^2 < 0; the two prunes below skip corrections whose real improvement is negative
-    // by a margin a thousand times the f32 rounding of the reference's comparison, so the surviving ones — evaluated
-    // with the reference's exact expression against the running best — give the reference's result.
-    if (best2 < bx.rin2) return;  // inside the inscribed sphere of the cell: no correction can win
-    for (int c = 0; c < bx.ncorr; ++c) {
-        const float dot = fmaf(s0, bx.corr[3 * c], fmaf(s1, bx.corr[3 * c + 1], s2 * bx.corr[3 * c + 2]));
-        if (dot > bx.corr_thr[c]) continue;  // cannot beat `start` by a wide margin: pruned
+    // The reference evaluates all (up to 26) triclinic corrections (periodic_box.rs:299-317).  A correction v can beat
+    // `start` only if 2 start.v + |v|^2 < 0.  Candidates are found from THREE dot products (start with the box vectors):
+    // start.(i a + j b + k c) is a sum of them, its negative serves the opposite correction, and a correction whose
+    // real improvement is negative by more than 1e-3 |v|^2 — a thousand times any f32 rounding involved — is dropped.
+    // The surviving ones (a bit mask, usually empty) are evaluated with the reference's exact expression against the
+    // running best in the reference's order, which gives the reference's result.
+    const float da = fmaf(s0, bx.m[0], fmaf(s1, bx.m[3], s2 * bx.m[6]));
+    const float db = fmaf(s0, bx.m[1], fmaf(s1, bx.m[4], s2 * bx.m[7]));
+    const float dc = fmaf(s0, bx.m[2], fmaf(s1, bx.m[5], s2 * bx.m[8]));
+    unsigned cand = 0u;
+#define MB_PAIR(P, EXPR)                                   \
+    {                                                      \
+        const float d = (EXPR);                            \
+        if (d < bx.pair_thr[P]) cand |= bx.pair_bit[2 * P];      \
+        if (-d < bx.pair_thr[P]) cand |= bx.pair_bit[2 * P + 1]; \
+    }
+    MB_PAIR(0, dc)                // ( 0, 0, 1)
+    MB_PAIR(1, db - dc)           // ( 0, 1,-1)
+    MB_PAIR(2, db)                // ( 0, 1, 0)
+    MB_PAIR(3, db + dc)           // ( 0, 1, 1)
+    MB_PAIR(4, (da - db) - dc)    // ( 1,-1,-1)
+    MB_PAIR(5, da - db)           // ( 1,-1, 0)
+    MB_PAIR(6, (da - db) + dc)    // ( 1,-1, 1)
+    MB_PAIR(7, da - dc)           // ( 1, 0,-1)
+    MB_PAIR(8, da)                // ( 1, 0, 0)
+    MB_PAIR(9, da + dc)           // ( 1, 0, 1)
+    MB_PAIR(10, (da + db) - dc)   // ( 1, 1,-1)
+    MB_PAIR(11, da + db)          // ( 1, 1, 0)
+    MB_PAIR(12, (da + db) + dc)   // ( 1, 1, 1)
+#undef MB_PAIR
+    while (cand) {
+        const int c = __ffs(cand) - 1;
+        cand &= cand - 1u;
         const float c0 = xadd(s0, bx.corr[3 * c]), c1 = xadd(s1, bx.corr[3 * c + 1]), c2 = xadd(s2, bx.corr[3 * c + 2]);
         const float n2 = xnorm2(c0, c1, c2);
         if (n2 < best2) {
