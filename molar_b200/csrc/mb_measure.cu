@@ -1159,8 +1159,7 @@ __global__ void __launch_bounds__(WS_BLOCK, 1) fit_ws_kernel(const WsParams P) {
     if (wid == 2) {
         // ---------------- publisher of pass 1 ----------------
         for (int f = 0; f < P.nf; ++f) {
-            if (lane == 0) mbar_wait_idle(&red1_full[f & 1], (unsigned)(f >> 1) & 1u);
-            __syncwarp();
+            mbar_wait_idle(&red1_full[f & 1], (unsigned)(f >> 1) & 1u);  // every reading lane acquires the phase itself
             if (lane < 16) {
                 double x = 0.0;
 #pragma unroll

@@ -26,7 +26,9 @@ tr = mb.fit_transform(s(), ref()); s().apply_transform(tr); r = mb.rmsd(s(), ref
 t = mb.Trajectory(); t.synth(1, 0, 4, 8000, M, mass_seed=1)
 c = t.search(1.2); c2 = t.search(1.2, count_only=True); rows = t.pipeline(1.2); rr = t.fit(0)
 t.set_option("fused_fit", 1); rr2 = t.fit(0)
-t.set_option("fused_fit", 3); rr3 = t.fit(0); t.set_option("fused_fit", 0)  # persistent kernel: solver warps, teams, L2-served lag
+t.set_option("fused_fit", 3); rr3 = t.fit(0)  # persistent kernel: solver warps, teams, L2-served lag
+t.set_option("fused_fit", 4); rr4 = t.fit(0); t.set_option("fused_fit", 0)  # warp-specialised kernel: TMA rings, mbarrier hand-overs
+assert np.allclose(rr4, rr, rtol=1e-9)
 print("ok", len(p), len(p2), len(w), len(p3), len(p4), c.tolist(), c2.tolist(), float(r))
 # ---- round 2 additions: periodic reductions, inertia, trajectory ingest, pair-list consumers ----
 from oracle import traj_oracle as T
@@ -36,6 +38,8 @@ s2.set_option("with_dist", 0)
 npl2 = mb._capi.check(s2._lib.mb_search_single(s2._h, 1.2, None, n, 7))    # pairs only
 pl2 = np.empty((npl2, 2), np.uint64); mb._capi.check(s2._lib.mb_fill_pairs(s2._h, pl2.ctypes.data, None))
 rp, cols = s2.connectivity()                                               # CSR adjacency
+rp2, cols2 = s2().search_connectivity(1.2, dims=[True] * 3)                # neighbour rows written by the search kernel (modes 4, 5)
+assert np.array_equal(rp, rp2) and len(cols2) == len(cols)
 cp = s2().com(dims=[True] * 3); cg = s2().cog(dims=[True, False, True]); gp = s2().gyration(pbc=True)
 mom, ax = s2().inertia(pbc=True); mom2, ax2 = s2().inertia(); ptr = s2().principal_transform()
 sels = s2(np.arange(0, n, 2, dtype=np.uint64)).unwrap_connectivity(0.25)   # union-find + persistent BFS kernel
