@@ -190,6 +190,10 @@ int64_t mb_connectivity(MbCtx* ctx, size_t n_index, uint64_t* row_ptr_out);
 int64_t mb_search_connectivity(MbCtx* ctx, float cutoff, const uint64_t* ids, size_t n, uint8_t pbc_dims,
                                uint64_t* row_ptr_out);
 int mb_fill_connectivity(MbCtx* ctx, uint64_t* cols_out);
+/* Order-independent checksum of the adjacency on the device (parity checks at sizes whose lists should not travel):
+   out4 = {sum, xor} of mix64((min << 32) | max) over the entries with row < column, then over those with row > column;
+   for a symmetric list both halves equal mb_pairs_checksum of the pair list. */
+int mb_connectivity_checksum(MbCtx* ctx, uint64_t out4[4]);
 /* unwrap_connectivity_dim: contact graph of the selection at `cutoff` (periodic in all dims), every atom moved to
  * its closest image (image_dims) next to the atom it is reached from, walking from the lowest-index atom of each
  * component; coordinates change in place on the device (mb_get_frame).  roots_out[k] (may be NULL) = position within

@@ -49,6 +49,7 @@ SIGNATURES = {
     "mb_connectivity": (C.c_int64, [C.c_void_p, C.c_size_t, u64p]),
     "mb_search_connectivity": (C.c_int64, [C.c_void_p, C.c_float, u64p, C.c_size_t, C.c_uint8, u64p]),
     "mb_fill_connectivity": (C.c_int, [C.c_void_p, u64p]),
+    "mb_connectivity_checksum": (C.c_int, [C.c_void_p, u64p]),
     "mb_unwrap_connectivity": (C.c_int64, [C.c_void_p, C.c_float, u64p, C.c_size_t, C.c_uint8, i64p]),
     "mb_reduce_many": (C.c_int, [C.c_void_p, u64p, u64p, C.c_size_t, C.c_int, f64p, C.POINTER(C.c_int)]),
     "mb_center_of_geometry": (C.c_int, [C.c_void_p, u64p, C.c_size_t, f64p]),

@@ -167,6 +167,13 @@ class System:
             check(self._lib.mb_fill_connectivity(self._h, cols.ctypes.data_as(u64p)))
         return row_ptr, cols
 
+    def connectivity_checksum(self):
+        """(sum, xor) of mix64((min << 32) | max) over the adjacency entries with row < column and over those with
+        row > column, computed on the device."""
+        out = np.zeros(4, np.uint64)
+        check(self._lib.mb_connectivity_checksum(self._h, out.ctypes.data_as(u64p)))
+        return int(out[0]), int(out[1]), int(out[2]), int(out[3])
+
 
 class Sel:
     def __init__(self, system, index, n):

@@ -46,6 +46,50 @@ __global__ void __launch_bounds__(256) csr_fill_kernel(const uint2* __restrict__
         cols[atomicAdd(&cursor[p.y], 1u)] = p.x;
     }
 }
+// order-independent checksum of the adjacency: the hash of mb_pairs_checksum (mix64((min << 32) | max), summed and
+// xor-ed) taken once over the entries with row < column and once over the entries with row > column — a symmetric
+// neighbour list gives the pair list's checksum twice.  One warp per row.
+__device__ __forceinline__ unsigned long long mix64c(unsigned long long x) {
+    x ^= x >> 33;
+    x *= 0xff51afd7ed558ccdULL;
+    x ^= x >> 33;
+    x *= 0xc4ceb9fe1a85ec53ULL;
+    x ^= x >> 33;
+    return x;
+}
+__global__ void __launch_bounds__(256) csr_checksum_kernel(const unsigned* __restrict__ row_ptr, const unsigned* __restrict__ cols,
+                                                           unsigned n, unsigned long long* __restrict__ out4) {
+    const unsigned lane = threadIdx.x & 31u, nw = (gridDim.x * blockDim.x) >> 5;
+    unsigned long long s0 = 0, x0 = 0, s1 = 0, x1 = 0;
+    for (unsigned i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += nw) {
+        const unsigned e1 = row_ptr[i + 1];
+        for (unsigned e = row_ptr[i] + lane; e < e1; e += 32) {
+            const unsigned j = cols[e];
+            if (i < j) {
+                const unsigned long long h = mix64c(((unsigned long long)i << 32) | j);
+                s0 += h;
+                x0 ^= h;
+            } else {
+                const unsigned long long h = mix64c(((unsigned long long)j << 32) | i);
+                s1 += h;
+                x1 ^= h;
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+        x0 ^= __shfl_xor_sync(0xffffffffu, x0, o);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        x1 ^= __shfl_xor_sync(0xffffffffu, x1, o);
+    }
+    if (lane == 0) {
+        atomicAdd(&out4[0], s0);
+        atomicXor(&out4[1], x0);
+        atomicAdd(&out4[2], s1);
+        atomicXor(&out4[3], x1);
+    }
+}
 __global__ void widen_u32_kernel(const unsigned* __restrict__ in, size_t n, unsigned long long* __restrict__ out) {
     size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (k < n) out[k] = in[k];
@@ -303,6 +347,22 @@ int64_t mb_search_connectivity(MbCtx* h, float cutoff, const uint64_t* ids, size
     }
     MB_CUDA(cudaStreamSynchronize(c->stream));
     return (int64_t)nnz;
+}
+
+int mb_connectivity_checksum(MbCtx* h, uint64_t out4[4]) {
+    if (!h || !out4) return fail(MB_ERR_ARG, "null argument");
+    Ctx* c = &h->c;
+    if (!c->conn_cols.p || c->conn_n == 0) return fail(MB_ERR_STATE, "no connectivity on this context");
+    MB_CUDA(cudaSetDevice(c->device));
+    MB_TRY(c->counters.reserve(256));
+    unsigned long long* d4 = c->counters.as<unsigned long long>() + 8;
+    MB_CUDA(cudaMemsetAsync(d4, 0, 4 * sizeof(unsigned long long), c->stream));
+    const unsigned* rp = c->conn_tmp.as<unsigned>() + (c->conn_n + 2);
+    csr_checksum_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(rp, c->conn_cols.as<unsigned>(), (unsigned)c->conn_n, d4);
+    c->launches++;
+    MB_CUDA(cudaMemcpyAsync(out4, d4, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+    MB_CUDA(cudaStreamSynchronize(c->stream));
+    return MB_OK;
 }
 
 int mb_fill_connectivity(MbCtx* h, uint64_t* cols_out) {

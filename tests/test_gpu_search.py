@@ -434,6 +434,10 @@ def test_config3_1m_triclinic_vs_oracle_checksum(mb, stray):
     out2 = (C.c_uint64 * 2)()
     assert s._lib.mb_pairs_checksum(s._h, out2) == 0
     assert (int(out2[0]), int(out2[1])) == (ssum, sxor)
+    # ... and as neighbour rows written by the search kernel itself (full shell, count pass + fill pass): 2 x cnt
+    # entries, and each half of the adjacency (row < column, row > column) hashes to the oracle's pair list
+    assert s._lib.mb_search_connectivity(s._h, C.c_float(1.2), None, n, 7, None) == 2 * cnt
+    assert s.connectivity_checksum() == (ssum, sxor, ssum, sxor)
     s.close()
 
 
