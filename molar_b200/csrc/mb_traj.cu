@@ -348,66 +348,78 @@ __global__ void __launch_bounds__(XTC_SCAN_THREADS) xtc_scan_kernel(const uint8_
     const unsigned long long total_bits = (unsigned long long)F.nbytes * 8ull;
     const unsigned fullbits = (unsigned)(F.bitsize ? F.bitsize : F.bitsizeint[0] + F.bitsizeint[1] + F.bitsizeint[2]);
     unsigned long long bp = 0;
-    int i = 0, run = 0, smallidx = F.smallidx;
+    int i = 0, nsmall = 0, smallidx = F.smallidx;  // nsmall = run / 3: small triples behind the full one of a group
     unsigned ng = 0;
     bool bad = false;
-    // The walk is one dependent chain per frame, so nothing hides memory latency but prefetching: keep the next
-    // 8 KB of the stream on their way into L2 and the next 1 KB into L1.
-    unsigned long long pf = 0;
+    // The walk is one dependent chain per frame — every set flag changes the layout of what follows — so its speed is
+    // the latency of one step.  The step is kept short: the flag AND the run code behind it come from one 16-bit window
+    // (two independent byte loads; the lane that finds its flag set already holds the new run code, which reaches the
+    // others by a shuffle instead of a second dependent load), the divisions are gone (run / 3 as a multiply, the
+    // group count of the tail only computed in the tail), and the prefetch is issued once per 1 KB of stream.
+    unsigned long long pf = 0, pf_blk = ~0ull;
     while (i < F.natoms) {
         if (smallidx < XTC_FIRSTIDX || smallidx >= XTC_LASTIDX) {
             bad = true;
             break;
         }
-        {
-            const unsigned long long cur = bp >> 3;
+        const unsigned long long cur = bp >> 3;
+        if ((cur >> 10) != pf_blk) {
+            pf_blk = cur >> 10;
             while (pf < cur + 8192ull && pf < F.nbytes) {
                 const unsigned long long a = pf + (unsigned long long)lane * 128ull;
                 if (a < F.nbytes) asm volatile("prefetch.global.L2 [%0];" ::"l"(d + a));
                 pf += 4096ull;
             }
             const unsigned long long a1 = cur + 256ull + (unsigned long long)lane * 128ull;
-            if (lane < 8u && a1 < F.nbytes) asm volatile("prefetch.global.L1 [%0];" ::"l"(d + a1));
+            if (lane < 16u && a1 < F.nbytes) asm volatile("prefetch.global.L1 [%0];" ::"l"(d + a1));
         }
-        const int nsmall = run / 3, per = 1 + nsmall;
+        const int per = 1 + nsmall;
         const unsigned len0 = fullbits + 1u + (unsigned)(nsmall * smallidx);  // length of a group whose flag is clear
-        const int left = (F.natoms - i + per - 1) / per;
+        const int remaining = F.natoms - i;
+        const int left = remaining >= 32 * per ? 32 : (remaining + per - 1) / per;
         const unsigned long long p = bp + (unsigned long long)lane * len0, fp = p + fullbits;
         const bool ok = (int)lane < left && fp < total_bits;
-        const unsigned flag = ok ? xtc_bits(d, fp, 1) : 1u;
-        const unsigned clear = __ballot_sync(0xffffffffu, flag == 0u);
+        // bits fp .. fp + 5: flag, then the 5-bit run code (meaningful when the flag is set); the stream is padded,
+        // so the window may be read past its end — whether the code is really there is checked below
+        unsigned six = 0x20u | 0x100u;  // no group here: reads as "flag set, no valid run code"
+        if (ok) {
+            const unsigned long long by = fp >> 3;
+            const unsigned w16 = ((unsigned)d[by] << 8) | (unsigned)d[by + 1];
+            six = (w16 >> (10u - (unsigned)(fp & 7ull))) & 0x3fu;
+            if (fp + 6 > total_bits) six |= 0x100u;
+        }
+        const unsigned clear = __ballot_sync(0xffffffffu, (six & 0x20u) == 0u);
         const int nz = clear == 0xffffffffu ? 32 : __ffs((int)~clear) - 1;
         if ((int)lane < nz) {
             const size_t e = F.group_off + ng + lane;
             g_bit[e] = (unsigned)p;
             g_atom[e] = (unsigned)(i + (int)lane * per);
-            g_meta[e] = (unsigned short)(smallidx | (run << 8));
+            g_meta[e] = (unsigned short)(smallidx | ((3 * nsmall) << 8));
         }
+        const unsigned nxt = __shfl_sync(0xffffffffu, six, nz & 31);
         bp += (unsigned long long)nz * len0;
         i += nz * per;
         ng += (unsigned)nz;
         if (nz < 32 && i < F.natoms) {
             // the next group has its flag set: new run code (and possibly a new small-integer width)
-            const unsigned long long q = bp + fullbits;
-            if (q + 6 > total_bits || xtc_bits(d, q, 1) == 0u) {
+            if (nxt & 0x100u) {
                 bad = true;
                 break;
             }
-            run = (int)xtc_bits(d, q + 1, 5);
-            int is_smaller = run % 3;
-            run -= is_smaller;
-            is_smaller--;
+            const int code = (int)(nxt & 31u);
+            const int ns = (code * 11) >> 5;  // code / 3 for code < 32
+            const int is_smaller = code - 3 * ns - 1;
             if (lane == 0) {
                 const size_t e = F.group_off + ng;
                 g_bit[e] = (unsigned)bp;
                 g_atom[e] = (unsigned)i;
-                g_meta[e] = (unsigned short)(smallidx | (run << 8));
+                g_meta[e] = (unsigned short)(smallidx | ((3 * ns) << 8));
             }
             ++ng;
-            const int ns = run / 3;
             i += 1 + ns;
-            bp = q + 6 + (unsigned long long)ns * (unsigned)smallidx;
+            bp += fullbits + 6ull + (unsigned long long)ns * (unsigned)smallidx;
             smallidx += is_smaller;
+            nsmall = ns;
         }
     }
     if (lane == 0) {
