@@ -831,18 +831,47 @@ __device__ __forceinline__ void emit_group(unsigned e0, unsigned e1, unsigned id
 #define MB_EMIT_Q(J, SH, H)                                                                        \
     MB_EMIT_ONE(J, "%1", "%5", H) SH MB_EMIT_ONE(J, "%2", "%6", H) SH MB_EMIT_ONE(J, "%3", "%7", H) SH \
         MB_EMIT_ONE(J, "%4", "%8", H) SH
+template <int NHOME>  // homes of the group that exist (the last group of a batch may hold fewer than four)
 __device__ __forceinline__ void emit_group4(unsigned e0, unsigned e1, unsigned e2, unsigned e3, unsigned id0, unsigned id1,
                                             unsigned id2, unsigned id3, unsigned& sp, uint4 h) {
-    asm volatile(
-        "{ .reg .pred p; .reg .b32 t;\n"
-        MB_EMIT_Q(1, "  shl.b32 t, t, 3;\n  add.u32 %0, %0, t;\n", "%9")
-        MB_EMIT_Q(2, "  shl.b32 t, t, 2;\n  add.u32 %0, %0, t;\n", "%10")
-        MB_EMIT_Q(4, "  shl.b32 t, t, 1;\n  add.u32 %0, %0, t;\n", "%11")
-        MB_EMIT_Q(8, "  add.u32 %0, %0, t;\n", "%12")
-        "}"
-        : "+r"(sp)
-        : "r"(e0), "r"(e1), "r"(e2), "r"(e3), "r"(id0), "r"(id1), "r"(id2), "r"(id3), "r"(h.x), "r"(h.y), "r"(h.z), "r"(h.w)
-        : "memory");
+    if (NHOME == 4)
+        asm volatile(
+            "{ .reg .pred p; .reg .b32 t;\n"
+            MB_EMIT_Q(1, "  shl.b32 t, t, 3;\n  add.u32 %0, %0, t;\n", "%9")
+            MB_EMIT_Q(2, "  shl.b32 t, t, 2;\n  add.u32 %0, %0, t;\n", "%10")
+            MB_EMIT_Q(4, "  shl.b32 t, t, 1;\n  add.u32 %0, %0, t;\n", "%11")
+            MB_EMIT_Q(8, "  add.u32 %0, %0, t;\n", "%12")
+            "}"
+            : "+r"(sp)
+            : "r"(e0), "r"(e1), "r"(e2), "r"(e3), "r"(id0), "r"(id1), "r"(id2), "r"(id3), "r"(h.x), "r"(h.y), "r"(h.z), "r"(h.w)
+            : "memory");
+    else if (NHOME == 3)
+        asm volatile(
+            "{ .reg .pred p; .reg .b32 t;\n"
+            MB_EMIT_Q(1, "  shl.b32 t, t, 3;\n  add.u32 %0, %0, t;\n", "%9")
+            MB_EMIT_Q(2, "  shl.b32 t, t, 2;\n  add.u32 %0, %0, t;\n", "%10")
+            MB_EMIT_Q(4, "  shl.b32 t, t, 1;\n  add.u32 %0, %0, t;\n", "%11")
+            "}"
+            : "+r"(sp)
+            : "r"(e0), "r"(e1), "r"(e2), "r"(e3), "r"(id0), "r"(id1), "r"(id2), "r"(id3), "r"(h.x), "r"(h.y), "r"(h.z), "r"(h.w)
+            : "memory");
+    else if (NHOME == 2)
+        asm volatile(
+            "{ .reg .pred p; .reg .b32 t;\n"
+            MB_EMIT_Q(1, "  shl.b32 t, t, 3;\n  add.u32 %0, %0, t;\n", "%9")
+            MB_EMIT_Q(2, "  shl.b32 t, t, 2;\n  add.u32 %0, %0, t;\n", "%10")
+            "}"
+            : "+r"(sp)
+            : "r"(e0), "r"(e1), "r"(e2), "r"(e3), "r"(id0), "r"(id1), "r"(id2), "r"(id3), "r"(h.x), "r"(h.y), "r"(h.z), "r"(h.w)
+            : "memory");
+    else
+        asm volatile(
+            "{ .reg .pred p; .reg .b32 t;\n"
+            MB_EMIT_Q(1, "  shl.b32 t, t, 3;\n  add.u32 %0, %0, t;\n", "%9")
+            "}"
+            : "+r"(sp)
+            : "r"(e0), "r"(e1), "r"(e2), "r"(e3), "r"(id0), "r"(id1), "r"(id2), "r"(id3), "r"(h.x), "r"(h.y), "r"(h.z), "r"(h.w)
+            : "memory");
 }
 #undef MB_EMIT_Q
 #undef MB_EMIT_ONE
@@ -1066,21 +1095,26 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32, MB_SEARCH_MIN_CTAS) search_
                                                      nzb = add2(pk2(q2.z, q3.z), zz2);
                             const unsigned long long nrc22 = pk2_once(-rc2, -rc2);
                             float tmin = 3.0e38f;
-                            const int nh4 = (nh + 3) & ~3;
+                            // homes from the top down (each test shifts its sign bit in, so home j ends up at bit j): the
+                            // nh mod 4 homes on top one by one, the rest four per round — no padded slots are tested
+                            auto test_home = [&](int j) {
+                                const float4 h = home[j];
+                                float t0, t1, t2, t3;
+                                upk2(d2f_minus_rc2(nxa, nya, nza, h, nrc22), t0, t1);
+                                upk2(d2f_minus_rc2(nxb, nyb, nzb, h, nrc22), t2, t3);
+                                m0 = __funnelshift_l(__float_as_uint(t0), m0, 1);
+                                m1 = __funnelshift_l(__float_as_uint(t1), m1, 1);
+                                m2 = __funnelshift_l(__float_as_uint(t2), m2, 1);
+                                m3 = __funnelshift_l(__float_as_uint(t3), m3, 1);
+                                tmin = min3abs(min3abs(tmin, t0, t1), t2, t3);
+                            };
+                            int top = nh;
 #pragma unroll 1
-                            for (int gj = nh4 - 4; gj >= 0; gj -= 4) {
+                            for (int r = nh & 3; r > 0; --r) test_home(--top);
+#pragma unroll 1
+                            for (int gj = top - 4; gj >= 0; gj -= 4) {
 #pragma unroll
-                                for (int jj = 3; jj >= 0; --jj) {
-                                    const float4 h = home[gj + jj];
-                                    float t0, t1, t2, t3;
-                                    upk2(d2f_minus_rc2(nxa, nya, nza, h, nrc22), t0, t1);
-                                    upk2(d2f_minus_rc2(nxb, nyb, nzb, h, nrc22), t2, t3);
-                                    m0 = __funnelshift_l(__float_as_uint(t0), m0, 1);
-                                    m1 = __funnelshift_l(__float_as_uint(t1), m1, 1);
-                                    m2 = __funnelshift_l(__float_as_uint(t2), m2, 1);
-                                    m3 = __funnelshift_l(__float_as_uint(t3), m3, 1);
-                                    tmin = min3abs(min3abs(tmin, t0, t1), t2, t3);
-                                }
+                                for (int jj = 3; jj >= 0; --jj) test_home(gj + jj);
                             }
                             fused = !__any_sync(0xffffffffu, tmin <= P.band);
                         }
@@ -1127,7 +1161,7 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32, MB_SEARCH_MIN_CTAS) search_
                             c0 += 64;  // the loop's own increment adds the other half
                             if (MODE == 2) {
                                 count += cnt;
-                                ntests += 4u * (unsigned)((nh + 3) & ~3);
+                                ntests += 4u * (unsigned)nh;
                                 continue;
                             }
                             int inc = cnt;
@@ -1167,16 +1201,29 @@ __global__ void __launch_bounds__(SEARCH_WARPS * 32, MB_SEARCH_MIN_CTAS) search_
                                 unsigned ha = hid_sa + 4u * (unsigned)h0;
                                 const int hend = min(nh, h0 + hstep);
                                 uint4 hqa = lds128u(ha), hqb = lds128u(ha + 16u);
+                                // full groups of four homes, two per round; then the last, partial group (1-3 homes)
+                                const int hfull = h0 + ((hend - h0) & ~3);
+                                bool odd = false;  // is the next group's id quad in hqb?
 #pragma unroll 1
-                                for (int gj = h0; gj < hend; gj += 8) {
-                                    emit_group4(e0, e1, e2, e3, id0, id1, id2, id3, sp, hqa);
+                                for (int gj = h0; gj < hfull; gj += 8) {
+                                    emit_group4<4>(e0, e1, e2, e3, id0, id1, id2, id3, sp, hqa);
                                     hqa = lds128u(ha + 32u);
                                     e0 >>= 4; e1 >>= 4; e2 >>= 4; e3 >>= 4;
-                                    if (gj + 4 >= hend) break;
-                                    emit_group4(e0, e1, e2, e3, id0, id1, id2, id3, sp, hqb);
+                                    if (gj + 4 >= hfull) {
+                                        odd = true;
+                                        break;
+                                    }
+                                    emit_group4<4>(e0, e1, e2, e3, id0, id1, id2, id3, sp, hqb);
                                     hqb = lds128u(ha + 48u);
                                     e0 >>= 4; e1 >>= 4; e2 >>= 4; e3 >>= 4;
                                     ha += 32u;
+                                }
+                                const int hrem = hend - hfull;
+                                if (hrem) {
+                                    const uint4 hq = odd ? hqb : hqa;
+                                    if (hrem == 3) emit_group4<3>(e0, e1, e2, e3, id0, id1, id2, id3, sp, hq);
+                                    else if (hrem == 2) emit_group4<2>(e0, e1, e2, e3, id0, id1, id2, id3, sp, hq);
+                                    else emit_group4<1>(e0, e1, e2, e3, id0, id1, id2, id3, sp, hq);
                                 }
                                 stage_n += need;
                             }
