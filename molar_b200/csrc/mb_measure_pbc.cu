@@ -50,23 +50,40 @@ __global__ void __launch_bounds__(PRED_THREADS) center_pbc_kernel(const __grid_c
     const size_t g0 = pgid(P, 0);
     const float p0x = P.xyz[3 * g0], p0y = P.xyz[3 * g0 + 1], p0z = P.xyz[3 * g0 + 2];
     double v[4] = {0, 0, 0, 0};
-    for (int k = blockIdx.x * PRED_THREADS + threadIdx.x; k < P.n; k += gridDim.x * PRED_THREADS) {
-        const size_t g = pgid(P, k);
-        const double m = P.masses ? (double)P.masses[g] : 1.0;
-        v[0] += m;
-        if (k == 0) continue;
-        const float x = P.xyz[3 * g], y = P.xyz[3 * g + 1], z = P.xyz[3 * g + 2];
-        float ix = x, iy = y, iz = z;
-        if (P.use_box) {
-            float s0, s1, s2;
-            shortest_vector_dev(P.box, xsub(x, p0x), xsub(y, p0y), xsub(z, p0z), P.w, s0, s1, s2);
-            ix = xadd(p0x, s0);
-            iy = xadd(p0y, s1);
-            iz = xadd(p0z, s2);
+    // four atoms per thread and round, all loads first: the kernel is a stream of 16 B per atom and what bounds it is
+    // the number of loads in flight
+    constexpr int U = 4;
+    const int stride = gridDim.x * PRED_THREADS;
+    for (int k0 = blockIdx.x * PRED_THREADS + threadIdx.x; k0 < P.n; k0 += U * stride) {
+        float x[U], y[U], z[U], mf[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int k = k0 + u * stride;
+            const size_t g = pgid(P, k < P.n ? k : k0);
+            x[u] = P.xyz[3 * g];
+            y[u] = P.xyz[3 * g + 1];
+            z[u] = P.xyz[3 * g + 2];
+            mf[u] = P.masses ? P.masses[g] : 1.0f;
         }
-        v[1] += m * ((double)ix - (double)p0x);
-        v[2] += m * ((double)iy - (double)p0y);
-        v[3] += m * ((double)iz - (double)p0z);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int k = k0 + u * stride;
+            if (k >= P.n) continue;
+            const double m = (double)mf[u];
+            v[0] += m;
+            if (k == 0) continue;
+            float ix = x[u], iy = y[u], iz = z[u];
+            if (P.use_box) {
+                float s0, s1, s2;
+                shortest_vector_dev(P.box, xsub(x[u], p0x), xsub(y[u], p0y), xsub(z[u], p0z), P.w, s0, s1, s2);
+                ix = xadd(p0x, s0);
+                iy = xadd(p0y, s1);
+                iz = xadd(p0z, s2);
+            }
+            v[1] += m * ((double)ix - (double)p0x);
+            v[2] += m * ((double)iy - (double)p0y);
+            v[3] += m * ((double)iz - (double)p0z);
+        }
     }
     __shared__ double res[4];
     if (!grid_reduce<4, PRED_THREADS>(v, P.partials, P.ticket, blockIdx.x, gridDim.x, res)) return;
@@ -95,29 +112,43 @@ __global__ void __launch_bounds__(PRED_THREADS) center_pbc_kernel(const __grid_c
 __global__ void __launch_bounds__(PRED_THREADS) tensor_kernel(const __grid_constant__ PbcRedParams P) {
     const float cx = (float)P.c[0], cy = (float)P.c[1], cz = (float)P.c[2];  // the reference's centre is a Pos (f32)
     double v[7] = {0, 0, 0, 0, 0, 0, 0};
-    for (int k = blockIdx.x * PRED_THREADS + threadIdx.x; k < P.n; k += gridDim.x * PRED_THREADS) {
-        const size_t g = pgid(P, k);
-        const double m = P.masses ? (double)P.masses[g] : 1.0;
-        const float x = P.xyz[3 * g], y = P.xyz[3 * g + 1], z = P.xyz[3 * g + 2];
-        double dx, dy, dz;
-        if (P.use_box) {
-            float s0, s1, s2;
-            shortest_vector_dev(P.box, xsub(x, cx), xsub(y, cy), xsub(z, cz), 7u, s0, s1, s2);
-            dx = s0;
-            dy = s1;
-            dz = s2;
-        } else {
-            dx = (double)x - P.c[0];
-            dy = (double)y - P.c[1];
-            dz = (double)z - P.c[2];
+    constexpr int U = 4;  // atoms per thread and round, loads first (see center_pbc_kernel)
+    const int stride = gridDim.x * PRED_THREADS;
+    for (int k0 = blockIdx.x * PRED_THREADS + threadIdx.x; k0 < P.n; k0 += U * stride) {
+        float x[U], y[U], z[U], mf[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int k = k0 + u * stride;
+            const size_t g = pgid(P, k < P.n ? k : k0);
+            x[u] = P.xyz[3 * g];
+            y[u] = P.xyz[3 * g + 1];
+            z[u] = P.xyz[3 * g + 2];
+            mf[u] = P.masses ? P.masses[g] : 1.0f;
         }
-        v[0] += m;
-        v[1] += m * dx * dx;
-        v[2] += m * dy * dy;
-        v[3] += m * dz * dz;
-        v[4] += m * dx * dy;
-        v[5] += m * dx * dz;
-        v[6] += m * dy * dz;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (k0 + u * stride >= P.n) continue;
+            const double m = (double)mf[u];
+            double dx, dy, dz;
+            if (P.use_box) {
+                float s0, s1, s2;
+                shortest_vector_dev(P.box, xsub(x[u], cx), xsub(y[u], cy), xsub(z[u], cz), 7u, s0, s1, s2);
+                dx = s0;
+                dy = s1;
+                dz = s2;
+            } else {
+                dx = (double)x[u] - P.c[0];
+                dy = (double)y[u] - P.c[1];
+                dz = (double)z[u] - P.c[2];
+            }
+            v[0] += m;
+            v[1] += m * dx * dx;
+            v[2] += m * dy * dy;
+            v[3] += m * dz * dz;
+            v[4] += m * dx * dy;
+            v[5] += m * dx * dz;
+            v[6] += m * dy * dz;
+        }
     }
     __shared__ double res[7];
     if (!grid_reduce<7, PRED_THREADS>(v, P.partials, P.ticket, blockIdx.x, gridDim.x, res)) return;
