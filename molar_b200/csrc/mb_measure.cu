@@ -1049,8 +1049,14 @@ struct WsParams {
     unsigned* flag;       // [nf]
     double* fitres;       // [nf][16]
 };
-constexpr int WS_S1 = 6;   // slots of ring 1 (DRAM latency)
-constexpr int WS_S = 4;    // slots of ring 2 (L2 latency)
+#ifndef MB_WS_S1
+#define MB_WS_S1 6
+#endif
+#ifndef MB_WS_S2
+#define MB_WS_S2 4
+#endif
+constexpr int WS_S1 = MB_WS_S1;   // slots of ring 1 (DRAM latency)
+constexpr int WS_S = MB_WS_S2;    // slots of ring 2 (L2 latency + store read-out)
 #ifndef MB_WS_NW
 #define MB_WS_NW 6
 #endif
