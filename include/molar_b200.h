@@ -79,7 +79,17 @@ void   mb_close(MbCtx* ctx);
 /* cudaStream_t the context launches on (as void*), so a host can time it with its own events */
 void*  mb_stream(MbCtx* ctx);
 int    mb_synchronize(MbCtx* ctx);
-/* tuning knob: subdivision of the reference grid used for traversal (0 = automatic) */
+/* Options (results never depend on them; unknown keys fail with MB_ERR_ARG):
+ *   with_dist 0/1        pair searches also compute the distances (default 1)
+ *   subdiv, subdiv_x/y/z, slice_x, atoms_per_cell   traversal grid of the pair kernel (0 = automatic)
+ *   force_brute 0/1      general all-pairs kernel instead of the cell kernel
+ *   exact_pbc 0/1        wrapped cell pairs always through the exact PeriodicBox expression (no shifted-image filter)
+ *   two_set_cells_min    two-set searches use the cell kernel when n1 * n2 exceeds this
+ *   batch_streams        streams the frames of mb_batch_search alternate over (0 = automatic)
+ *   fused_fit            mb_batch_fit: 0 two kernels per frame group (default); 1, 2 TMA-staged single-pass kernels;
+ *                        3 persistent kernel with an L2-served lagging second pass; 4 warp-specialised persistent
+ *                        kernel (TMA rings, mbarrier hand-overs).  fit_lag / fit_teams / fit_group / fit_streams tune them
+ *   profile 0/1          CUDA events around every pair-kernel launch (mb_stat) */
 int    mb_set_option(MbCtx* ctx, const char* key, double value);
 
 /* ---- frame ------------------------------------------------------------------------------- */
