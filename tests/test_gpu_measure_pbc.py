@@ -127,6 +127,32 @@ def test_config5_scale_pbc_reductions_1m(mb):
     s.close()
 
 
+def test_inertia_axes_reference_known_answer(mb, golden_dir):
+    """molar/src/selection.rs:198-213: the reference's `test_inertia` (all atoms of tests/protein.pdb) keeps the three
+    inertia axes it expects as a comment; the CUDA path (moments1_kernel -> tensor_kernel -> host eigenproblem)
+    reproduces them to the precision those numbers carry, and its moments agree with the oracle's f64 build to 1e-9."""
+    import os
+    g = np.load(os.path.join(golden_dir, "protein_inertia.npz"))
+    s = mb.System(g["xyz"], masses=g["masses"], box=g["box"])
+    mom, axes = s().inertia()
+    ref = g["ref_axes"][::-1]  # the comment lists the axes by descending moment
+    for k in range(3):
+        assert min(np.abs(axes[:, k] - ref[k]).max(), np.abs(axes[:, k] + ref[k]).max()) < 1e-5
+    rc, tensor, omom, oaxes, centre = orc.inertia(g["xyz"], g["masses"], box=None, prec="f64")
+    assert np.allclose(mom, omom, rtol=1e-9)
+    s.close()
+
+
+def test_center_pbc_through_the_pymolar_shortest_vector_known_answer(mb):
+    """molar_python/tests/test_2.py:233-245: in the 1 x 2 x 3 box the shortest image of (0.9, 0.5, 0.6) is
+    (-0.1, 0.5, 0.6).  center_of_geometry_pbc of the two atoms {origin, (0.9, 0.5, 0.6)} is the first atom plus half of
+    that vector (measure.rs:142-170), so the reference's own known answer goes through center_pbc_kernel."""
+    xyz = np.array([[0.0, 0.0, 0.0], [0.9, 0.5, 0.6]], np.float32)
+    s = mb.System(xyz, box=np.diag([1.0, 2.0, 3.0]).astype(np.float32))
+    assert np.allclose(s().cog(dims=[True] * 3), [-0.05, 0.25, 0.3], rtol=0, atol=1e-6)
+    s.close()
+
+
 def test_errors(mb):
     xyz, m = _cluster(ORTHO, 100)
     s = mb.System(xyz, masses=m)  # no box

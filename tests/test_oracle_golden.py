@@ -62,6 +62,34 @@ def test_shortest_vector_dims_orthogonal(dims, expect):
     assert np.linalg.norm(r - np.asarray(expect, np.float32)) < 1e-6
 
 
+def test_shortest_vector_pymolar_known_answer():
+    """The reference's Python test suite holds one more known answer (molar_python/tests/test_2.py:233-245): box
+    PeriodicBox([1, 2, 3], [90, 90, 90]) — a diagonal matrix by from_vectors_angles (periodic_box.rs:229-232) — maps
+    (0.9, 0.5, 0.6) onto (-0.1, 0.5, 0.6), abs 1e-6."""
+    r = orc.Box(matrix=np.diag([1.0, 2.0, 3.0])).shortest_vector([0.9, 0.5, 0.6], 7)
+    assert np.allclose(r, [-0.1, 0.5, 0.6], rtol=0, atol=1e-6)
+
+
+def _axes_match(axes_cols, ref_rows_descending, tol):
+    """columns of axes_cols (ascending moments) against the reference's three axes (listed by descending moment);
+    an axis is defined up to its sign"""
+    ref = np.asarray(ref_rows_descending)[::-1]
+    return all(min(np.abs(axes_cols[:, k] - ref[k]).max(), np.abs(axes_cols[:, k] + ref[k]).max()) < tol for k in range(3))
+
+
+def test_inertia_axes_reference_known_answer(golden_dir):
+    """The one known answer the reference holds for the measure path: molar/src/selection.rs:198-213 (`test_inertia`,
+    all 4295 atoms of tests/protein.pdb) keeps the three inertia axes it expects as a comment (:209-211).  The oracle's
+    inertia restatement (masses from the element column, mass-weighted centre, tensor, symmetric eigenproblem,
+    measure.rs:88-98,573-610) reproduces them to the precision those numbers carry (5e-6: they come from an f32
+    build), in every precision mode.  Fixture: tools/make_golden_inertia.py."""
+    g = np.load(os.path.join(golden_dir, "protein_inertia.npz"))
+    for prec in ("f64", "f32", "mixed"):
+        rc, tensor, mom, axes, centre = orc.inertia(g["xyz"], g["masses"], box=None, prec=prec)
+        assert rc == 0 and mom[0] < mom[1] < mom[2]
+        assert _axes_match(axes, g["ref_axes"], 1e-5), prec
+
+
 def test_orthogonal_has_no_tric_corrections():  # :546-551
     assert len(orc.Box(matrix=np.diag([10.0, 20.0, 30.0])).corrections) == 0
 
