@@ -197,6 +197,22 @@ int Ctx::harvest_profile() {
     return MB_OK;
 }
 
+int Ctx::host_results() {
+    if (h_res) return MB_OK;
+    void* hp = nullptr;
+    cudaError_t e = cudaHostAlloc(&hp, 64 * sizeof(double), cudaHostAllocMapped);
+    if (e != cudaSuccess) return fail(MB_ERR_CUDA, "cudaHostAlloc(mapped results) failed: %s", cudaGetErrorString(e));
+    void* dp = nullptr;
+    e = cudaHostGetDevicePointer(&dp, hp, 0);
+    if (e != cudaSuccess) {
+        cudaFreeHost(hp);
+        return fail(MB_ERR_CUDA, "cudaHostGetDevicePointer failed: %s", cudaGetErrorString(e));
+    }
+    h_res = static_cast<double*>(hp);
+    d_res = static_cast<double*>(dp);
+    return MB_OK;
+}
+
 int Ctx::pinned_reserve(size_t bytes) {
     if (bytes <= h_pinned_cap) return MB_OK;
     if (h_pinned) cudaFreeHost(h_pinned);
@@ -295,6 +311,7 @@ void mb_close(MbCtx* h) {
         if (e) cudaEventDestroy(e);
     if (c.copy_stream) cudaStreamDestroy(c.copy_stream);
     if (c.h_pinned) cudaFreeHost(c.h_pinned);
+    if (c.h_res) cudaFreeHost(c.h_res);
     for (int i = 0; i < 4; ++i)
         if (c.aux_stream[i]) cudaStreamDestroy(c.aux_stream[i]);
     if (c.aux_event) cudaEventDestroy(c.aux_event);

@@ -120,6 +120,11 @@ struct Ctx {
     void* h_pinned = nullptr;
     size_t h_pinned_cap = 0;
     int pinned_reserve(size_t bytes);
+    // Small results (a centre, a tensor, a transform) are written by the finishing thread of a reduction kernel straight
+    // into mapped page-locked host memory: the call ends with the stream synchronisation, without a D2H copy behind it.
+    double* h_res = nullptr;  // host view (64 doubles)
+    double* d_res = nullptr;  // device view of the same memory
+    int host_results();
 
     // search scratch
     DevBuf tmp4a, tmp4b;    // binned atoms (float4: eff pos + id bits), unsorted

@@ -1453,12 +1453,13 @@ static int com_gyr(Ctx* c, const uint64_t* ids, size_t n, double out8[8]) {
     int nb = red_blocks(c, n, 8);
     RedScratch s;
     MB_TRY(red_scratch(c, 1, (size_t)nb * 5, 8, &s));
+    MB_TRY(c->host_results());  // the finishing thread writes the row into mapped host memory: no D2H copy
     moments1_kernel<<<dim3(nb, 1), RED_THREADS, 0, c->stream>>>(c->d_xyz, 0, d_ids, (int)n, c->masses.as<float>(),
-                                                               s.partials, s.tickets, s.results);
+                                                               s.partials, s.tickets, c->d_res);
     c->launches++;
     MB_CUDA(cudaGetLastError());
-    MB_CUDA(cudaMemcpyAsync(out8, s.results, 8 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     MB_CUDA(cudaStreamSynchronize(c->stream));
+    for (int k = 0; k < 8; ++k) out8[k] = c->h_res[k];
     if (out8[5] != 0.0) return fail(MB_ERR_ZERO_MASS, "zero mass");
     return MB_OK;
 }
@@ -1831,14 +1832,14 @@ int mb_rmsd(MbCtx* h, const uint64_t* ids1, size_t n1, const uint64_t* ids2, siz
     int nb = red_blocks(c, n1, 4);
     RedScratch s;
     MB_TRY(red_scratch(c, 1, (size_t)nb * 2, 8, &s));
+    MB_TRY(c->host_results());
     rmsd_kernel<<<nb, RED_THREADS, 0, c->stream>>>(SelView{c->d_xyz, d1, (int)n1}, SelView{xyz2, d2, (int)n2},
                                                   mass_weighted ? c->masses.as<float>() : nullptr, s.partials,
-                                                  s.tickets, s.results);
+                                                  s.tickets, c->d_res);
     c->launches++;
     MB_CUDA(cudaGetLastError());
-    double r[2];
-    MB_CUDA(cudaMemcpyAsync(r, s.results, sizeof(r), cudaMemcpyDeviceToHost, c->stream));
     MB_CUDA(cudaStreamSynchronize(c->stream));
+    const double r[2] = {c->h_res[0], c->h_res[1]};
     if (mass_weighted) {
         if (r[1] == 0.0) return fail(MB_ERR_ZERO_MASS, "zero mass");
         *out = std::sqrt(r[0] / r[1]);
@@ -1869,14 +1870,15 @@ int mb_fit_transform(MbCtx* h, const uint64_t* ids1, size_t n1, const uint64_t* 
     int nb = red_blocks(c, n1, 4);
     RedScratch s;
     MB_TRY(red_scratch(c, 1, (size_t)nb * 20, 16, &s));
+    MB_TRY(c->host_results());
     fit_moments_kernel<true><<<dim3(nb, 1), RED_THREADS, 0, c->stream>>>(c->d_xyz, 0, d1, xyz2, d2, (int)n1,
                                                                         c->masses.as<float>(), at_origin, s.partials,
-                                                                        s.tickets, s.results);
+                                                                        s.tickets, c->d_res);
     c->launches++;
     MB_CUDA(cudaGetLastError());
-    double r[16];
-    MB_CUDA(cudaMemcpyAsync(r, s.results, sizeof(r), cudaMemcpyDeviceToHost, c->stream));
     MB_CUDA(cudaStreamSynchronize(c->stream));
+    double r[13];
+    for (int k = 0; k < 13; ++k) r[k] = c->h_res[k];
     if (r[12] == 1.0) return fail(MB_ERR_ZERO_MASS, "zero mass");
     if (r[12] == 3.0) return fail(MB_ERR_SVD, "SVD failed");
     for (int col = 0; col < 3; ++col)

@@ -166,7 +166,8 @@ static int pbc_scratch(Ctx* c, int nb, int K, PbcRedParams& P) {
     if (fresh) MB_CUDA(cudaMemsetAsync(c->pbc_tmp.p, 0, P_TICKET_BYTES, c->stream));
     char* base = static_cast<char*>(c->pbc_tmp.p);
     P.ticket = reinterpret_cast<unsigned*>(base);
-    P.results = reinterpret_cast<double*>(base + P_TICKET_BYTES);
+    MB_TRY(c->host_results());
+    P.results = c->d_res;  // mapped host memory: the finishing thread's stores ARE the transfer
     P.partials = reinterpret_cast<double*>(base + P_TICKET_BYTES + 256);
     return MB_OK;
 }
@@ -203,8 +204,8 @@ static int run_center(Ctx* c, PbcRedParams& P, int nb, int use_box, unsigned w, 
     center_pbc_kernel<<<nb, PRED_THREADS, 0, c->stream>>>(P);
     c->launches++;
     MB_CUDA(cudaGetLastError());
-    MB_CUDA(cudaMemcpyAsync(out5, P.results, 5 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     MB_CUDA(cudaStreamSynchronize(c->stream));
+    for (int k = 0; k < 5; ++k) out5[k] = c->h_res[k];
     if (out5[4] != 0.0) return fail(MB_ERR_ZERO_MASS, "zero mass");
     return MB_OK;
 }
@@ -216,8 +217,8 @@ static int run_tensor(Ctx* c, PbcRedParams& P, int nb, int use_box, const double
     tensor_kernel<<<nb, PRED_THREADS, 0, c->stream>>>(P);
     c->launches++;
     MB_CUDA(cudaGetLastError());
-    MB_CUDA(cudaMemcpyAsync(out7, P.results, 7 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     MB_CUDA(cudaStreamSynchronize(c->stream));
+    for (int k = 0; k < 7; ++k) out7[k] = c->h_res[k];
     return MB_OK;
 }
 
