@@ -16,6 +16,9 @@
 //   cell_start[nc+1]  u32     exclusive scan of fine-cell populations
 //   pairs  [P]        uint2   canonical (i<j) global ids, bump-allocated in 8-KB warp flushes
 //   dists  [P]        f32     sqrt(d2) (optional)
+//   neighbour-list modes (SearchConnectivity, connectivity.rs:8-38, without a pair list in between):
+//   deg / row_ptr [N+1] u32   neighbours per atom (kernel mode 4, full shell) and their exclusive scan
+//   cols   [2P]       u32     every atom's row, written at its own cursor (kernel mode 5)
 // The fine grid is the reference grid subdivided k[d] times per dimension in FRACTIONAL space, so a
 // fine cell lies inside exactly one reference cell and the (adjacent?, wrapped dims) decision is
 // uniform per (home fine cell, neighbour run) — nothing but the distance test is left per pair.
