@@ -265,6 +265,12 @@ const void* mb_batch_scalars_device(MbCtx* ctx, size_t* n_rows, size_t* row_doub
    out_band: [rc2_lo, rc2_hi] of the filter.  For tests of the planning logic. */
 int mb_plan_describe(const float* box9_colmajor, float cutoff, uint8_t pbc_dims, size_t n, int full_shell,
                      int out_int[16], signed char* rows4_out, float out_band[2]);
+/* Host only, no device needed: the periodic-box tables of the kernels — the reference's triclinic corrections
+   (periodic_box.rs:25-66; ncorr vectors, 3 floats each) and the 13 (+v, -v) pair table (threshold per pair, bit
+   1 << index-in-the-list per member, 0 when the reference's list does not hold it) the minimum-image code prunes them
+   with.  For tests of the table logic. */
+int mb_box_describe(const float* box9_colmajor, int* ncorr_out, float corr78_out[78], float pair_thr13_out[13],
+                    uint32_t pair_bit26_out[26]);
 /* ---- multi-GPU: frames shard across ranks, the per-frame scalars are gathered over NCCL ------------------------
  * The per-frame loop (analysis_task.rs:113-280) is embarrassingly parallel over frames: rank r (one GPU, one context)
  * processes its block of frames with the mb_batch_* / mb_stream_* calls and nothing is exchanged until the end of a

@@ -71,6 +71,7 @@ SIGNATURES = {
     "mb_batch_fit": (C.c_int, [C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, f64p]),
     "mb_batch_pipeline": (C.c_int, [C.c_void_p, C.c_float, C.c_uint8, C.c_size_t, C.c_size_t, f64p]),
     "mb_batch_scalars_device": (C.c_void_p, [C.c_void_p, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
+    "mb_box_describe": (C.c_int, [f32p, C.POINTER(C.c_int), f32p, f32p, C.POINTER(C.c_uint32)]),
     "mb_plan_describe": (C.c_int, [f32p, C.c_float, C.c_uint8, C.c_size_t, C.c_int, C.POINTER(C.c_int), C.c_void_p, f32p]),
     "mb_comm_unique_id": (C.c_int, [C.c_void_p]),
     "mb_comm_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),

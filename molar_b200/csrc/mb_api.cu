@@ -356,6 +356,22 @@ int mb_set_option(MbCtx* h, const char* key, double value) {
     return MB_OK;
 }
 
+// Host only (no device needed): the periodic-box tables the kernels use — the reference's triclinic corrections
+// (build_tric_corrections, periodic_box.rs:25-66) and the 13 (+v, -v) pair table with its thresholds that
+// shortest_vector_dev prunes them with.  Exists so that the table logic can be tested on the CPU.
+int mb_box_describe(const float* box9_colmajor, int* ncorr_out, float corr78_out[78], float pair_thr13_out[13],
+                    uint32_t pair_bit26_out[26]) {
+    if (!box9_colmajor || !ncorr_out) return fail(MB_ERR_ARG, "null argument");
+    HostBox hb;
+    MB_TRY(host_box_from_colmajor(box9_colmajor, &hb));
+    const DevBox d = to_dev_box(hb);
+    *ncorr_out = d.ncorr;
+    if (corr78_out) memcpy(corr78_out, d.corr, sizeof(d.corr));
+    if (pair_thr13_out) memcpy(pair_thr13_out, d.pair_thr, sizeof(d.pair_thr));
+    if (pair_bit26_out) memcpy(pair_bit26_out, d.pair_bit, sizeof(d.pair_bit));
+    return MB_OK;
+}
+
 static int set_box(Ctx& c, const float* box9) {
     if (box9) {
         MB_TRY(host_box_from_colmajor(box9, &c.box));
